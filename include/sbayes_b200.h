@@ -1,0 +1,129 @@
+/* sbayes_b200.h -- C ABI of the B200 backend for the sBayes MCMC inner loop.
+ *
+ * One `sb_ctx` owns one GPU: the packed problem (shared by all chains), the per-chain
+ * state buffers in HBM, one CUDA stream and the persistent step kernel.  Every entry
+ * point returns 0 on success and a negative code on failure (`sb_last_error` gives the
+ * text); nothing throws across the boundary.  The caller owns all host buffers; the ctx
+ * owns all device memory.  One host thread per ctx.
+ *
+ * Which reference interface each entry point stands in for (paths are into the sBayes
+ * reference tree, v1.1):
+ *
+ *   sb_create            Data + Model construction as seen by the chain
+ *                        (sbayes/load_data.py:85-256, sbayes/model/model.py:24-45,
+ *                         sbayes/model/prior.py:155-255,325-354,438-455,704-853)
+ *   sb_chain_config      MCMCChain.__init__ (sbayes/sampling/mcmc_chain.py:30-72) and
+ *                        get_operator_schedule (sbayes/sampling/operators.py:28-209)
+ *   sb_set_state         Sample.from_numpy_arrays + recalculate_feature_counts
+ *                        (sbayes/sampling/state.py:492-552, sbayes/sampling/counts.py:35-52)
+ *   sb_get_state         reading Sample.clusters/weights/source/feature_counts
+ *                        (sbayes/sampling/loggers.py:157-301,426-442)
+ *   sb_eval              Model.likelihood(sample, caching=False) + Model.prior(sample,
+ *                        caching=False) (sbayes/model/model.py:47-51,
+ *                        sbayes/model/likelihood.py:47-101, sbayes/model/prior.py:74-88)
+ *   sb_run               MCMCChain.run / MCMCChain.step for every chain of the ctx
+ *                        (sbayes/sampling/mcmc_chain.py:128-255) including the ten scheduled
+ *                        operators (sbayes/sampling/operators.py:423-1827)
+ *   sb_posterior         MCMCChain._ll / _prior and Sample.last_lh / last_prior
+ *                        (sbayes/sampling/mcmc_chain.py:87,108)
+ *   sb_op_stats          Operator.accepts / rejects (sbayes/sampling/operators.py:278-293)
+ *   sb_swap              swap_chains (sbayes/mcmc_setup.py:365-418)
+ *   sb_counts_rebuild_mma  recalculate_feature_counts as an int8 tensor-core contraction
+ *                        (sbayes/sampling/counts.py:10-52)
+ */
+#ifndef SBAYES_B200_H
+#define SBAYES_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_N_OPS 10      /* scheduled operators, order of sbayes/sampling/operators.py:50-205 */
+#define SB_N_SITES 14    /* random-draw sites of one step (see sb_tape) */
+#define SB_MAX_COMPONENTS 8
+#define SB_NA 255
+
+typedef struct sb_ctx sb_ctx;
+
+/* Packed problem.  All pointers are host memory and are copied by sb_create. */
+typedef struct sb_problem_desc {
+    int32_t n_objects, n_features, n_states, n_clusters, n_confounders;
+    const uint8_t *x;             /* [N, F]   state index, 255 = missing            */
+    const uint8_t *applicable;    /* [F, S]   1 where the state exists for f        */
+    const int32_t *conf_gid;      /* [n_conf, N] group of each object, -1 = none    */
+    const int32_t *conf_ngroups;  /* [n_conf]                                        */
+    const double *alpha;          /* [G_tot, F, S] Dirichlet concentration, rows =   *
+                                   *   K cluster rows, then every confounder's groups */
+    const double *alpha_w;        /* [F, C] weights-prior concentration              */
+    int32_t min_size, max_size;
+    int32_t size_prior;           /* 0 uniform_area, 1 uniform_size, 2 quadratic     */
+    int32_t weights_prior_uniform;
+    int32_t geo_enabled;          /* cost_based geo prior with MST skeleton          */
+    int32_t geo_aggregation;      /* 0 mean, 1 sum, 2 max                            */
+    int32_t geo_prob_fn;          /* 0 exponential, 1 sigmoid                        */
+    double geo_rate, geo_inflection;
+    const double *geo_cost;       /* [N, N] or NULL                                  */
+    const int32_t *adj_indptr;    /* [N+1] CSR adjacency (may be NULL: no neighbours)*/
+    const int32_t *adj_indices;
+} sb_problem_desc;
+
+/* Per-chain run parameters. */
+typedef struct sb_chain_cfg {
+    double temperature, prior_temperature;
+    int32_t sample_from_prior;
+    int32_t reserved;
+    double op_weights[SB_N_OPS];  /* normalised operator probabilities               */
+    double p_grow;
+    uint64_t seed;                /* Philox key of the chain                         */
+} sb_chain_cfg;
+
+/* Draw tape for replay mode: the draws of every step recorded from the reference
+ * (layout of oracle/fixtures.py:flatten_tapes).  NULL tape = Philox streams. */
+typedef struct sb_tape {
+    const double *vals;           /* [total]                                         */
+    const int32_t *off;           /* [n_steps, SB_N_SITES] offset into vals, -1 = absent */
+    const int32_t *len;           /* [n_steps, SB_N_SITES]                           */
+    const int32_t *wide_rows;     /* [n_steps] n_avail of the wide operator's step   */
+    int64_t n_vals;
+} sb_tape;
+
+/* One record per chain and step (optional output of sb_run). */
+typedef struct sb_step_record {
+    int32_t op, accept, changed, n_changed;
+    double log_q, log_q_back, ll_new, prior_new, mh_ratio, log_u;
+} sb_step_record;
+
+/* posterior terms of a chain, un-tempered */
+typedef struct sb_posterior {
+    double ll, prior, size_prior, geo_prior, weights_prior, source_prior;
+} sb_posterior_t;
+
+int sb_create(const sb_problem_desc *desc, int device, int n_chains, int team_ctas, sb_ctx **out);
+void sb_destroy(sb_ctx *ctx);
+const char *sb_last_error(const sb_ctx *ctx);       /* ctx may be NULL: error of the last failed sb_create */
+
+int sb_chain_config(sb_ctx *ctx, int chain, const sb_chain_cfg *cfg);
+int sb_set_state(sb_ctx *ctx, int chain, const int32_t *cluster_of, const float *W, const uint8_t *src,
+                 int64_t i_step);
+int sb_get_state(sb_ctx *ctx, int chain, int32_t *cluster_of, float *W, uint8_t *src, int32_t *counts);
+int sb_eval(sb_ctx *ctx, int chain, sb_posterior_t *out);          /* full uncached evaluation */
+int sb_posterior(sb_ctx *ctx, int chain, sb_posterior_t *out);     /* cached values of the current state */
+int sb_run(sb_ctx *ctx, int64_t n_steps, const sb_tape *tape, sb_step_record *records);
+int sb_run_async(sb_ctx *ctx, int64_t n_steps);                     /* enqueue only; sb_sync waits */
+int sb_sync(sb_ctx *ctx);
+int sb_op_stats(sb_ctx *ctx, int chain, int64_t *accepts, int64_t *rejects);
+int sb_swap(sb_ctx *ctx, int attempts, int only_neighbours, uint64_t seed, int64_t round,
+            int32_t *state_of_slot, int32_t *n_accepted);
+int sb_get_slots(sb_ctx *ctx, int32_t *state_of_slot);
+int sb_set_slots(sb_ctx *ctx, const int32_t *state_of_slot);
+int sb_counts_rebuild_mma(sb_ctx *ctx, int chain, int32_t *counts_out, float *ms);
+int sb_counts_rebuild_hist(sb_ctx *ctx, int chain, int32_t *counts_out, float *ms);
+int sb_info(const sb_ctx *ctx, int32_t *out8);     /* {device, n_chains, team, grid, block, smem, n_sm, launches} */
+uint64_t sb_stream(const sb_ctx *ctx);              /* cudaStream_t of the ctx (for event timing) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,254 @@
+"""ctypes binding of the C ABI in include/sbayes_b200.h (libsbayes_b200.so, sm_100a CUDA).
+
+There is no CPU fallback: `load()` raises if the CUDA library has not been built and
+`DeviceContext` raises if the library cannot create a context on a B200.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .packed import Problem, ChainState, ChainConfig, NA, N_OPS
+
+N_SITES = 14
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libsbayes_b200.so")
+
+
+class SbError(RuntimeError):
+    pass
+
+
+class _ProblemDesc(C.Structure):
+    _fields_ = [
+        ("n_objects", C.c_int32), ("n_features", C.c_int32), ("n_states", C.c_int32), ("n_clusters", C.c_int32),
+        ("n_confounders", C.c_int32),
+        ("x", C.c_void_p), ("applicable", C.c_void_p), ("conf_gid", C.c_void_p), ("conf_ngroups", C.c_void_p),
+        ("alpha", C.c_void_p), ("alpha_w", C.c_void_p),
+        ("min_size", C.c_int32), ("max_size", C.c_int32), ("size_prior", C.c_int32), ("weights_prior_uniform", C.c_int32),
+        ("geo_enabled", C.c_int32), ("geo_aggregation", C.c_int32), ("geo_prob_fn", C.c_int32),
+        ("geo_rate", C.c_double), ("geo_inflection", C.c_double),
+        ("geo_cost", C.c_void_p), ("adj_indptr", C.c_void_p), ("adj_indices", C.c_void_p),
+    ]
+
+
+class _ChainCfg(C.Structure):
+    _fields_ = [
+        ("temperature", C.c_double), ("prior_temperature", C.c_double), ("sample_from_prior", C.c_int32),
+        ("reserved", C.c_int32), ("op_weights", C.c_double * N_OPS), ("p_grow", C.c_double), ("seed", C.c_uint64),
+    ]
+
+
+class _Tape(C.Structure):
+    _fields_ = [("vals", C.c_void_p), ("off", C.c_void_p), ("len", C.c_void_p), ("wide_rows", C.c_void_p),
+                ("n_vals", C.c_int64)]
+
+
+class _Posterior(C.Structure):
+    _fields_ = [("ll", C.c_double), ("prior", C.c_double), ("size_prior", C.c_double), ("geo_prior", C.c_double),
+                ("weights_prior", C.c_double), ("source_prior", C.c_double)]
+
+
+RECORD_DTYPE = np.dtype([("op", "<i4"), ("accept", "<i4"), ("changed", "<i4"), ("n_changed", "<i4"),
+                         ("log_q", "<f8"), ("log_q_back", "<f8"), ("ll_new", "<f8"), ("prior_new", "<f8"),
+                         ("mh_ratio", "<f8"), ("log_u", "<f8")])
+
+EXPORTS = ["sb_create", "sb_destroy", "sb_last_error", "sb_chain_config", "sb_set_state", "sb_get_state", "sb_eval",
+           "sb_posterior", "sb_run", "sb_run_async", "sb_sync", "sb_op_stats", "sb_swap", "sb_get_slots",
+           "sb_set_slots", "sb_counts_rebuild_mma", "sb_counts_rebuild_hist", "sb_info", "sb_stream"]
+
+
+def _bind(lib):
+    vp, i32, i64, u64 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64
+    lib.sb_create.argtypes = [C.POINTER(_ProblemDesc), i32, i32, i32, C.POINTER(vp)]
+    lib.sb_destroy.argtypes = [vp]
+    lib.sb_destroy.restype = None
+    lib.sb_last_error.argtypes = [vp]
+    lib.sb_last_error.restype = C.c_char_p
+    lib.sb_chain_config.argtypes = [vp, i32, C.POINTER(_ChainCfg)]
+    lib.sb_set_state.argtypes = [vp, i32, vp, vp, vp, i64]
+    lib.sb_get_state.argtypes = [vp, i32, vp, vp, vp, vp]
+    lib.sb_eval.argtypes = [vp, i32, C.POINTER(_Posterior)]
+    lib.sb_posterior.argtypes = [vp, i32, C.POINTER(_Posterior)]
+    lib.sb_run.argtypes = [vp, i64, C.POINTER(_Tape), vp]
+    lib.sb_run_async.argtypes = [vp, i64]
+    lib.sb_sync.argtypes = [vp]
+    lib.sb_op_stats.argtypes = [vp, i32, vp, vp]
+    lib.sb_swap.argtypes = [vp, i32, i32, u64, i64, vp, vp]
+    lib.sb_get_slots.argtypes = [vp, vp]
+    lib.sb_set_slots.argtypes = [vp, vp]
+    lib.sb_counts_rebuild_mma.argtypes = [vp, i32, vp, vp]
+    lib.sb_counts_rebuild_hist.argtypes = [vp, i32, vp, vp]
+    lib.sb_info.argtypes = [vp, vp]
+    lib.sb_stream.argtypes = [vp]
+    lib.sb_stream.restype = u64
+    return lib
+
+
+_lib = None
+
+
+def load():
+    """Open libsbayes_b200.so (built by `__graft_entry__.build()`); no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SbError(f"{LIB_PATH} is missing: build the CUDA library first (python -c 'import __graft_entry__ as g; "
+                          f"g.build()'); sbayes_b200 has no CPU fallback")
+        _lib = _bind(C.CDLL(LIB_PATH))
+    return _lib
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class DeviceContext:
+    """One GPU: the packed problem plus `n_chains` chain states resident in HBM.
+
+    Mirrors what a reference chain sees of `Data` and `Model`
+    (sbayes/load_data.py:187-256, sbayes/model/model.py:24-45)."""
+
+    def __init__(self, prob: Problem, n_chains: int = 1, device: int = 0, team: int = 0, _lib=None):
+        self.lib = _lib if _lib is not None else load()
+        self.prob = prob
+        self.n_chains = n_chains
+        self._keep = []
+
+        def keep(a, dt):
+            a = np.ascontiguousarray(a, dtype=dt)
+            self._keep.append(a)
+            return a
+
+        d = _ProblemDesc()
+        d.n_objects, d.n_features, d.n_states, d.n_clusters = prob.N, prob.F, prob.S, prob.K
+        d.n_confounders = len(prob.conf_gid)
+        d.x = _ptr(keep(prob.x, np.uint8))
+        d.applicable = _ptr(keep(prob.applicable, np.uint8))
+        gid = np.stack(prob.conf_gid) if prob.conf_gid else np.zeros((0, prob.N), np.int32)
+        d.conf_gid = _ptr(keep(gid, np.int32))
+        d.conf_ngroups = _ptr(keep(np.array(prob.conf_ngroups, np.int32), np.int32))
+        d.alpha = _ptr(keep(prob.alpha_stacked(), np.float64))
+        d.alpha_w = _ptr(keep(prob.alpha_w, np.float64))
+        d.min_size, d.max_size, d.size_prior = prob.min_size, prob.max_size, prob.size_prior
+        d.weights_prior_uniform = int(prob.weights_prior_uniform)
+        if prob.geo is not None:
+            d.geo_enabled, d.geo_aggregation, d.geo_prob_fn = 1, prob.geo.aggregation, prob.geo.prob_fn
+            d.geo_rate, d.geo_inflection = prob.geo.rate, prob.geo.inflection
+            d.geo_cost = _ptr(keep(prob.geo.cost, np.float64))
+        if prob.adj_indptr is not None:
+            d.adj_indptr = _ptr(keep(prob.adj_indptr, np.int32))
+            d.adj_indices = _ptr(keep(prob.adj_indices if len(prob.adj_indices) else np.zeros(1, np.int32), np.int32))
+        h = C.c_void_p()
+        rc = self.lib.sb_create(C.byref(d), device, n_chains, team, C.byref(h))
+        if rc != 0:
+            raise SbError(f"sb_create failed ({rc}): {self.lib.sb_last_error(None).decode()}")
+        self.h = h
+        self._keep.clear()
+
+    # ------------------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc != 0:
+            raise SbError(f"sbayes_b200 error {rc}: {self.lib.sb_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self) -> dict:
+        out = np.zeros(8, np.int32)
+        self._ck(self.lib.sb_info(self.h, _ptr(out)))
+        return dict(zip(["device", "n_chains", "team", "grid", "block", "smem", "n_sm", "launches"], out.tolist()))
+
+    def stream(self) -> int:
+        return int(self.lib.sb_stream(self.h))
+
+    def configure(self, chain: int, cfg: ChainConfig):
+        c = _ChainCfg()
+        c.temperature, c.prior_temperature = cfg.temperature, cfg.prior_temperature
+        c.sample_from_prior = int(cfg.sample_from_prior)
+        w = cfg.op_weight_vector(self.prob.K)
+        for i in range(N_OPS):
+            c.op_weights[i] = float(w[i])
+        c.p_grow, c.seed = cfg.p_grow, int(cfg.seed)
+        self._ck(self.lib.sb_chain_config(self.h, chain, C.byref(c)))
+
+    def set_state(self, chain: int, st: ChainState, i_step: int = 0):
+        co = np.ascontiguousarray(st.cluster_of, np.int32)
+        W = np.ascontiguousarray(st.W, np.float32)
+        src = np.ascontiguousarray(st.src, np.uint8)
+        assert co.shape == (self.prob.N,) and W.shape == (self.prob.F, self.prob.C) and src.shape == (self.prob.N, self.prob.F)
+        self._ck(self.lib.sb_set_state(self.h, chain, _ptr(co), _ptr(W), _ptr(src), int(i_step)))
+
+    def get_state(self, chain: int) -> ChainState:
+        p = self.prob
+        co, W = np.empty(p.N, np.int32), np.empty((p.F, p.C), np.float32)
+        src, counts = np.empty((p.N, p.F), np.uint8), np.empty((p.G_tot, p.F, p.S), np.int32)
+        self._ck(self.lib.sb_get_state(self.h, chain, _ptr(co), _ptr(W), _ptr(src), _ptr(counts)))
+        return ChainState(co, W, src, counts)
+
+    def eval(self, chain: int) -> dict:
+        """Full uncached evaluation (count rebuild + likelihood + all prior terms)."""
+        out = _Posterior()
+        self._ck(self.lib.sb_eval(self.h, chain, C.byref(out)))
+        return {k: getattr(out, k) for k, _ in _Posterior._fields_}
+
+    def posterior(self, chain: int) -> dict:
+        out = _Posterior()
+        self._ck(self.lib.sb_posterior(self.h, chain, C.byref(out)))
+        return {k: getattr(out, k) for k, _ in _Posterior._fields_}
+
+    def run(self, n_steps: int, tape: Optional[dict] = None, records: bool = False):
+        """Advance every chain by n_steps.  `tape` = dict(vals, off, len, wide_rows) replays
+        recorded draws (single chain); records=True returns one record per chain and step."""
+        t = None
+        keep = []
+        if tape is not None:
+            t = _Tape()
+            vals = np.ascontiguousarray(tape["vals"], np.float64)
+            off = np.ascontiguousarray(tape["off"][:n_steps], np.int32)
+            ln = np.ascontiguousarray(tape["len"][:n_steps], np.int32)
+            wr = np.ascontiguousarray(tape["wide_rows"][:n_steps], np.int32)
+            keep += [vals, off, ln, wr]
+            t.vals, t.off, t.len, t.wide_rows, t.n_vals = _ptr(vals), _ptr(off), _ptr(ln), _ptr(wr), vals.size
+        rec = np.zeros((self.n_chains, n_steps), RECORD_DTYPE) if records else None
+        self._ck(self.lib.sb_run(self.h, int(n_steps), C.byref(t) if t is not None else None, _ptr(rec)))
+        return rec
+
+    def run_async(self, n_steps: int):
+        self._ck(self.lib.sb_run_async(self.h, int(n_steps)))
+
+    def sync(self):
+        self._ck(self.lib.sb_sync(self.h))
+
+    def op_stats(self, chain: int):
+        a, r = np.zeros(N_OPS, np.int64), np.zeros(N_OPS, np.int64)
+        self._ck(self.lib.sb_op_stats(self.h, chain, _ptr(a), _ptr(r)))
+        return a, r
+
+    def swap(self, attempts: int, only_neighbours: bool, seed: int, round_: int):
+        sos, n = np.zeros(self.n_chains, np.int32), np.zeros(1, np.int32)
+        self._ck(self.lib.sb_swap(self.h, int(attempts), int(only_neighbours), int(seed), int(round_), _ptr(sos), _ptr(n)))
+        return sos, int(n[0])
+
+    def slots(self) -> np.ndarray:
+        s = np.zeros(self.n_chains, np.int32)
+        self._ck(self.lib.sb_get_slots(self.h, _ptr(s)))
+        return s
+
+    def counts_rebuild(self, chain: int, mma: bool = False):
+        p = self.prob
+        counts, ms = np.empty((p.G_tot, p.F, p.S), np.int32), np.zeros(1, np.float32)
+        fn = self.lib.sb_counts_rebuild_mma if mma else self.lib.sb_counts_rebuild_hist
+        self._ck(fn(self.h, chain, _ptr(counts), _ptr(ms)))
+        return counts, float(ms[0])

@@ -1,0 +1,523 @@
+// sb_api.cu -- C ABI of the B200 backend (include/sbayes_b200.h): problem upload, chain
+// state in HBM, launches of the persistent step kernel, MC3 swap.
+//
+// Product build: nvcc -gencode arch=compute_100a,code=sm_100a.  With -DSB_HOSTSIM (tests
+// only) the device memory is host memory and launches go to the fibre emulator.
+#include <string>
+#include <vector>
+#include <cstring>
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <algorithm>
+#include <map>
+
+#include "sb_core.cuh"
+#include "sb_counts.cuh"
+
+#ifdef SB_HOSTSIM
+#define SB_API extern "C" __attribute__((visibility("default")))
+typedef void *sb_stream_t;
+#else
+#define SB_API extern "C" __attribute__((visibility("default")))
+typedef cudaStream_t sb_stream_t;
+#endif
+
+static std::string g_create_error;
+
+struct sb_ctx {
+    int device = 0, n_chains = 0, team = 1, n_teams = 1, grid = 1, block = 256, n_sm = 1, smem_members = 0;
+    size_t smem = 0;
+    long long launches = 0;
+    SbProblem P;
+    std::vector<SbState> h_states;
+    SbState *d_states = nullptr;
+    SbSlot *d_slots = nullptr;
+    unsigned long long *d_bars = nullptr;
+    double *d_tred = nullptr;
+    uint8_t *d_src_tmp = nullptr;
+    int32_t *d_counts_tmp = nullptr;
+    std::vector<void *> allocs;
+    sb_stream_t stream = 0;
+    std::string err;
+};
+
+// ---------------------------------------------------------------------------------------
+// device memory shim
+// ---------------------------------------------------------------------------------------
+#ifdef SB_HOSTSIM
+static int dev_alloc(sb_ctx *c, void **p, size_t n) { *p = calloc(1, n ? n : 1); c->allocs.push_back(*p); return *p ? 0 : -1; }
+static void dev_free_all(sb_ctx *c) { for (void *p : c->allocs) free(p); c->allocs.clear(); }
+static int h2d(sb_ctx *, void *d, const void *h, size_t n) { memcpy(d, h, n); return 0; }
+static int d2h(sb_ctx *, void *h, const void *d, size_t n) { memcpy(h, d, n); return 0; }
+static int dev_zero(sb_ctx *, void *d, size_t n) { memset(d, 0, n); return 0; }
+static int dev_sync(sb_ctx *) { return 0; }
+#else
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            c->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            return -2;                                                                             \
+        }                                                                                          \
+    } while (0)
+static int dev_alloc(sb_ctx *c, void **p, size_t n) {
+    CK(cudaMalloc(p, n ? n : 1));
+    c->allocs.push_back(*p);
+    CK(cudaMemsetAsync(*p, 0, n ? n : 1, c->stream));
+    return 0;
+}
+static void dev_free_all(sb_ctx *c) { for (void *p : c->allocs) cudaFree(p); c->allocs.clear(); }
+static int h2d(sb_ctx *c, void *d, const void *h, size_t n) { CK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream)); return 0; }
+static int d2h(sb_ctx *c, void *h, const void *d, size_t n) { CK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); return 0; }
+static int dev_zero(sb_ctx *c, void *d, size_t n) { CK(cudaMemsetAsync(d, 0, n, c->stream)); return 0; }
+static int dev_sync(sb_ctx *c) { CK(cudaStreamSynchronize(c->stream)); return 0; }
+#endif
+
+#define TRY(x) do { int r_ = (x); if (r_) return r_; } while (0)
+template <class T> static int up(sb_ctx *c, const T **dst, const std::vector<T> &v) {
+    void *p; TRY(dev_alloc(c, &p, v.size() * sizeof(T)));
+    if (!v.empty()) TRY(h2d(c, p, v.data(), v.size() * sizeof(T)));
+    *dst = (const T *)p; return 0;
+}
+template <class T> static int mk(sb_ctx *c, T **dst, size_t n) { void *p; TRY(dev_alloc(c, &p, n * sizeof(T))); *dst = (T *)p; return 0; }
+
+static int fail(sb_ctx *c, const char *msg) { if (c) c->err = msg; else g_create_error = msg; return -1; }
+
+// ---------------------------------------------------------------------------------------
+SB_API const char *sb_last_error(const sb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+SB_API void sb_destroy(sb_ctx *c) {
+    if (!c) return;
+#ifndef SB_HOSTSIM
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+#endif
+    dev_free_all(c);
+#ifndef SB_HOSTSIM
+    if (c->stream) cudaStreamDestroy(c->stream);
+#endif
+    delete c;
+}
+
+static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_chains, int team) {
+    const int N = d->n_objects, F = d->n_features, S = d->n_states, K = d->n_clusters, nc = d->n_confounders;
+    const int C = 1 + nc;
+    if (N <= 0 || F <= 0 || S <= 0 || S > 254 || K <= 0 || K > SB_MAXK) return fail(c, "bad problem dimensions");
+    if (C > SB_MAXC) return fail(c, "too many mixture components (max 8)");
+    if (n_chains <= 0) return fail(c, "n_chains must be positive");
+    c->device = device; c->n_chains = n_chains;
+#ifndef SB_HOSTSIM
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(c, "sbayes_b200 needs an sm_100a (B200) device");
+    c->n_sm = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+#else
+    c->n_sm = 4;
+#endif
+    SbProblem &P = c->P;
+    memset(&P, 0, sizeof(P));
+    P.N = N; P.F = F; P.S = S; P.K = K; P.C = C; P.n_conf = nc;
+    P.ldx = (F + 15) / 16 * 16;
+    P.goff[0] = 0; P.goff[1] = K;
+    for (int i = 0; i < nc; i++) { P.conf_ng[i] = d->conf_ngroups[i]; P.goff[i + 2] = P.goff[i + 1] + d->conf_ngroups[i]; }
+    P.G_tot = P.goff[C];
+    P.min_size = d->min_size; P.max_size = d->max_size; P.size_prior = d->size_prior;
+    P.wprior_uniform = d->weights_prior_uniform;
+    P.geo = d->geo_enabled && d->geo_cost; P.geo_agg = d->geo_aggregation; P.geo_pf = d->geo_prob_fn;
+    P.geo_rate = d->geo_rate; P.geo_infl = d->geo_inflection;
+
+    // packed observations, row stride padded to 16 bytes
+    std::vector<uint8_t> x((size_t)N * P.ldx, SB_NA_U8);
+    for (int o = 0; o < N; o++) memcpy(&x[(size_t)o * P.ldx], d->x + (size_t)o * F, F);
+    for (size_t i = 0; i < x.size(); i++) if (x[i] != SB_NA_U8 && x[i] >= S) return fail(c, "state index out of range");
+    TRY(up(c, &P.x, x));
+    std::vector<int32_t> gid(d->conf_gid, d->conf_gid + (size_t)nc * N);
+    for (int i = 0; i < nc; i++) for (int o = 0; o < N; o++) if (gid[(size_t)i * N + o] >= P.conf_ng[i]) return fail(c, "confounder group id out of range");
+    TRY(up(c, &P.conf_gid, gid));
+    // distinct confounder has-patterns
+    std::map<int, int> pat_index; std::vector<int32_t> pat_bits; std::vector<uint8_t> pat_id(N);
+    for (int o = 0; o < N; o++) {
+        int bits = 0;
+        for (int i = 0; i < nc; i++) if (gid[(size_t)i * N + o] >= 0) bits |= 1 << (i + 1);
+        auto it = pat_index.find(bits);
+        if (it == pat_index.end()) { it = pat_index.emplace(bits, (int)pat_bits.size()).first; pat_bits.push_back(bits); }
+        pat_id[o] = (uint8_t)it->second;
+    }
+    P.n_pat = (int)pat_bits.size();
+    TRY(up(c, &P.pat_id, pat_id)); TRY(up(c, &P.pat_bits, pat_bits));
+    // concentrations and the count-independent part of the Dirichlet-categorical marginal
+    const size_t nG = (size_t)P.G_tot * F * S;
+    std::vector<double> alpha(d->alpha, d->alpha + nG), asum((size_t)P.G_tot * F), dcc((size_t)P.G_tot * F), unif((size_t)F * S);
+    for (size_t gf = 0; gf < (size_t)P.G_tot * F; gf++) {
+        double sa = 0.0, sl = 0.0;
+        for (int s = 0; s < S; s++) { double a = alpha[gf * S + s]; sa += a; if (a > 0.0) sl += lgamma(a); }
+        asum[gf] = sa; dcc[gf] = lgamma(sa) - sl;
+    }
+    for (size_t i = 0; i < unif.size(); i++) unif[i] = d->applicable[i] ? 1.0 : 0.0;
+    TRY(up(c, &P.alpha, alpha)); TRY(up(c, &P.asum, asum)); TRY(up(c, &P.dcc, dcc)); TRY(up(c, &P.unif, unif));
+    std::vector<double> aw(d->alpha_w, d->alpha_w + (size_t)F * C), wlnB(F);
+    for (int f = 0; f < F; f++) {
+        double sa = 0.0, sl = 0.0;
+        for (int cc = 0; cc < C; cc++) { sa += aw[(size_t)f * C + cc]; sl += lgamma(aw[(size_t)f * C + cc]); }
+        wlnB[f] = sl - lgamma(sa);
+    }
+    TRY(up(c, &P.alpha_w, aw)); TRY(up(c, &P.wlnB, wlnB));
+    if (P.geo) { std::vector<double> cost(d->geo_cost, d->geo_cost + (size_t)N * N); TRY(up(c, &P.cost, cost)); }
+    if (d->adj_indptr) {
+        std::vector<int32_t> ip(d->adj_indptr, d->adj_indptr + N + 1);
+        std::vector<int32_t> ix(d->adj_indices, d->adj_indices + ip[N]);
+        TRY(up(c, &P.adj_ptr, ip)); TRY(up(c, &P.adj_idx, ix));
+    }
+    c->smem_members = P.geo ? std::min(std::max(P.max_size + 1, 32), N) : 1;
+    if (c->smem_members > 8192) return fail(c, "geo prior: max cluster size above 8192 is not supported");
+    c->smem = sb_smem_bytes(K, c->smem_members);
+
+    // launch geometry: teams of `team` CTAs, co-resident (cooperative launch)
+#ifdef SB_HOSTSIM
+    const char *eb = getenv("SB_HOSTSIM_BLOCK");
+    c->block = eb ? atoi(eb) : 64;
+    int capacity = 64;
+#else
+    c->block = 256;
+    CK(cudaFuncSetAttribute(sb_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sb_run_kernel, c->block, c->smem));
+    if (per_sm < 1) return fail(c, "step kernel does not fit on an SM");
+    int capacity = per_sm * c->n_sm;
+#endif
+    if (team <= 0) {   // auto: spread the GPU over the chains, at most ~4K observations per CTA and pass
+        long long want = ((long long)N * F + 4095) / 4096;
+        team = (int)std::max(1LL, std::min<long long>(std::min<long long>(want, capacity / std::max(1, std::min(n_chains, capacity))), c->n_sm));
+    }
+    if (team > capacity) team = capacity;
+    c->team = team;
+    c->n_teams = std::max(1, std::min(n_chains, capacity / team));
+    c->grid = c->n_teams * team;
+
+    // per-chain state
+    const size_t nS = (size_t)N * P.ldx, nH = (size_t)P.n_pat * 2 * F * C;
+    c->h_states.resize(n_chains);
+    for (int i = 0; i < n_chains; i++) {
+        SbState &s = c->h_states[i];
+        TRY(mk(c, &s.cluster_of, N)); TRY(mk(c, &s.cl_new, N)); TRY(mk(c, &s.sizes, K)); TRY(mk(c, &s.W, (size_t)F * C));
+        for (int b = 0; b < 2; b++) {
+            TRY(mk(c, &s.src[b], nS)); TRY(mk(c, &s.counts[b], nG)); TRY(mk(c, &s.tabP[b], nG)); TRY(mk(c, &s.tabT[b], nG));
+            TRY(mk(c, &s.lh[b], P.G_tot)); TRY(mk(c, &s.geo_agg[b], K)); TRY(mk(c, &s.geo_val[b], K));
+        }
+        TRY(mk(c, &s.osel, N)); TRY(mk(c, &s.ochg, N)); TRY(mk(c, &s.gsel, P.G_tot)); TRY(mk(c, &s.dirty, P.G_tot));
+        TRY(mk(c, &s.dneg, nG)); TRY(mk(c, &s.dpos, nG)); TRY(mk(c, &s.H, nH));
+        TRY(mk(c, &s.w1, nH)); TRY(mk(c, &s.wp, nH)); TRY(mk(c, &s.wq, nH)); TRY(mk(c, &s.lw, nH));
+        TRY(mk(c, &s.val, N)); TRY(mk(c, &s.red_a, N)); TRY(mk(c, &s.red_b, N));
+        TRY(mk(c, &s.list_a, N)); TRY(mk(c, &s.list_b, N)); TRY(mk(c, &s.flag_a, N)); TRY(mk(c, &s.flag_b, N));
+        TRY(mk(c, &s.sc, 64)); TRY(mk(c, &s.post, 8));
+    }
+    TRY(mk(c, &c->d_states, n_chains)); TRY(h2d(c, c->d_states, c->h_states.data(), sizeof(SbState) * n_chains));
+    std::vector<SbSlot> slots(n_chains);
+    memset(slots.data(), 0, sizeof(SbSlot) * n_chains);
+    for (int i = 0; i < n_chains; i++) {
+        slots[i].state = i; slots[i].cfg.temperature = 1.0; slots[i].cfg.prior_temperature = 1.0; slots[i].cfg.p_grow = 0.5;
+        slots[i].cfg.seed = (uint64_t)i;
+    }
+    TRY(mk(c, &c->d_slots, n_chains)); TRY(h2d(c, c->d_slots, slots.data(), sizeof(SbSlot) * n_chains));
+    TRY(mk(c, &c->d_bars, c->n_teams + 1));
+    TRY(mk(c, &c->d_tred, (size_t)c->n_teams * 2 * team * SB_REDW));
+    TRY(mk(c, &c->d_src_tmp, nS)); TRY(mk(c, &c->d_counts_tmp, nG));
+    return dev_sync(c);
+}
+
+SB_API int sb_create(const sb_problem_desc *desc, int device, int n_chains, int team_ctas, sb_ctx **out) {
+    if (!desc || !out) { g_create_error = "null argument"; return -1; }
+    sb_ctx *c = new sb_ctx();
+    int r = create_impl(c, desc, device, n_chains, team_ctas);
+    if (r) { g_create_error = c->err; sb_destroy(c); *out = nullptr; return r; }
+    *out = c;
+    return 0;
+}
+
+static int check_chain(sb_ctx *c, int chain) {
+    if (!c) return -1;
+    if (chain < 0 || chain >= c->n_chains) return fail(c, "chain index out of range");
+#ifndef SB_HOSTSIM
+    CK(cudaSetDevice(c->device));
+#endif
+    return 0;
+}
+static int get_slot(sb_ctx *c, int chain, SbSlot *s) { return d2h(c, s, c->d_slots + chain, sizeof(SbSlot)); }
+
+SB_API int sb_chain_config(sb_ctx *c, int chain, const sb_chain_cfg *cfg) {
+    TRY(check_chain(c, chain));
+    if (!(cfg->temperature > 0) || !(cfg->prior_temperature > 0)) return fail(c, "temperatures must be positive");
+    return h2d(c, &c->d_slots[chain].cfg, cfg, sizeof(sb_chain_cfg));
+}
+
+SB_API int sb_set_state(sb_ctx *c, int chain, const int32_t *cluster_of, const float *W, const uint8_t *src, int64_t i_step) {
+    TRY(check_chain(c, chain));
+    const SbProblem &P = c->P;
+    SbSlot slot; TRY(get_slot(c, chain, &slot));
+    SbState &s = c->h_states[slot.state];
+    std::vector<int> size(P.K, 0);
+    for (int o = 0; o < P.N; o++) {
+        if (cluster_of[o] >= P.K) return fail(c, "cluster index out of range");
+        if (cluster_of[o] >= 0) size[cluster_of[o]]++;
+    }
+    std::vector<uint8_t> sp((size_t)P.N * P.ldx, SB_NA_U8);
+    for (int o = 0; o < P.N; o++) memcpy(&sp[(size_t)o * P.ldx], src + (size_t)o * P.F, P.F);
+    for (int o = 0; o < P.N; o++)
+        for (int f = 0; f < P.F; f++) {
+            uint8_t v = sp[(size_t)o * P.ldx + f];
+            if (v != SB_NA_U8 && v >= P.C) return fail(c, "source component out of range");
+        }
+    TRY(h2d(c, s.cluster_of, cluster_of, sizeof(int32_t) * P.N));
+    TRY(h2d(c, s.W, W, sizeof(float) * P.F * P.C));
+    TRY(h2d(c, s.src[0], sp.data(), sp.size()));
+    TRY(dev_zero(c, s.osel, P.N));
+    double post[8] = {0, 0, 0, 0, 0, (double)i_step, 0, 0};
+    TRY(h2d(c, s.post, post, sizeof(post)));
+    int one = 1;
+    TRY(h2d(c, &c->d_slots[chain].active, &one, sizeof(int)));
+    return 0;
+}
+
+static int launch(sb_ctx *c, long long n_steps, const sb_tape *tape_dev, sb_step_record *rec_dev) {
+    SbLaunch L;
+    memset(&L, 0, sizeof(L));
+    L.P = c->P; L.states = c->d_states; L.slots = c->d_slots; L.n_slots = c->n_chains; L.team = c->team;
+    L.n_steps = n_steps; L.bars = c->d_bars; L.tred = c->d_tred; L.records = rec_dev; L.smem_members = c->smem_members;
+    if (tape_dev) L.tape = *tape_dev;
+    TRY(dev_zero(c, c->d_bars, sizeof(unsigned long long) * (c->n_teams + 1)));
+    c->launches++;
+#ifdef SB_HOSTSIM
+    hostsim::launch([&]() { sb_run_kernel(L); }, c->grid, c->block, c->smem);
+#else
+    void *args[] = {&L};
+    CK(cudaLaunchCooperativeKernel((void *)sb_run_kernel, dim3(c->grid), dim3(c->block), args, c->smem, c->stream));
+#endif
+    return 0;
+}
+
+static int check_errors(sb_ctx *c) {
+    std::vector<SbSlot> slots(c->n_chains);
+    TRY(d2h(c, slots.data(), c->d_slots, sizeof(SbSlot) * c->n_chains));
+    for (int i = 0; i < c->n_chains; i++)
+        if (slots[i].err) {
+            static const char *msg[] = {"", "non-finite posterior accepted (sbayes/sampling/mcmc_chain.py:231-236)",
+                                        "source component out of range in state", "cluster larger than the geo-prior member list",
+                                        "wide operator could not change the cluster"};
+            char buf[256];
+            snprintf(buf, sizeof buf, "chain %d: %s", i, msg[std::min(slots[i].err, 4)]);
+            c->err = buf;
+            int zero = 0; h2d(c, &c->d_slots[i].err, &zero, sizeof(int));
+            return -3;
+        }
+    return 0;
+}
+
+SB_API int sb_sync(sb_ctx *c) {
+    if (!c) return -1;
+    TRY(dev_sync(c));
+    return check_errors(c);
+}
+
+SB_API int sb_run_async(sb_ctx *c, int64_t n_steps) {
+    TRY(check_chain(c, 0));
+    return launch(c, n_steps, nullptr, nullptr);
+}
+
+SB_API int sb_run(sb_ctx *c, int64_t n_steps, const sb_tape *tape, sb_step_record *records) {
+    TRY(check_chain(c, 0));
+    sb_tape td; memset(&td, 0, sizeof td);
+    std::vector<void *> tmp_from = c->allocs;   // tape / record buffers are released after the run
+    size_t n_keep = c->allocs.size();
+    if (tape && tape->vals) {
+        double *v; int32_t *o, *l, *w;
+        TRY(mk(c, &v, (size_t)std::max<int64_t>(tape->n_vals, 1))); TRY(h2d(c, v, tape->vals, sizeof(double) * tape->n_vals));
+        TRY(mk(c, &o, (size_t)n_steps * SB_N_SITES)); TRY(h2d(c, o, tape->off, sizeof(int32_t) * n_steps * SB_N_SITES));
+        TRY(mk(c, &l, (size_t)n_steps * SB_N_SITES)); TRY(h2d(c, l, tape->len, sizeof(int32_t) * n_steps * SB_N_SITES));
+        td.vals = v; td.off = o; td.len = l; td.n_vals = tape->n_vals;
+        if (tape->wide_rows) { TRY(mk(c, &w, (size_t)n_steps)); TRY(h2d(c, w, tape->wide_rows, sizeof(int32_t) * n_steps)); td.wide_rows = w; }
+    }
+    sb_step_record *rd = nullptr;
+    size_t n_rec = (size_t)c->n_chains * (size_t)n_steps;
+    if (records && n_rec) TRY(mk(c, &rd, n_rec));
+    int r = launch(c, n_steps, (tape && tape->vals) ? &td : nullptr, rd);
+    if (!r) r = dev_sync(c);
+    if (!r && rd) r = d2h(c, records, rd, sizeof(sb_step_record) * n_rec);
+    while (c->allocs.size() > n_keep) {
+#ifdef SB_HOSTSIM
+        free(c->allocs.back());
+#else
+        cudaFree(c->allocs.back());
+#endif
+        c->allocs.pop_back();
+    }
+    if (r) return r;
+    return check_errors(c);
+}
+
+SB_API int sb_posterior(sb_ctx *c, int chain, sb_posterior_t *out) {
+    TRY(check_chain(c, chain));
+    SbSlot slot; TRY(get_slot(c, chain, &slot));
+    double post[8];
+    TRY(d2h(c, post, c->h_states[slot.state].post, sizeof(post)));
+    out->ll = post[0]; out->size_prior = post[1]; out->geo_prior = post[2]; out->weights_prior = post[3]; out->source_prior = post[4];
+    out->prior = post[1] + post[2] + post[3] + post[4];
+    return 0;
+}
+
+SB_API int sb_eval(sb_ctx *c, int chain, sb_posterior_t *out) {
+    TRY(check_chain(c, chain));
+    TRY(launch(c, 0, nullptr, nullptr));
+    TRY(dev_sync(c));
+    TRY(check_errors(c));
+    return sb_posterior(c, chain, out);
+}
+
+SB_API int sb_get_state(sb_ctx *c, int chain, int32_t *cluster_of, float *W, uint8_t *src, int32_t *counts) {
+    TRY(check_chain(c, chain));
+    const SbProblem &P = c->P;
+    SbSlot slot; TRY(get_slot(c, chain, &slot));
+    SbState &s = c->h_states[slot.state];
+    if (cluster_of) TRY(d2h(c, cluster_of, s.cluster_of, sizeof(int32_t) * P.N));
+    if (W) TRY(d2h(c, W, s.W, sizeof(float) * P.F * P.C));
+    if (src || counts) {
+#ifdef SB_HOSTSIM
+        hostsim::launch([&]() { sb_export_kernel(P, s, c->d_src_tmp, c->d_counts_tmp); }, 2, 64, 0);
+#else
+        sb_export_kernel<<<c->n_sm * 2, 256, 0, c->stream>>>(P, s, c->d_src_tmp, c->d_counts_tmp);
+        CK(cudaGetLastError());
+#endif
+        c->launches++;
+        if (src) {
+            std::vector<uint8_t> sp((size_t)P.N * P.ldx);
+            TRY(d2h(c, sp.data(), c->d_src_tmp, sp.size()));
+            for (int o = 0; o < P.N; o++) memcpy(src + (size_t)o * P.F, &sp[(size_t)o * P.ldx], P.F);
+        }
+        if (counts) TRY(d2h(c, counts, c->d_counts_tmp, sizeof(int32_t) * P.G_tot * P.F * P.S));
+    }
+    return 0;
+}
+
+SB_API int sb_op_stats(sb_ctx *c, int chain, int64_t *accepts, int64_t *rejects) {
+    TRY(check_chain(c, chain));
+    SbSlot slot; TRY(get_slot(c, chain, &slot));
+    for (int i = 0; i < SB_N_OPS; i++) { accepts[i] = slot.accepts[i]; rejects[i] = slot.rejects[i]; }
+    return 0;
+}
+
+SB_API int sb_get_slots(sb_ctx *c, int32_t *state_of_slot) {
+    TRY(check_chain(c, 0));
+    std::vector<SbSlot> slots(c->n_chains);
+    TRY(d2h(c, slots.data(), c->d_slots, sizeof(SbSlot) * c->n_chains));
+    for (int i = 0; i < c->n_chains; i++) state_of_slot[i] = slots[i].state;
+    return 0;
+}
+SB_API int sb_set_slots(sb_ctx *c, const int32_t *state_of_slot) {
+    TRY(check_chain(c, 0));
+    std::vector<char> seen(c->n_chains, 0);
+    for (int i = 0; i < c->n_chains; i++) {
+        int s = state_of_slot[i];
+        if (s < 0 || s >= c->n_chains || seen[s]) return fail(c, "state_of_slot must be a permutation");
+        seen[s] = 1;
+    }
+    for (int i = 0; i < c->n_chains; i++) TRY(h2d(c, &c->d_slots[i].state, &state_of_slot[i], sizeof(int)));
+    return 0;
+}
+
+// swap_chains (sbayes/mcmc_setup.py:365-418).  The states stay where they are in HBM; a
+// swap exchanges which state a temperature slot points at.  The decisions are taken on
+// the host from the per-chain scalars (48 bytes per chain), with the same Philox
+// addressing as oracle/draws.py: swap_pairs / swap_uniform (step = round).
+SB_API int sb_swap(sb_ctx *c, int attempts, int only_neighbours, uint64_t seed, int64_t round,
+                   int32_t *state_of_slot, int32_t *n_accepted) {
+    TRY(check_chain(c, 0));
+    TRY(dev_sync(c));
+    const int n = c->n_chains;
+    std::vector<SbSlot> slots(n);
+    TRY(d2h(c, slots.data(), c->d_slots, sizeof(SbSlot) * n));
+    std::vector<double> ll(n), pr(n);
+    for (int s = 0; s < n; s++) {
+        double post[8];
+        TRY(d2h(c, post, c->h_states[s].post, sizeof(post)));
+        ll[s] = post[0]; pr[s] = post[1] + post[2] + post[3] + post[4];
+    }
+    std::vector<std::pair<int, int>> pairs;
+    if (only_neighbours) for (int i = 0; i + 1 < n; i++) pairs.push_back({i, i + 1});
+    else for (int i = 0; i + 1 < n; i++) for (int j = i + 1; j < n; j++) pairs.push_back({i, j});
+    attempts = std::min<int>(attempts, (int)pairs.size());
+    Draws D; memset(&D, 0, sizeof D);
+    D.k0 = (uint32_t)(seed & 0xFFFFFFFFull); D.k1 = (uint32_t)(seed >> 32); D.step = (unsigned long long)round;
+    auto uni = [&](uint32_t idx, int sub) {
+        uint32_t c1 = (uint32_t)SITE_SWAP | ((uint32_t)sub << 8);
+        Philox4 p = philox4x32_10(idx, c1, (uint32_t)(D.step & 0xFFFFFFFFull), (uint32_t)(D.step >> 32), D.k0, D.k1);
+        return u01_double(p.w[0], p.w[1]);
+    };
+    std::vector<int> idx(pairs.size());
+    for (size_t i = 0; i < idx.size(); i++) idx[i] = (int)i;
+    int acc = 0;
+    for (int a = 0; a < attempts; a++) {
+        int rem = (int)idx.size() - a;
+        int j = a + std::min((int)(uni((uint32_t)a, 0) * rem), rem - 1);
+        std::swap(idx[a], idx[j]);
+        int i0 = pairs[idx[a]].first, j0 = pairs[idx[a]].second;
+        int si = slots[i0].state, sj = slots[j0].state;
+        double Ti = slots[i0].cfg.temperature, Tj = slots[j0].cfg.temperature;
+        double Pi = slots[i0].cfg.prior_temperature, Pj = slots[j0].cfg.prior_temperature;
+        double r = -((pr[si] - pr[sj]) * (1.0 / Pi - 1.0 / Pj) + (ll[si] - ll[sj]) * (1.0 / Ti - 1.0 / Tj));
+        double u = uni((uint32_t)a, 1);
+        double lu = u > 0 ? log(u) : -INFINITY;
+        if (lu < r) { slots[i0].state = sj; slots[j0].state = si; acc++; }
+    }
+    for (int i = 0; i < n; i++) {
+        TRY(h2d(c, &c->d_slots[i].state, &slots[i].state, sizeof(int)));
+        if (state_of_slot) state_of_slot[i] = slots[i].state;
+    }
+    if (n_accepted) *n_accepted = acc;
+    return 0;
+}
+
+SB_API int sb_info(const sb_ctx *c, int32_t *out8) {
+    if (!c) return -1;
+    out8[0] = c->device; out8[1] = c->n_chains; out8[2] = c->team; out8[3] = c->grid; out8[4] = c->block;
+    out8[5] = (int)c->smem; out8[6] = c->n_sm; out8[7] = (int)c->launches;
+    return 0;
+}
+
+SB_API uint64_t sb_stream(const sb_ctx *c) { return c ? (uint64_t)(uintptr_t)c->stream : 0; }
+
+// bulk count rebuild as stand-alone kernels (sb_counts.cuh): shared-memory histogram and the
+// int8 tensor-core contraction.  Both read the committed state of `chain` and return the
+// stacked counts; `ms` receives the device time of the kernel.
+static int counts_common(sb_ctx *c, int chain, int32_t *counts_out, float *ms, bool mma) {
+    TRY(check_chain(c, chain));
+    const SbProblem &P = c->P;
+    SbSlot slot; TRY(get_slot(c, chain, &slot));
+    SbState &s = c->h_states[slot.state];
+    const size_t nG = (size_t)P.G_tot * P.F * P.S;
+    TRY(dev_zero(c, c->d_counts_tmp, sizeof(int32_t) * nG));
+    float t = 0.f;
+#ifdef SB_HOSTSIM
+    if (mma) return fail(c, "the tensor-core rebuild needs a GPU");
+    hostsim::launch([&]() { sb_counts_hist_kernel(P, s, c->d_counts_tmp); }, 2, 64, sb_counts_hist_smem(P));
+#else
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, c->stream));
+    int r = mma ? sb_counts_mma_launch(P, s, c->d_counts_tmp, c->n_sm, c->stream)
+                : sb_counts_hist_launch(P, s, c->d_counts_tmp, c->n_sm, c->stream);
+    if (r) return fail(c, "count rebuild launch failed");
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(e1, c->stream));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaEventElapsedTime(&t, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+#endif
+    c->launches++;
+    if (ms) *ms = t;
+    if (counts_out) TRY(d2h(c, counts_out, c->d_counts_tmp, sizeof(int32_t) * nG));
+    return 0;
+}
+SB_API int sb_counts_rebuild_hist(sb_ctx *c, int chain, int32_t *counts_out, float *ms) { return counts_common(c, chain, counts_out, ms, false); }
+SB_API int sb_counts_rebuild_mma(sb_ctx *c, int chain, int32_t *counts_out, float *ms) { return counts_common(c, chain, counts_out, ms, true); }
