@@ -1,0 +1,122 @@
+"""GPU parity tests (run on the B200 box): the CUDA library, through the C ABI, against
+(a) the golden fixtures recorded from the live reference and (b) the fp64 oracle."""
+import numpy as np
+import pytest
+
+import parity
+from conftest import golden_cases
+from oracle import model as M
+from sbayes_b200 import synth
+from sbayes_b200.backend import DeviceContext
+from sbayes_b200.packed import ChainConfig
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", golden_cases())
+@pytest.mark.parametrize("team", [1, 3])
+def test_replay_reference_tape(case, team):
+    parity.replay_golden(case, team=team)
+
+
+def test_replay_team_auto():
+    parity.replay_golden("synth_c2_width", team=0)
+
+
+@pytest.mark.parametrize("team", [1, 8])
+def test_philox_lockstep_small(team):
+    prob, _ = synth.make_problem(N=80, F=16, S=4, K=3, n_fam=4, seed=7, jagged_states=True, max_size=30)
+    cfgs = [ChainConfig(seed=10), ChainConfig(temperature=1.3, prior_temperature=1.2, seed=11),
+            ChainConfig(seed=12, sample_from_prior=True)]
+    st0 = [synth.initial_state(prob, seed=20 + i, objects_per_cluster=6) for i in range(3)]
+    parity.philox_lockstep(prob, st0, cfgs, 400, team=team)
+
+
+def test_philox_lockstep_geo():
+    prob, _ = synth.make_problem(N=48, F=10, S=3, K=2, n_fam=3, seed=3, geo_cost_based=True, max_size=20)
+    cfgs = [ChainConfig(seed=5), ChainConfig(temperature=1.1, seed=6)]
+    st0 = [synth.initial_state(prob, seed=30 + i, objects_per_cluster=5) for i in range(2)]
+    parity.philox_lockstep(prob, st0, cfgs, 300, team=2)
+
+
+def test_philox_lockstep_c2_shape():
+    """BASELINE config 2 shape (1000 x 100 x 4, K=5, 8 families), 4 MC3 temperatures."""
+    prob, _ = synth.make_problem(N=1000, F=100, S=4, K=5, n_fam=8, seed=2)
+    cfgs = [ChainConfig(temperature=1.0 + 0.05 * c, prior_temperature=1.0, seed=40 + c) for c in range(4)]
+    st0 = [synth.initial_state(prob, seed=50 + c) for c in range(4)]
+    parity.philox_lockstep(prob, st0, cfgs, 60, team=0)
+
+
+@pytest.mark.parametrize("shape", [(5, 2, 2, 2, 2), (100, 36, 5, 3, 6), (1000, 100, 4, 5, 8), (5000, 200, 6, 5, 20)])
+def test_full_eval_matches_oracle(shape):
+    """Count rebuild bit-exact, log-likelihood and priors 1e-10 relative (north_star)."""
+    N, F, S, K, nf = shape
+    prob, _ = synth.make_problem(N=N, F=F, S=S, K=K, n_fam=nf, seed=1, min_size=1 if N < 10 else 3)
+    st = synth.initial_state(prob, seed=2, objects_per_cluster=1 if N < 10 else 10)
+    ctx = DeviceContext(prob, 1)
+    try:
+        ctx.set_state(0, st)
+        ev = ctx.eval(0)
+        got = ctx.get_state(0)
+        assert np.array_equal(got.counts, M.rebuild_counts(prob, st))
+        hist, _ = ctx.counts_rebuild(0)
+        assert np.array_equal(hist, got.counts)
+        st.counts = got.counts
+        assert parity.rel(M.log_likelihood(prob, st), ev["ll"]) < 1e-10
+        assert parity.rel(M.log_prior(prob, st), ev["prior"]) < 1e-10
+        assert np.array_equal(got.src, st.src) and np.array_equal(got.cluster_of, st.cluster_of)
+    finally:
+        ctx.close()
+
+
+def test_incremental_counts_after_long_run():
+    """size-independent property at the bench shape: after many steps the incrementally
+    maintained counts equal a bulk rebuild, and cached posterior == uncached evaluation."""
+    prob, _ = synth.make_problem(N=1000, F=100, S=4, K=5, n_fam=8, seed=2)
+    ctx = DeviceContext(prob, 4)
+    try:
+        for c in range(4):
+            ctx.configure(c, ChainConfig(temperature=1.0 + 0.05 * c, seed=c))
+            ctx.set_state(c, synth.initial_state(prob, seed=c))
+        ctx.run(3000)
+        for c in range(4):
+            st = ctx.get_state(c)
+            assert np.array_equal(st.counts, M.rebuild_counts(prob, st))
+            hist, _ = ctx.counts_rebuild(c)
+            assert np.array_equal(hist, st.counts)
+            assert np.all((st.src == 255) == (prob.x == 255))
+            post = ctx.posterior(c)
+            assert parity.rel(M.log_likelihood(prob, st), post["ll"]) < 1e-10
+            assert parity.rel(M.log_prior(prob, st), post["prior"]) < 1e-10
+            a, r = ctx.op_stats(c)
+            assert int(a.sum() + r.sum()) == 3000
+    finally:
+        ctx.close()
+
+
+def test_mc3_swap_matches_oracle():
+    from oracle import chain as CH
+    from oracle.draws import PhiloxDraws
+    prob, _ = synth.make_problem(N=100, F=20, S=4, K=3, n_fam=4, seed=9, max_size=30)
+    n = 4
+    T, Tp = CH.temperature_ladder(n, 0.3, 0.1, False)
+    ctx = DeviceContext(prob, n)
+    try:
+        sts = [synth.initial_state(prob, seed=60 + c) for c in range(n)]
+        for c in range(n):
+            ctx.configure(c, ChainConfig(temperature=float(T[c]), prior_temperature=float(Tp[c]), seed=70 + c))
+            ctx.set_state(c, sts[c])
+        ctx.run(50)
+        posts = [ctx.posterior(c) for c in range(n)]
+        slot = list(range(n))
+        d = PhiloxDraws(1234)
+        d.begin_step(7)
+        acc = CH.swap_chains([p["ll"] for p in posts], [p["prior"] for p in posts], T, Tp, slot, d, attempts=100)
+        sos, n_acc = ctx.swap(100, False, 1234, 7)
+        assert n_acc == len(acc) and sos.tolist() == slot
+        # the chain at slot c now runs the state that was swapped in
+        for c in range(n):
+            assert parity.rel(ctx.posterior(c)["ll"], posts[slot[c]]["ll"]) == 0.0
+        ctx.run(20)
+    finally:
+        ctx.close()

@@ -1,0 +1,33 @@
+"""CPU-side check of the *device code's control flow*: the CUDA sources compiled for the fibre
+emulator (tests/hostsim) replay the reference's recorded steps and run in lockstep with
+the oracle.  The emulator is test infrastructure; the real parity tests are the `-m gpu`
+ones, which call the CUDA library through the same C ABI."""
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim"))
+import build as HB  # noqa: E402
+import parity  # noqa: E402
+from sbayes_b200 import synth  # noqa: E402
+from sbayes_b200.packed import ChainConfig  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return HB.load()
+
+
+@pytest.mark.parametrize("case,team,n", [("synth_small", 1, 150), ("synth_tempered", 2, 150), ("synth_geo", 2, 120),
+                                         ("synth_geo_sigmoid", 1, 80), ("synth_tiny_all", 3, 200), ("c1_testfiles", 2, 200),
+                                         ("c3_south_america", 3, 60), ("c3_south_america_hot", 1, 60)])
+def test_emulated_replay(lib, case, team, n):
+    parity.replay_golden(case, lib=lib, team=team, n_steps=n)
+
+
+def test_emulated_philox_lockstep(lib):
+    prob, _ = synth.make_problem(N=50, F=12, S=4, K=3, n_fam=4, seed=7, jagged_states=True, max_size=20)
+    cfgs = [ChainConfig(seed=100), ChainConfig(temperature=1.2, prior_temperature=1.1, seed=101)]
+    st0 = [synth.initial_state(prob, seed=5 + i, objects_per_cluster=5) for i in range(2)]
+    parity.philox_lockstep(prob, st0, cfgs, 120, lib=lib, team=2)
