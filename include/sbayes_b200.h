@@ -26,7 +26,7 @@
  *                        operators (sbayes/sampling/operators.py:423-1827)
  *   sb_posterior         MCMCChain._ll / _prior and Sample.last_lh / last_prior
  *                        (sbayes/sampling/mcmc_chain.py:87,108)
- *   sb_op_stats          Operator.accepts / rejects (sbayes/sampling/operators.py:278-293)
+ *   sb_op_stats          Operator.accepts / rejects / step_times (sbayes/sampling/operators.py:278-293)
  *   sb_swap              swap_chains (sbayes/mcmc_setup.py:365-418)
  *   sb_counts_rebuild_mma  recalculate_feature_counts as an int8 tensor-core contraction
  *                        (sbayes/sampling/counts.py:10-52)
@@ -113,7 +113,7 @@ int sb_posterior(sb_ctx *ctx, int chain, sb_posterior_t *out);     /* cached val
 int sb_run(sb_ctx *ctx, int64_t n_steps, const sb_tape *tape, sb_step_record *records);
 int sb_run_async(sb_ctx *ctx, int64_t n_steps);                     /* enqueue only; sb_sync waits */
 int sb_sync(sb_ctx *ctx);
-int sb_op_stats(sb_ctx *ctx, int chain, int64_t *accepts, int64_t *rejects);
+int sb_op_stats(sb_ctx *ctx, int chain, int64_t *accepts, int64_t *rejects, int64_t *cycles /* may be NULL */);
 int sb_swap(sb_ctx *ctx, int attempts, int only_neighbours, uint64_t seed, int64_t round,
             int32_t *state_of_slot, int32_t *n_accepted);
 int sb_get_slots(sb_ctx *ctx, int32_t *state_of_slot);

@@ -76,7 +76,7 @@ def _bind(lib):
     lib.sb_run.argtypes = [vp, i64, C.POINTER(_Tape), vp]
     lib.sb_run_async.argtypes = [vp, i64]
     lib.sb_sync.argtypes = [vp]
-    lib.sb_op_stats.argtypes = [vp, i32, vp, vp]
+    lib.sb_op_stats.argtypes = [vp, i32, vp, vp, vp]
     lib.sb_swap.argtypes = [vp, i32, i32, u64, i64, vp, vp]
     lib.sb_get_slots.argtypes = [vp, vp]
     lib.sb_set_slots.argtypes = [vp, vp]
@@ -233,8 +233,14 @@ class DeviceContext:
 
     def op_stats(self, chain: int):
         a, r = np.zeros(N_OPS, np.int64), np.zeros(N_OPS, np.int64)
-        self._ck(self.lib.sb_op_stats(self.h, chain, _ptr(a), _ptr(r)))
+        self._ck(self.lib.sb_op_stats(self.h, chain, _ptr(a), _ptr(r), None))
         return a, r
+
+    def op_cycles(self, chain: int) -> np.ndarray:
+        """SM cycles spent per operator (Operator.step_times, operators.py:232-293)."""
+        a, r, cy = np.zeros(N_OPS, np.int64), np.zeros(N_OPS, np.int64), np.zeros(N_OPS, np.int64)
+        self._ck(self.lib.sb_op_stats(self.h, chain, _ptr(a), _ptr(r), _ptr(cy)))
+        return cy
 
     def swap(self, attempts: int, only_neighbours: bool, seed: int, round_: int):
         sos, n = np.zeros(self.n_chains, np.int32), np.zeros(1, np.int32)

@@ -400,10 +400,10 @@ SB_API int sb_get_state(sb_ctx *c, int chain, int32_t *cluster_of, float *W, uin
     return 0;
 }
 
-SB_API int sb_op_stats(sb_ctx *c, int chain, int64_t *accepts, int64_t *rejects) {
+SB_API int sb_op_stats(sb_ctx *c, int chain, int64_t *accepts, int64_t *rejects, int64_t *cycles) {
     TRY(check_chain(c, chain));
     SbSlot slot; TRY(get_slot(c, chain, &slot));
-    for (int i = 0; i < SB_N_OPS; i++) { accepts[i] = slot.accepts[i]; rejects[i] = slot.rejects[i]; }
+    for (int i = 0; i < SB_N_OPS; i++) { accepts[i] = slot.accepts[i]; rejects[i] = slot.rejects[i]; if (cycles) cycles[i] = slot.cycles[i]; }
     return 0;
 }
 

@@ -1316,6 +1316,7 @@ SB_DEV void rebuild_state(Run &R) {
 // -----------------------------------------------------------------------------------------
 SB_DEV void mcmc_step(Run &R, sb_step_record *rec) {
     const SbProblem &P = *R.P;
+    const long long t_begin = sb_clock();
     R.i_step++;
     R.D.step = (unsigned long long)R.i_step;
     // operator choice (mcmc_chain.py:179-184)
@@ -1378,7 +1379,10 @@ SB_DEV void mcmc_step(Run &R, sb_step_record *rec) {
         rec->prior_new = (touched && !pr.force_reject) ? prior_new : R.pr_size + R.pr_geo + R.pr_w + R.pr_src;
         rec->mh_ratio = ratio; rec->log_u = log_u;
     }
-    if (R.rank == 0 && sb_tid() == 0) { if (accept) R.slot->accepts[op]++; else R.slot->rejects[op]++; }
+    if (R.rank == 0 && sb_tid() == 0) {
+        if (accept) R.slot->accepts[op]++; else R.slot->rejects[op]++;
+        R.slot->cycles[op] += sb_clock() - t_begin;
+    }
     if (touched && op != OP_WEIGHTS) {
         team_sync(R);     // every CTA has finished reading the candidate view
         const int F = P.F, C = P.C;

@@ -77,6 +77,7 @@ struct SbState {
 struct SbSlot {
     sb_chain_cfg cfg;
     long long accepts[SB_N_OPS], rejects[SB_N_OPS];
+    long long cycles[SB_N_OPS];  // SM clock cycles spent in each operator's steps (rank-0 CTA)
     int state;                   // which SbState currently sits at this temperature
     int err;
     int active;                  // a state has been uploaded
