@@ -30,8 +30,12 @@ struct sb_ctx {
     size_t smem = 0;
     long long launches = 0;
     SbProblem P;
-    std::vector<SbState> h_states;
-    SbState *d_states = nullptr;
+    std::vector<SbShared> h_states;
+    SbShared *d_states = nullptr;
+    SbPlace place;
+    char *d_rep = nullptr;
+    int use_cluster = 0;
+    std::vector<int32_t> cg_ptr, cg_idx;
     SbSlot *d_slots = nullptr;
     unsigned long long *d_bars = nullptr;
     double *d_tred = nullptr;
@@ -171,50 +175,109 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
         std::vector<int32_t> ix(d->adj_indices, d->adj_indices + ip[N]);
         TRY(up(c, &P.adj_ptr, ip)); TRY(up(c, &P.adj_idx, ix));
     }
-    c->smem_members = P.geo ? std::min(std::max(P.max_size + 1, 32), N) : 1;
+    // members of every confounder group (CSR, sorted): the GROUPS selector of the source operator
+    {
+        std::vector<int32_t> ptr(1, 0), idx;
+        for (int i = 0; i < nc; i++)
+            for (int g = 0; g < P.conf_ng[i]; g++) {
+                for (int o = 0; o < N; o++) if (gid[(size_t)i * N + o] == g) idx.push_back(o);
+                ptr.push_back((int32_t)idx.size());
+            }
+        if (idx.empty()) idx.push_back(0);
+        TRY(up(c, &P.cg_ptr, ptr)); TRY(up(c, &P.cg_idx, idx));
+    }
+    c->smem_members = std::max(P.G_tot, 32);
+    if (P.geo) c->smem_members = std::max(c->smem_members, std::min(std::max(P.max_size + 1, 32), N));
     if (c->smem_members > 8192) return fail(c, "geo prior: max cluster size above 8192 is not supported");
-    c->smem = sb_smem_bytes(K, c->smem_members);
 
-    // launch geometry: teams of `team` CTAs, co-resident (cooperative launch)
+    // replica placement: shared memory first (most reused arrays first), HBM slice otherwise
+    const size_t nS = (size_t)N * P.ldx, nH = (size_t)P.n_pat * 2 * F * C;
+    {
+        SbPlace &pl = c->place;
+        memset(&pl, 0, sizeof(pl));
+        size_t bytes[A_N];
+        bytes[A_WQ] = nH * 8; bytes[A_TABT] = nG * 8; bytes[A_TABP] = nG * 8; bytes[A_H0] = nH * 4; bytes[A_H1] = nH * 4;
+        bytes[A_LW] = nH * 8; bytes[A_COUNTS] = nG * 4; bytes[A_WP] = nH * 8; bytes[A_W1] = nH * 8;
+        bytes[A_DNEG] = nG * 4; bytes[A_DPOS] = nG * 4;
+        size_t budget = 200 * 1024;
+#ifdef SB_HOSTSIM
+        const char *eb2 = getenv("SB_HOSTSIM_SMEM");
+        if (eb2) budget = (size_t)atol(eb2);
+#else
+        int max_optin = 0;
+        CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        budget = (size_t)max_optin;
+#endif
+        FixedSmem fx0 = sb_fixed_smem(P.G_tot, K, F, C, c->smem_members, 0);
+        if (fx0.end + 1024 > budget) return fail(c, "problem too large for the fixed shared-memory part of the step kernel");
+        size_t soff = 0, goff = 0;
+        for (int a = 0; a < A_N; a++) {
+            size_t b = (bytes[a] + 15) & ~(size_t)15;
+            pl.glob_off[a] = goff; goff += b;
+            if (soff + b + fx0.end + 256 <= budget) { pl.in_smem[a] = 1; pl.smem_off[a] = (unsigned)soff; soff += b; }
+        }
+        pl.cand_off[0] = goff; goff += (nG * 4 + 15) & ~(size_t)15;
+        pl.cand_off[1] = goff; goff += nG * 8;
+        pl.cand_off[2] = goff; goff += nG * 8;
+        pl.sel_off = goff; goff += ((size_t)N + 15) & ~(size_t)15;
+        pl.rep_bytes = (goff + 255) & ~(size_t)255;
+        pl.fixed_off = (unsigned)soff;
+        pl.smem_bytes = sb_fixed_smem(P.G_tot, K, F, C, c->smem_members, pl.fixed_off).end;
+        c->smem = pl.smem_bytes;
+    }
+
+    // launch geometry: teams of `team` CTAs; a team of <= 16 CTAs is a thread-block cluster
 #ifdef SB_HOSTSIM
     const char *eb = getenv("SB_HOSTSIM_BLOCK");
     c->block = eb ? atoi(eb) : 64;
     int capacity = 64;
 #else
-    c->block = 256;
+    c->block = SB_BLOCK;
     CK(cudaFuncSetAttribute(sb_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
+    CK(cudaFuncSetAttribute(sb_run_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sb_run_kernel, c->block, c->smem));
     if (per_sm < 1) return fail(c, "step kernel does not fit on an SM");
     int capacity = per_sm * c->n_sm;
 #endif
-    if (team <= 0) {   // auto: spread the GPU over the chains, at most ~4K observations per CTA and pass
-        long long want = ((long long)N * F + 4095) / 4096;
-        team = (int)std::max(1LL, std::min<long long>(std::min<long long>(want, capacity / std::max(1, std::min(n_chains, capacity))), c->n_sm));
+    if (team <= 0) {   // auto: about 8K observations per CTA and pass, at most a 16-CTA cluster per chain
+        long long want = ((long long)N * F + 8191) / 8192;
+        long long cap_per_chain = std::max(1, capacity / std::max(1, std::min(n_chains, capacity)));
+        team = (int)std::max(1LL, std::min(want, cap_per_chain));
+        if (team > 16 && want <= 32) team = 16;
     }
     if (team > capacity) team = capacity;
     c->team = team;
+    c->use_cluster = 0;
+#ifndef SB_HOSTSIM
+    if (team > 1 && team <= 16 && !getenv("SB_NO_CLUSTER")) {
+        // largest number of co-resident clusters of this shape
+        cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(team * std::max(1, capacity / team)); cfg.blockDim = dim3(c->block); cfg.dynamicSmemBytes = c->smem;
+        cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = team; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int n_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&n_clusters, sb_run_kernel, &cfg) == cudaSuccess && n_clusters >= 1) {
+            c->use_cluster = 1;
+            capacity = n_clusters * team;
+        } else cudaGetLastError();
+    }
+#endif
     c->n_teams = std::max(1, std::min(n_chains, capacity / team));
     c->grid = c->n_teams * team;
 
-    // per-chain state
-    const size_t nS = (size_t)N * P.ldx, nH = (size_t)P.n_pat * 2 * F * C;
+    // per-chain shared state and per-CTA replica slices
     c->h_states.resize(n_chains);
     for (int i = 0; i < n_chains; i++) {
-        SbState &s = c->h_states[i];
-        TRY(mk(c, &s.cluster_of, N)); TRY(mk(c, &s.cl_new, N)); TRY(mk(c, &s.sizes, K)); TRY(mk(c, &s.W, (size_t)F * C));
-        for (int b = 0; b < 2; b++) {
-            TRY(mk(c, &s.src[b], nS)); TRY(mk(c, &s.counts[b], nG)); TRY(mk(c, &s.tabP[b], nG)); TRY(mk(c, &s.tabT[b], nG));
-            TRY(mk(c, &s.lh[b], P.G_tot)); TRY(mk(c, &s.geo_agg[b], K)); TRY(mk(c, &s.geo_val[b], K));
-        }
-        TRY(mk(c, &s.osel, N)); TRY(mk(c, &s.ochg, N)); TRY(mk(c, &s.gsel, P.G_tot)); TRY(mk(c, &s.dirty, P.G_tot));
-        TRY(mk(c, &s.dneg, nG)); TRY(mk(c, &s.dpos, nG)); TRY(mk(c, &s.H, nH));
-        TRY(mk(c, &s.w1, nH)); TRY(mk(c, &s.wp, nH)); TRY(mk(c, &s.wq, nH)); TRY(mk(c, &s.lw, nH));
-        TRY(mk(c, &s.val, N)); TRY(mk(c, &s.red_a, N)); TRY(mk(c, &s.red_b, N));
+        SbShared &s = c->h_states[i];
+        TRY(mk(c, &s.cluster_of, N)); TRY(mk(c, &s.W, (size_t)F * C));
+        for (int b = 0; b < 2; b++) { TRY(mk(c, &s.src[b], nS)); TRY(mk(c, &s.val[b], N)); }
+        TRY(mk(c, &s.osel, N)); TRY(mk(c, &s.counts, nG)); TRY(mk(c, &s.H, nH)); TRY(mk(c, &s.sizes, K));
         TRY(mk(c, &s.list_a, N)); TRY(mk(c, &s.list_b, N)); TRY(mk(c, &s.flag_a, N)); TRY(mk(c, &s.flag_b, N));
-        TRY(mk(c, &s.sc, 64)); TRY(mk(c, &s.post, 8));
+        TRY(mk(c, &s.post, 8));
     }
-    TRY(mk(c, &c->d_states, n_chains)); TRY(h2d(c, c->d_states, c->h_states.data(), sizeof(SbState) * n_chains));
+    TRY(mk(c, &c->d_rep, c->place.rep_bytes * (size_t)c->grid));
+    TRY(mk(c, &c->d_states, n_chains)); TRY(h2d(c, c->d_states, c->h_states.data(), sizeof(SbShared) * n_chains));
     std::vector<SbSlot> slots(n_chains);
     memset(slots.data(), 0, sizeof(SbSlot) * n_chains);
     for (int i = 0; i < n_chains; i++) {
@@ -225,6 +288,7 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
     TRY(mk(c, &c->d_bars, c->n_teams + 1));
     TRY(mk(c, &c->d_tred, (size_t)c->n_teams * 2 * team * SB_REDW));
     TRY(mk(c, &c->d_src_tmp, nS)); TRY(mk(c, &c->d_counts_tmp, nG));
+    (void)nH;
     return dev_sync(c);
 }
 
@@ -257,7 +321,7 @@ SB_API int sb_set_state(sb_ctx *c, int chain, const int32_t *cluster_of, const f
     TRY(check_chain(c, chain));
     const SbProblem &P = c->P;
     SbSlot slot; TRY(get_slot(c, chain, &slot));
-    SbState &s = c->h_states[slot.state];
+    SbShared &s = c->h_states[slot.state];
     std::vector<int> size(P.K, 0);
     for (int o = 0; o < P.N; o++) {
         if (cluster_of[o] >= P.K) return fail(c, "cluster index out of range");
@@ -286,14 +350,24 @@ static int launch(sb_ctx *c, long long n_steps, const sb_tape *tape_dev, sb_step
     memset(&L, 0, sizeof(L));
     L.P = c->P; L.states = c->d_states; L.slots = c->d_slots; L.n_slots = c->n_chains; L.team = c->team;
     L.n_steps = n_steps; L.bars = c->d_bars; L.tred = c->d_tred; L.records = rec_dev; L.smem_members = c->smem_members;
+    L.rep_base = c->d_rep; L.place = c->place; L.use_cluster = c->use_cluster;
     if (tape_dev) L.tape = *tape_dev;
     TRY(dev_zero(c, c->d_bars, sizeof(unsigned long long) * (c->n_teams + 1)));
     c->launches++;
 #ifdef SB_HOSTSIM
     hostsim::launch([&]() { sb_run_kernel(L); }, c->grid, c->block, c->smem);
 #else
-    void *args[] = {&L};
-    CK(cudaLaunchCooperativeKernel((void *)sb_run_kernel, dim3(c->grid), dim3(c->block), args, c->smem, c->stream));
+    if (c->use_cluster) {
+        cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(c->grid); cfg.blockDim = dim3(c->block); cfg.dynamicSmemBytes = c->smem; cfg.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = c->team; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, sb_run_kernel, L));
+    } else {
+        void *args[] = {&L};
+        CK(cudaLaunchCooperativeKernel((void *)sb_run_kernel, dim3(c->grid), dim3(c->block), args, c->smem, c->stream));
+    }
 #endif
     return 0;
 }
@@ -379,24 +453,24 @@ SB_API int sb_get_state(sb_ctx *c, int chain, int32_t *cluster_of, float *W, uin
     TRY(check_chain(c, chain));
     const SbProblem &P = c->P;
     SbSlot slot; TRY(get_slot(c, chain, &slot));
-    SbState &s = c->h_states[slot.state];
+    SbShared &s = c->h_states[slot.state];
     if (cluster_of) TRY(d2h(c, cluster_of, s.cluster_of, sizeof(int32_t) * P.N));
     if (W) TRY(d2h(c, W, s.W, sizeof(float) * P.F * P.C));
-    if (src || counts) {
+    if (src) {
 #ifdef SB_HOSTSIM
-        hostsim::launch([&]() { sb_export_kernel(P, s, c->d_src_tmp, c->d_counts_tmp); }, 2, 64, 0);
+        hostsim::launch([&]() { sb_export_kernel(P, s, c->d_src_tmp); }, 2, 64, 0);
 #else
-        sb_export_kernel<<<c->n_sm * 2, 256, 0, c->stream>>>(P, s, c->d_src_tmp, c->d_counts_tmp);
+        sb_export_kernel<<<c->n_sm * 2, 256, 0, c->stream>>>(P, s, c->d_src_tmp);
         CK(cudaGetLastError());
 #endif
         c->launches++;
-        if (src) {
+        {
             std::vector<uint8_t> sp((size_t)P.N * P.ldx);
             TRY(d2h(c, sp.data(), c->d_src_tmp, sp.size()));
             for (int o = 0; o < P.N; o++) memcpy(src + (size_t)o * P.F, &sp[(size_t)o * P.ldx], P.F);
         }
-        if (counts) TRY(d2h(c, counts, c->d_counts_tmp, sizeof(int32_t) * P.G_tot * P.F * P.S));
     }
+    if (counts) TRY(d2h(c, counts, s.counts, sizeof(int32_t) * P.G_tot * P.F * P.S));
     return 0;
 }
 
@@ -494,7 +568,7 @@ static int counts_common(sb_ctx *c, int chain, int32_t *counts_out, float *ms, b
     TRY(check_chain(c, chain));
     const SbProblem &P = c->P;
     SbSlot slot; TRY(get_slot(c, chain, &slot));
-    SbState &s = c->h_states[slot.state];
+    SbShared &s = c->h_states[slot.state];
     const size_t nG = (size_t)P.G_tot * P.F * P.S;
     TRY(dev_zero(c, c->d_counts_tmp, sizeof(int32_t) * nG));
     float t = 0.f;

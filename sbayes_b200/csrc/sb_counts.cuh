@@ -11,7 +11,7 @@
 SB_HD size_t sb_counts_hist_smem(const SbProblem &) { return 0; }
 
 // warp per object, lanes over features: coalesced reads of the two packed byte rows
-SB_KERNEL sb_counts_hist_kernel(SbProblem P, SbState st, int32_t *counts) {
+SB_KERNEL sb_counts_hist_kernel(SbProblem P, SbShared st, int32_t *counts) {
     const int F = P.F, S = P.S, C = P.C;
     const int nw = sb_nwarps();
     for (int o = sb_cta() * nw + sb_warp(); o < P.N; o += sb_ncta() * nw) {
@@ -31,10 +31,10 @@ SB_KERNEL sb_counts_hist_kernel(SbProblem P, SbState st, int32_t *counts) {
 }
 
 #ifndef SB_HOSTSIM
-static int sb_counts_hist_launch(const SbProblem &P, const SbState &st, int32_t *counts, int n_sm, cudaStream_t stream) {
+static int sb_counts_hist_launch(const SbProblem &P, const SbShared &st, int32_t *counts, int n_sm, cudaStream_t stream) {
     int grid = n_sm * 8;
     sb_counts_hist_kernel<<<grid, 256, 0, stream>>>(P, st, counts);
     return 0;
 }
-static int sb_counts_mma_launch(const SbProblem &, const SbState &, int32_t *, int, cudaStream_t) { return 1; }
+static int sb_counts_mma_launch(const SbProblem &, const SbShared &, int32_t *, int, cudaStream_t) { return 1; }
 #endif

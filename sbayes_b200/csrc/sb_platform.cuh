@@ -6,6 +6,7 @@
 // (test builds only, see tests/hostsim/hostsim.h) the same wrappers bind to a fibre
 // emulator so the control flow can be checked without a GPU.
 #pragma once
+#define SB_BLOCK 512   /* threads per CTA of the step kernel (product build) */
 #include <stdint.h>
 #include <math.h>
 
@@ -14,6 +15,7 @@
 #define SB_DEV inline
 #define SB_HD inline
 #define SB_KERNEL static void
+#define SB_KERNEL_BIG static void
 #define SB_RESTRICT
 SB_DEV int sb_tid() { return hostsim::tid(); }
 SB_DEV int sb_nthr() { return hostsim::nthr(); }
@@ -45,6 +47,7 @@ template <class T> SB_DEV T sb_ldg(const T *p) { return *p; }
 #define SB_DEV __device__ __forceinline__
 #define SB_HD __host__ __device__ __forceinline__
 #define SB_KERNEL __global__ void
+#define SB_KERNEL_BIG __global__ void __launch_bounds__(SB_BLOCK, 1)
 #define SB_RESTRICT __restrict__
 SB_DEV int sb_tid() { return threadIdx.x; }
 SB_DEV int sb_nthr() { return blockDim.x; }

@@ -41,44 +41,56 @@ struct SbProblem {
     const double *cost;          // [N, N] or null
     const int32_t *adj_ptr;      // [N+1] or null
     const int32_t *adj_idx;
+    const int32_t *cg_ptr;       // [sum conf groups + 1] CSR: members of every confounder group (sorted)
+    const int32_t *cg_idx;
 };
 
-// Everything one chain state owns in HBM.  Group-indexed rows (counts, tables, lh, geo) and
-// object-indexed rows (src) exist twice; `gsel[g]` / `osel[o]` say which copy is the
-// committed one, the other copy receives the candidate of the running proposal and a
-// commit is a flip of the selector (no copy, free rollback).
-struct SbState {
+// ---------------------------------------------------------------------------------------
+// State of one chain.
+//
+// (1) SbShared: what the whole team of CTAs that advances the chain shares, in HBM: the
+//     object-indexed arrays.  Source rows exist twice; osel[o] says which copy is committed,
+//     the other one receives the candidate of the running proposal (commit = set osel).
+// (2) SbRep: every CTA of the team keeps a *private replica* of the group-indexed state
+//     (counts, effect tables, per-group likelihoods, weight tables, the (pattern, feature,
+//     component) histogram, cluster sizes).  Replicas live in shared memory where they fit
+//     and in a private slice of HBM otherwise (SbPlace, decided by the host).  All CTAs
+//     apply the same proposal to their replica, so nothing group-indexed ever has to be
+//     exchanged inside a step; only sums over objects cross CTAs.
+// ---------------------------------------------------------------------------------------
+struct SbShared {
     int32_t *cluster_of;         // [N] committed membership, -1 = none
-    int32_t *cl_new;             // [N] candidate membership (== cluster_of outside a proposal)
-    int32_t *sizes;              // [K] committed cluster sizes
-    float *W;                    // [F, C]
     uint8_t *src[2];             // [N, ldx]
     uint8_t *osel;               // [N]
-    uint8_t *ochg;               // [N] object is part of the running proposal
-    int32_t *counts[2];          // [G_tot, F, S]
-    double *tabP[2];             // [G_tot, F, S] plain tables   norm(counts + alpha)
-    double *tabT[2];             // [G_tot, F, S] tempered tables norm(u + (alpha-u)/Tp + counts/T)
-    double *lh[2];               // [G_tot] per-group log-likelihood
-    double *geo_agg[2];          // [K] aggregated MST cost of every cluster
-    double *geo_val[2];          // [K] geo prior of every cluster
-    uint8_t *gsel;               // [G_tot]
-    uint8_t *dirty;              // [G_tot] group row is being re-proposed
-    int32_t *dneg, *dpos;        // [G_tot, F, S] observations removed / added by the proposal
-    int32_t *H;                  // [n_pat*2, F, C] #objects with has-pattern (p, z) whose source at f is c
-    double *w1, *wp, *wq, *lw;   // [n_pat*2, F, C] weight tables (see sb_core.cuh: weight_tables)
-    double *val;                 // [N] proposal probabilities
-    double *red_a, *red_b;       // [N] per-object partial sums
+    float *W;                    // [F, C]   import / export copy of the weights
+    int32_t *counts;             // [G_tot, F, S] export copy of the committed counts; rebuild scratch
+    int32_t *H;                  // [n_pat*2, F, C] rebuild scratch of the histogram
+    int32_t *sizes;              // [K] rebuild scratch
+    double *val[2];              // [N] proposal probabilities (alternating per pick)
     int32_t *list_a, *list_b;    // [N] compacted object lists
     uint8_t *flag_a, *flag_b;    // [N]
-    double *sc;                  // [64] scalars published inside a step
     double *post;                // [8] committed posterior terms {ll, size, geo, weights, source, i_step}
+};
+
+// replica arrays that may live in shared memory
+enum { A_WQ = 0, A_TABT, A_TABP, A_H0, A_H1, A_LW, A_COUNTS, A_WP, A_W1, A_DNEG, A_DPOS, A_N };
+
+struct SbPlace {
+    int in_smem[A_N];
+    unsigned smem_off[A_N];      // byte offset inside the dynamic shared memory (if in_smem)
+    size_t glob_off[A_N];        // byte offset inside the CTA's private HBM slice
+    size_t cand_off[3];          // candidate rows: counts, tabP, tabT (always in the HBM slice)
+    size_t sel_off;              // selbuf [N]
+    size_t rep_bytes;            // size of one CTA's private HBM slice
+    unsigned fixed_off;          // start of the always-in-smem small arrays
+    unsigned smem_bytes;         // total dynamic shared memory
 };
 
 struct SbSlot {
     sb_chain_cfg cfg;
     long long accepts[SB_N_OPS], rejects[SB_N_OPS];
     long long cycles[SB_N_OPS];  // SM clock cycles spent in each operator's steps (rank-0 CTA)
-    int state;                   // which SbState currently sits at this temperature
+    int state;                   // which SbShared currently sits at this temperature
     int err;
     int active;                  // a state has been uploaded
     int pad_;
@@ -86,13 +98,16 @@ struct SbSlot {
 
 struct SbLaunch {
     SbProblem P;
-    SbState *states;
+    SbShared *states;
     SbSlot *slots;
     int n_slots, team;
     long long n_steps;
     unsigned long long *bars;    // [n_teams] barrier counters (zeroed before launch)
     double *tred;                // [n_teams, 2, team, SB_REDW]
+    char *rep_base;              // [grid] private HBM slices of the CTAs
+    SbPlace place;
     sb_tape tape;                // device pointers; vals == null => Philox
     sb_step_record *records;     // [n_slots, n_steps] or null
     int smem_members;            // capacity of the shared-memory member list (geo prior)
+    int use_cluster;             // team == thread-block cluster: hardware cluster barrier
 };

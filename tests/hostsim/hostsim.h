@@ -65,7 +65,24 @@ inline void launch(std::function<void()> body, int n_cta, int n_thr, size_t smem
     grid() = &G;
     size_t alive = G.fibers.size();
     unsigned long rounds = 0;
+    // SB_HOSTSIM_SKEW=k: before every round one randomly favoured CTA runs k extra rounds on
+    // its own, so CTAs of a team drift apart as far as the barriers allow (exposes missing
+    // barriers between a fast CTA's writes and a slow CTA's reads).
+    const char *sk = getenv("SB_HOSTSIM_SKEW");
+    const int skew = sk ? atoi(sk) : 0;
+    unsigned long long lcg = 0x9E3779B97F4A7C15ull;
     while (alive) {
+        if (skew > 0) {
+            lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+            int fav = (int)((lcg >> 33) % (unsigned)n_cta);
+            for (int r = 0; r < skew; r++)
+                for (int t = 0; t < n_thr; t++) {
+                    Fiber &f = G.fibers[(size_t)fav * n_thr + t];
+                    if (f.done) continue;
+                    G.cur = &f;
+                    swapcontext(&G.sched, &f.ctx);
+                }
+        }
         alive = 0;
         for (auto &f : G.fibers) {
             if (f.done) continue;
