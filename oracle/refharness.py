@@ -112,77 +112,22 @@ def build_reference_model(x: np.ndarray, applicable: np.ndarray, locations: np.n
 
 
 def problem_from_reference(data, model) -> P.Problem:
-    """Packed `Problem` equivalent to a reference (Data, Model) pair."""
-    r = ref()
-    prior = model.prior
-    x = P.pack_onehot(data.features.values)
-    conf_gid, conf_ng, alpha_conf, names = [], [], [], []
-    for name, conf in data.confounders.items():
-        conf_gid.append(P.gid_from_bool(conf.group_assignment))
-        conf_ng.append(conf.n_groups)
-        cp = prior.prior_confounding_effects[name]
-        if cp.any_dynamic_priors:
-            raise NotImplementedError("hierarchical 'universal' prior type is rejected by the reference config")
-        alpha_conf.append(np.array(cp._concentration_array, dtype=np.float64))
-        names.append(name)
-    sp = prior.size_prior
-    size_type = {sp.PriorType.UNIFORM_AREA: P.SIZE_UNIFORM_AREA, sp.PriorType.UNIFORM_SIZE: P.SIZE_UNIFORM_SIZE,
-                 sp.PriorType.QUADRATIC_SIZE: P.SIZE_QUADRATIC}[sp.prior_type]
-    gp = prior.geo_prior
-    geo = None
-    if gp.prior_type is gp.PriorTypes.COST_BASED:
-        GC = r.config.GeoPriorConfig
-        if gp.config.skeleton is not GC.Skeleton.MST:
-            raise NotImplementedError("only the MST skeleton is supported")
-        geo = P.GeoPriorSpec(
-            cost=np.array(gp.cost_matrix, dtype=np.float64),
-            aggregation={GC.AggregationStrategies.MEAN: P.AGG_MEAN, GC.AggregationStrategies.SUM: P.AGG_SUM,
-                         GC.AggregationStrategies.MAX: P.AGG_MAX}[gp.aggregation_policy],
-            prob_fn={GC.ProbabilityFunction.EXPONENTIAL: P.PF_EXPONENTIAL,
-                     GC.ProbabilityFunction.SIGMOID: P.PF_SIGMOID}[gp.probability_function],
-            rate=float(gp.scale), inflection=float(gp.inflection_point or 0.0))
-    elif gp.prior_type is not gp.PriorTypes.UNIFORM:
-        raise NotImplementedError(f"geo prior {gp.prior_type}")
-    wp = prior.prior_weights
-    adj = data.network.adj_mat.tocsr()
-    return P.Problem(
-        x=x, applicable=np.array(data.features.states, dtype=bool),
-        conf_gid=conf_gid, conf_ngroups=conf_ng,
-        alpha_cluster=np.array(prior.prior_cluster_effect.concentration_array, dtype=np.float64),
-        alpha_conf=alpha_conf,
-        alpha_w=np.array(wp.concentration_array, dtype=np.float64),
-        n_clusters=model.n_clusters, min_size=int(model.min_size), max_size=int(model.max_size),
-        size_prior=size_type, weights_prior_uniform=(wp.prior_type is wp.PriorType.UNIFORM),
-        geo=geo, adj_indptr=np.array(adj.indptr, dtype=np.int32), adj_indices=np.array(adj.indices, dtype=np.int32),
-        conf_names=names)
+    """Packed `Problem` equivalent to a reference (Data, Model) pair (the product's own
+    converter, sbayes_b200/refbridge.py)."""
+    from sbayes_b200 import refbridge
+    return refbridge.problem_from_reference(data, model)
 
 
 def state_from_sample(prob: P.Problem, sample) -> P.ChainState:
     """Reference `Sample` -> packed `ChainState` (counts stacked [G_tot,F,S] int32)."""
-    src = P.pack_onehot(sample.source.value)
-    parts = [sample.feature_counts["clusters"].value]
-    parts += [sample.feature_counts[n].value for n in prob.conf_names]
-    counts = np.concatenate(parts, axis=0)
-    assert np.all(counts == np.round(counts))
-    return P.ChainState(cluster_of=P.cluster_of_from_bool(sample.clusters.value),
-                        W=np.array(sample.weights.value, dtype=np.float32),
-                        src=src, counts=counts.astype(np.int32))
+    from sbayes_b200 import refbridge
+    return refbridge.state_from_sample(prob, sample)
 
 
 def sample_from_state(prob: P.Problem, model, data, st: P.ChainState, i_step: int = 0):
     """Packed `ChainState` -> reference `Sample` (fresh caches)."""
-    r = ref()
-    offs = prob.group_offsets()
-    counts = st.counts
-    if counts is None:
+    from sbayes_b200 import refbridge
+    if st.counts is None:
         from .model import rebuild_counts
-        counts = rebuild_counts(prob, st)
-    fc = {"clusters": counts[offs[0]:offs[1]].astype(np.float32)}
-    for i, n in enumerate(prob.conf_names):
-        fc[n] = counts[offs[i + 1]:offs[i + 2]].astype(np.float32)
-    s = r.state.Sample.from_numpy_arrays(
-        clusters=st.clusters_bool(prob.K), weights=st.W.copy(), confounders=data.confounders,
-        source=P.unpack_onehot(st.src, prob.C), feature_counts=fc, model_shapes=model.shapes)
-    s.i_step = i_step
-    s.everything_changed()
-    return s
+        st = P.ChainState(st.cluster_of, st.W, st.src, rebuild_counts(prob, st))
+    return refbridge.sample_from_state(prob, model, data, st, ref().state.Sample, i_step=i_step)

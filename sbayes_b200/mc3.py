@@ -124,8 +124,8 @@ class DeviceMC3:
         import torch
         import torch.distributed as dist
         dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
-        t = torch.from_numpy(local).to(dev)
-        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=dev)
+        t = torch.from_numpy(np.ascontiguousarray(local)).to(dev).reshape(-1)
+        out = torch.empty(self.world * t.numel(), dtype=t.dtype, device=dev)
         dist.all_gather_into_tensor(out, t)
         return out.cpu().numpy().reshape(self.n_total, 2)
 
