@@ -22,7 +22,7 @@ def sources():
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(s) for s in sources()):
         return OUT
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, "sb_api.cu"), "-lcudart", "-o", OUT]
+    cmd = [NVCC] + FLAGS + os.environ.get("SB_CFLAGS", "").split() + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, "sb_api.cu"), "-lcudart", "-o", OUT]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode:
         sys.stderr.write(r.stdout + r.stderr)

@@ -11,9 +11,23 @@
 #include <cmath>
 #include <algorithm>
 #include <map>
+#include <functional>
 
+// the step kernel, instantiated for up to 4 and up to 8 mixture components (the loops over
+// components are unrolled to that width; the narrow one is what the reference's configs need)
+#define SB_UC 4
+#define SB_NS uc4
 #include "sb_core.cuh"
+#undef SB_UC
+#undef SB_NS
+#define SB_UC 8
+#define SB_NS uc8
+#include "sb_core.cuh"
+#undef SB_UC
+#undef SB_NS
 #include "sb_counts.cuh"
+using uc4::FixedSmem; using uc4::sb_fixed_smem; using uc4::Draws; using uc4::Philox4; using uc4::philox4x32_10; using uc4::u01_double;
+using uc4::sb_export_kernel;
 
 #ifdef SB_HOSTSIM
 #define SB_API extern "C" __attribute__((visibility("default")))
@@ -34,7 +48,11 @@ struct sb_ctx {
     SbShared *d_states = nullptr;
     SbPlace place;
     char *d_rep = nullptr;
-    int use_cluster = 0;
+    int use_cluster = 0, req_team = 0;
+    size_t rep_alloc = 0;
+    const void *kernel = nullptr;
+    std::function<int(int, int)> place_fn;
+    std::vector<sb_chain_cfg> h_cfg;
     std::vector<int32_t> cg_ptr, cg_idx;
     SbSlot *d_slots = nullptr;
     unsigned long long *d_bars = nullptr;
@@ -108,7 +126,7 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
     const int N = d->n_objects, F = d->n_features, S = d->n_states, K = d->n_clusters, nc = d->n_confounders;
     const int C = 1 + nc;
     if (N <= 0 || F <= 0 || S <= 0 || S > 254 || K <= 0 || K > SB_MAXK) return fail(c, "bad problem dimensions");
-    if (C > SB_MAXC) return fail(c, "too many mixture components (max 8)");
+    if (C > SB_MAX_COMPONENTS) return fail(c, "too many mixture components (max 8)");
     if (n_chains <= 0) return fail(c, "n_chains must be positive");
     c->device = device; c->n_chains = n_chains;
 #ifndef SB_HOSTSIM
@@ -152,16 +170,52 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
     }
     P.n_pat = (int)pat_bits.size();
     TRY(up(c, &P.pat_id, pat_id)); TRY(up(c, &P.pat_bits, pat_bits));
-    // concentrations and the count-independent part of the Dirichlet-categorical marginal
-    const size_t nG = (size_t)P.G_tot * F * S;
-    std::vector<double> alpha(d->alpha, d->alpha + nG), asum((size_t)P.G_tot * F), dcc((size_t)P.G_tot * F), unif((size_t)F * S);
-    for (size_t gf = 0; gf < (size_t)P.G_tot * F; gf++) {
-        double sa = 0.0, sl = 0.0;
-        for (int s = 0; s < S; s++) { double a = alpha[gf * S + s]; sa += a; if (a > 0.0) sl += lgamma(a); }
-        asum[gf] = sa; dcc[gf] = lgamma(sa) - sl;
+    // distinct tuples of confounder groups ("combos", sb_types.h)
+    {
+        std::map<std::vector<int>, int> combo_index;
+        std::vector<int32_t> combo_id(N), combo_rows, combo_pat;
+        for (int o = 0; o < N; o++) {
+            std::vector<int> key(nc);
+            for (int i = 0; i < nc; i++) key[i] = gid[(size_t)i * N + o];
+            auto it = combo_index.find(key);
+            if (it == combo_index.end()) {
+                it = combo_index.emplace(key, (int)combo_pat.size()).first;
+                for (int i = 0; i < nc; i++) combo_rows.push_back(key[i] < 0 ? -1 : P.goff[i + 1] + key[i]);
+                combo_pat.push_back(pat_id[o]);
+            }
+            combo_id[o] = it->second;
+        }
+        P.n_combos = (int)combo_pat.size();
+        if (combo_rows.empty()) combo_rows.push_back(-1);
+        TRY(up(c, &P.combo_id, combo_id)); TRY(up(c, &P.combo_rows, combo_rows)); TRY(up(c, &P.combo_pat, combo_pat));
+        // per-combo pass tables: 16 B per (combo, feature, state) and CTA
+        P.use_tables = (size_t)P.n_combos * F * S * 16 <= ((size_t)8 << 20);
+#ifdef SB_HOSTSIM
+        if (getenv("SB_NO_TABLES")) P.use_tables = 0;
+#endif
     }
-    for (size_t i = 0; i < unif.size(); i++) unif[i] = d->applicable[i] ? 1.0 : 0.0;
-    TRY(up(c, &P.alpha, alpha)); TRY(up(c, &P.asum, asum)); TRY(up(c, &P.dcc, dcc)); TRY(up(c, &P.unif, unif));
+    // concentrations and the count-independent part of the Dirichlet-categorical marginal;
+    // the K cluster rows are stored once when they are identical
+    const size_t nG = (size_t)P.G_tot * F * S;
+    {
+        const size_t FS = (size_t)F * S;
+        bool same = true;
+        for (int k = 1; k < K && same; k++) same = memcmp(d->alpha, d->alpha + (size_t)k * FS, FS * sizeof(double)) == 0;
+        P.dedup = same ? 1 : 0; P.arow_off = same ? K - 1 : 0; P.A_rows = P.G_tot - P.arow_off;
+        const double *src = d->alpha + (size_t)P.arow_off * FS;
+        std::vector<double> alpha(src, src + (size_t)P.A_rows * FS), asum((size_t)P.A_rows * F), dcc((size_t)P.A_rows * F), unif(FS);
+        for (size_t gf = 0; gf < (size_t)P.A_rows * F; gf++) {
+            double sa = 0.0, sl = 0.0;
+            for (int s = 0; s < S; s++) { double a = alpha[gf * S + s]; sa += a; if (a > 0.0) sl += lgamma(a); }
+            asum[gf] = sa; dcc[gf] = lgamma(sa) - sl;
+        }
+        for (size_t i = 0; i < unif.size(); i++) unif[i] = d->applicable[i] ? 1.0 : 0.0;
+        P.use_mask = S <= 64;
+        std::vector<uint64_t> applm(F, 0);
+        if (P.use_mask) for (int f = 0; f < F; f++) for (int s = 0; s < S; s++) if (d->applicable[(size_t)f * S + s]) applm[f] |= 1ull << s;
+        TRY(up(c, &P.alpha, alpha)); TRY(up(c, &P.asum, asum)); TRY(up(c, &P.dcc, dcc)); TRY(up(c, &P.unif, unif));
+        TRY(up(c, &P.applm, applm));
+    }
     std::vector<double> aw(d->alpha_w, d->alpha_w + (size_t)F * C), wlnB(F);
     for (int f = 0; f < F; f++) {
         double sa = 0.0, sl = 0.0;
@@ -190,15 +244,26 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
     if (P.geo) c->smem_members = std::max(c->smem_members, std::min(std::max(P.max_size + 1, 32), N));
     if (c->smem_members > 8192) return fail(c, "geo prior: max cluster size above 8192 is not supported");
 
-    // replica placement: shared memory first (most reused arrays first), HBM slice otherwise
+    // replica placement: shared memory first (priority = enum order of sb_types.h), HBM slice otherwise
     const size_t nS = (size_t)N * P.ldx, nH = (size_t)P.n_pat * 2 * F * C;
-    {
+    c->req_team = team;
+    c->place_fn = [c, N, F, S, K, C, nG, nH, device](int team_for_xblk, int alias_w) -> int {
+        const SbProblem &P = c->P;
         SbPlace &pl = c->place;
         memset(&pl, 0, sizeof(pl));
+        const size_t nGF = (size_t)P.G_tot * F, nT = P.use_tables ? (size_t)P.n_combos * F * S : 1;
         size_t bytes[A_N];
-        bytes[A_WQ] = nH * 8; bytes[A_TABT] = nG * 8; bytes[A_TABP] = nG * 8; bytes[A_H0] = nH * 4; bytes[A_H1] = nH * 4;
-        bytes[A_LW] = nH * 8; bytes[A_COUNTS] = nG * 4; bytes[A_WP] = nH * 8; bytes[A_W1] = nH * 8;
-        bytes[A_DNEG] = nG * 4; bytes[A_DPOS] = nG * 4;
+        bytes[A_TAB0] = nT * 8; bytes[A_TAB1] = nT * 8; bytes[A_WQ] = nH * 8; bytes[A_COUNTS] = nG * 4; bytes[A_NN] = nGF * 4;
+        bytes[A_RT] = nGF * 8; bytes[A_RP] = nGF * 8; bytes[A_WP] = alias_w ? 0 : nH * 8; bytes[A_W1] = alias_w ? 0 : nH * 8; bytes[A_LW] = nH * 8;
+        bytes[A_H0] = nH * 4; bytes[A_H1] = nH * 4; bytes[A_DCNT] = nG * 4; bytes[A_LLGF] = nGF * 8; bytes[A_BST] = nGF * 8;
+        bytes[A_BK_LLGF] = nGF * 8; bytes[A_BK_RP] = nGF * 8; bytes[A_BK_RT] = nGF * 8;
+        bytes[A_ALPHA] = (size_t)P.A_rows * F * S * 8; bytes[A_ASUM] = (size_t)P.A_rows * F * 8;
+        bytes[A_APPLM] = P.use_mask ? (size_t)F * 8 : 0;
+        bytes[A_MCL] = K < 32767 ? (size_t)N * 2 : 0; bytes[A_MCOMBO] = P.n_combos < 65535 ? (size_t)N * 2 : 0; bytes[A_MOSEL] = (size_t)N;
+        bytes[A_COMBOT] = (size_t)P.n_combos * (P.n_conf + 1) * 4;
+        pl.alias_w = alias_w;
+        pl.xblk_rows = team_for_xblk > 0 ? (N + team_for_xblk - 1) / team_for_xblk : 0;
+        bytes[A_XBLK] = (size_t)pl.xblk_rows * P.ldx;
         size_t budget = 200 * 1024;
 #ifdef SB_HOSTSIM
         const char *eb2 = getenv("SB_HOSTSIM_SMEM");
@@ -210,21 +275,25 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
 #endif
         FixedSmem fx0 = sb_fixed_smem(P.G_tot, K, F, C, c->smem_members, 0);
         if (fx0.end + 1024 > budget) return fail(c, "problem too large for the fixed shared-memory part of the step kernel");
+        // arrays that only exist in shared memory (the global originals serve otherwise)
+        auto smem_only = [](int a) { return a == A_XBLK || a == A_ALPHA || a == A_ASUM || a == A_APPLM || a == A_MCL || a == A_MCOMBO || a == A_MOSEL || a == A_COMBOT; };
         size_t soff = 0, goff = 0;
         for (int a = 0; a < A_N; a++) {
             size_t b = (bytes[a] + 15) & ~(size_t)15;
-            pl.glob_off[a] = goff; goff += b;
-            if (soff + b + fx0.end + 256 <= budget) { pl.in_smem[a] = 1; pl.smem_off[a] = (unsigned)soff; soff += b; }
+            pl.glob_off[a] = goff;
+            if (!smem_only(a)) goff += b;
+            if (b > 0 && soff + b + fx0.end + 256 <= budget) { pl.in_smem[a] = 1; pl.smem_off[a] = (unsigned)soff; soff += b; }
         }
-        pl.cand_off[0] = goff; goff += (nG * 4 + 15) & ~(size_t)15;
-        pl.cand_off[1] = goff; goff += nG * 8;
-        pl.cand_off[2] = goff; goff += nG * 8;
+        if (!pl.in_smem[A_XBLK]) pl.xblk_rows = 0;
         pl.sel_off = goff; goff += ((size_t)N + 15) & ~(size_t)15;
         pl.rep_bytes = (goff + 255) & ~(size_t)255;
         pl.fixed_off = (unsigned)soff;
         pl.smem_bytes = sb_fixed_smem(P.G_tot, K, F, C, c->smem_members, pl.fixed_off).end;
         c->smem = pl.smem_bytes;
-    }
+        return 0;
+    };
+    auto place = [c](int t) { return c->place_fn(t, 0); };
+    TRY(place(0));
 
     // launch geometry: teams of `team` CTAs; a team of <= 16 CTAs is a thread-block cluster
 #ifdef SB_HOSTSIM
@@ -233,10 +302,11 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
     int capacity = 64;
 #else
     c->block = SB_BLOCK;
-    CK(cudaFuncSetAttribute(sb_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
-    CK(cudaFuncSetAttribute(sb_run_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    c->kernel = C <= 4 ? (const void *)uc4::sb_run_kernel : (const void *)uc8::sb_run_kernel;
+    CK(cudaFuncSetAttribute(c->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
+    CK(cudaFuncSetAttribute(c->kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sb_run_kernel, c->block, c->smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, c->kernel, c->block, c->smem));
     if (per_sm < 1) return fail(c, "step kernel does not fit on an SM");
     int capacity = per_sm * c->n_sm;
 #endif
@@ -257,7 +327,7 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
         cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = team; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         int n_clusters = 0;
-        if (cudaOccupancyMaxActiveClusters(&n_clusters, sb_run_kernel, &cfg) == cudaSuccess && n_clusters >= 1) {
+        if (cudaOccupancyMaxActiveClusters(&n_clusters, c->kernel, &cfg) == cudaSuccess && n_clusters >= 1) {
             c->use_cluster = 1;
             capacity = n_clusters * team;
         } else cudaGetLastError();
@@ -265,6 +335,11 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
 #endif
     c->n_teams = std::max(1, std::min(n_chains, capacity / team));
     c->grid = c->n_teams * team;
+    // worst-case private slice (no aliasing); the placement itself is recomputed at every launch
+    TRY(c->place_fn(team, 0));
+    c->rep_alloc = c->place.rep_bytes;
+    c->h_cfg.assign(n_chains, sb_chain_cfg());
+    for (int i = 0; i < n_chains; i++) { c->h_cfg[i].temperature = 1.0; c->h_cfg[i].prior_temperature = 1.0; }
 
     // per-chain shared state and per-CTA replica slices
     c->h_states.resize(n_chains);
@@ -276,7 +351,7 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
         TRY(mk(c, &s.list_a, N)); TRY(mk(c, &s.list_b, N)); TRY(mk(c, &s.flag_a, N)); TRY(mk(c, &s.flag_b, N));
         TRY(mk(c, &s.post, 8));
     }
-    TRY(mk(c, &c->d_rep, c->place.rep_bytes * (size_t)c->grid));
+    TRY(mk(c, &c->d_rep, c->rep_alloc * (size_t)c->grid));
     TRY(mk(c, &c->d_states, n_chains)); TRY(h2d(c, c->d_states, c->h_states.data(), sizeof(SbShared) * n_chains));
     std::vector<SbSlot> slots(n_chains);
     memset(slots.data(), 0, sizeof(SbSlot) * n_chains);
@@ -314,6 +389,7 @@ static int get_slot(sb_ctx *c, int chain, SbSlot *s) { return d2h(c, s, c->d_slo
 SB_API int sb_chain_config(sb_ctx *c, int chain, const sb_chain_cfg *cfg) {
     TRY(check_chain(c, chain));
     if (!(cfg->temperature > 0) || !(cfg->prior_temperature > 0)) return fail(c, "temperatures must be positive");
+    c->h_cfg[chain] = *cfg;
     return h2d(c, &c->d_slots[chain].cfg, cfg, sizeof(sb_chain_cfg));
 }
 
@@ -346,16 +422,24 @@ SB_API int sb_set_state(sb_ctx *c, int chain, const int32_t *cluster_of, const f
 }
 
 static int launch(sb_ctx *c, long long n_steps, const sb_tape *tape_dev, sb_step_record *rec_dev) {
+    int alias_w = 1;
+    for (const sb_chain_cfg &g : c->h_cfg) if (g.prior_temperature != 1.0) alias_w = 0;
+    TRY(c->place_fn(c->team, alias_w));
+    if (c->place.rep_bytes > c->rep_alloc) return fail(c, "internal: replica slice larger than allocated");
+#ifndef SB_HOSTSIM
+    CK(cudaFuncSetAttribute(c->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
+#endif
     SbLaunch L;
     memset(&L, 0, sizeof(L));
     L.P = c->P; L.states = c->d_states; L.slots = c->d_slots; L.n_slots = c->n_chains; L.team = c->team;
     L.n_steps = n_steps; L.bars = c->d_bars; L.tred = c->d_tred; L.records = rec_dev; L.smem_members = c->smem_members;
-    L.rep_base = c->d_rep; L.place = c->place; L.use_cluster = c->use_cluster;
+    L.rep_base = c->d_rep; L.place = c->place; L.use_cluster = c->use_cluster; L.rep_stride = c->rep_alloc;
     if (tape_dev) L.tape = *tape_dev;
     TRY(dev_zero(c, c->d_bars, sizeof(unsigned long long) * (c->n_teams + 1)));
     c->launches++;
 #ifdef SB_HOSTSIM
-    hostsim::launch([&]() { sb_run_kernel(L); }, c->grid, c->block, c->smem);
+    if (c->P.C <= 4) hostsim::launch([&]() { uc4::sb_run_kernel(L); }, c->grid, c->block, c->smem);
+    else hostsim::launch([&]() { uc8::sb_run_kernel(L); }, c->grid, c->block, c->smem);
 #else
     if (c->use_cluster) {
         cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
@@ -363,10 +447,11 @@ static int launch(sb_ctx *c, long long n_steps, const sb_tape *tape_dev, sb_step
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = c->team; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        CK(cudaLaunchKernelEx(&cfg, sb_run_kernel, L));
+        void *args[] = {&L};
+        CK(cudaLaunchKernelExC(&cfg, c->kernel, args));
     } else {
         void *args[] = {&L};
-        CK(cudaLaunchCooperativeKernel((void *)sb_run_kernel, dim3(c->grid), dim3(c->block), args, c->smem, c->stream));
+        CK(cudaLaunchCooperativeKernel(c->kernel, dim3(c->grid), dim3(c->block), args, c->smem, c->stream));
     }
 #endif
     return 0;
@@ -595,3 +680,19 @@ static int counts_common(sb_ctx *c, int chain, int32_t *counts_out, float *ms, b
 }
 SB_API int sb_counts_rebuild_hist(sb_ctx *c, int chain, int32_t *counts_out, float *ms) { return counts_common(c, chain, counts_out, ms, false); }
 SB_API int sb_counts_rebuild_mma(sb_ctx *c, int chain, int32_t *counts_out, float *ms) { return counts_common(c, chain, counts_out, ms, true); }
+
+#if defined(SB_PHASE_PROF) && !defined(SB_HOSTSIM)
+// debug builds only (not part of the ABI): phase cycle counters of the step kernel
+SB_API int sb_debug_phases(sb_ctx *c, long long *phase /* [SB_N_OPS * SB_NPH] */, long long *n /* [SB_N_OPS] */, int reset) {
+    if (!c) return -1;
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpyFromSymbol(phase, uc4::g_phase, sizeof(long long) * SB_N_OPS * SB_NPH));
+    CK(cudaMemcpyFromSymbol(n, uc4::g_phase_n, sizeof(long long) * SB_N_OPS));
+    if (reset) {
+        static long long z[SB_N_OPS * SB_NPH];
+        CK(cudaMemcpyToSymbol(uc4::g_phase, z, sizeof(long long) * SB_N_OPS * SB_NPH));
+        CK(cudaMemcpyToSymbol(uc4::g_phase_n, z, sizeof(long long) * SB_N_OPS));
+    }
+    return 0;
+}
+#endif

@@ -11,20 +11,41 @@
 // is split across the team by contiguous object blocks; its sums cross CTAs through
 // `team_sum` / `team_pick` / `team_compact`, which end in a team barrier and leave the
 // *same* value in every thread, so all control flow is uniform across the team.
-// Everything group-indexed (counts, effect tables, per-group likelihoods, weight tables,
-// the source histogram) is kept as a private replica per CTA (shared memory where it
-// fits): every CTA applies the same proposal to its replica, redundantly, which removes
-// all barriers and L2 round trips from the resampling / table-update / accept phases.
-// Object-indexed state in HBM is written by *all* CTAs with identical values, so each CTA
-// always observes its own writes; barriers are only needed to keep a fast CTA's commit
-// from overtaking a slow CTA's reads (one barrier between the last read and the commit).
+// Everything group-indexed (counts, per-(group, feature) totals, reciprocals and
+// log-likelihood terms, weight tables, the source histogram) is kept as a private replica
+// per CTA (shared memory where it fits): every CTA applies the same proposal to its replica
+// *in place*, redundantly, and undoes it on a reject, which removes all barriers and L2
+// round trips from the resampling / table-update / accept phases.  Object-indexed state in
+// HBM is written by *all* CTAs with identical values, so each CTA always observes its own
+// writes; barriers are only needed to keep a fast CTA's commit from overtaking a slow CTA's
+// reads (one barrier between the last read and the commit).
+//
+// Arithmetic.  Sums of logs over features are accumulated as products with a separately
+// tracked binary exponent (`Prod`): one fp64 multiply per observation instead of one `log`.
+// The passes over many objects gather from per-combo tables A0 / A1 (`build_tables`): a
+// combo is a distinct tuple of confounder groups, so all objects of a combo see the same
+// confounder mixture sum_c p_c[f, x] * w_c; per observation that is one byte load, two
+// 8-byte table loads and two multiplies.  Log-likelihood terms are updated by
+// lgamma(z + d) - lgamma(z) = sum log (for the few counts a proposal changes) instead of
+// re-evaluating lgamma over whole rows.
 //
 // What follows which reference code is cited function by function; the algorithmic
 // specification is SURVEY.md Appendix A, the executable one is oracle/operators.py.
-#pragma once
+// This file is compiled once per unroll width of the mixture-component loops: the includer
+// defines SB_UC (4 or 8: the largest number of components the instantiation handles) and
+// SB_NS (the namespace the instantiation lives in); see sb_api.cu.
 #include "sb_platform.cuh"
 #include "sb_types.h"
+#ifndef SB_UC
+#error "define SB_UC and SB_NS before including sb_core.cuh"
+#endif
+namespace SB_NS {
 
+#undef SB_FOR_C
+#undef SB_FOR_C1
+#undef PH
+#undef SB_NPH
+#ifndef SB_EPS32
 #define SB_EPS32 1.1920928955078125e-07   /* np.finfo(np.float32).eps, sbayes/util.py:34 */
 #define SB_SMOOTH 1e-6                    /* additive smoothing, sbayes/sampling/operators.py:978 */
 #define SB_W_STAY 0.15                    /* operators.py:133 */
@@ -32,15 +53,36 @@
 #define SB_SRC_MIN 10                     /* operators.py:440 */
 #define SB_SRC_MAX_RANDOM 20              /* operators.py:185 */
 #define SB_SRC_MAX_GROUPS 30              /* operators.py:194 */
+#define SB_LN2 0.6931471805599453
+#endif
+// loops over the mixture components are unrolled to the compile-time maximum and guarded, so
+// that the per-component arrays stay in registers (a runtime trip count puts them in local memory)
+#ifdef SB_HOSTSIM
+#define SB_FOR_C(c, C) for (int c = 0; c < (C); c++)
+#define SB_FOR_C1(c, C) for (int c = 1; c < (C); c++)
+#else
+#define SB_FOR_C(c, C) _Pragma("unroll") for (int c = 0; c < SB_UC; c++) if (c < (C))
+#define SB_FOR_C1(c, C) _Pragma("unroll") for (int c = 1; c < SB_UC; c++) if (c < (C))
+#endif
 
+#ifndef SB_INF
 #ifdef SB_HOSTSIM
 #define SB_INF (__builtin_inf())
 #else
 #define SB_INF (__longlong_as_double(0x7ff0000000000000LL))
 #endif
+#endif
 
-// scalars published in st.sc[] during a step
-enum { SC_LQ = 0, SC_LQB, SC_SP_NEW, SC_GEO_NEW, SC_WP_NEW, SC_AUX0, SC_AUX1, SC_AUX2, SC_AUX3 };
+// phase profiling (debug builds with -DSB_PHASE_PROF only): cycles of thread 0 of the rank-0
+// CTA between consecutive probes, per operator
+#if defined(SB_PHASE_PROF) && !defined(SB_HOSTSIM)
+#define SB_NPH 48
+__device__ long long g_phase[SB_N_OPS][SB_NPH];
+__device__ long long g_phase_n[SB_N_OPS];
+#define PH(R, id) do { if (sb_tid() == 0 && (R).rank == 0) { long long t_ = clock64(); g_phase[(R).cur_op][id] += t_ - (R).pt; (R).pt = t_; } } while (0)
+#else
+#define PH(R, id) do { } while (0)
+#endif
 
 // -----------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011); stream addressing identical to oracle/philox.py
@@ -78,7 +120,7 @@ SB_DEV Philox4 draw_words(const Draws &D, int site, int sub, uint32_t idx) {
     return philox4x32_10(idx, c1, (uint32_t)(D.step & 0xFFFFFFFFull), (uint32_t)(D.step >> 32), D.k0, D.k1);
 }
 SB_DEV double draw_uniform(const Draws &D, int site, uint32_t idx = 0, int sub = 0) {
-    if (D.tv) return D.tv[D.toff[site] + idx];
+    if (D.tv) return D.toff[site] >= 0 ? D.tv[D.toff[site] + idx] : 0.0;   // absent: the reference did not draw here
     Philox4 p = draw_words(D, site, sub, idx);
     return u01_double(p.w[0], p.w[1]);
 }
@@ -128,59 +170,101 @@ SB_DEV double draw_beta(const Draws &D, double a, double b, uint32_t f) {
 }
 
 // -----------------------------------------------------------------------------------------
+// products with a separately tracked binary exponent: sum_f log a_f == log(prod a_f)
+// -----------------------------------------------------------------------------------------
+struct Prod { double m; int e; };
+SB_DEV Prod prod_one() { Prod p; p.m = 1.0; p.e = 0; return p; }
+SB_DEV void prod_renorm(Prod &p) {      // move the exponent of m into e (zero / inf / nan / denormals are left alone)
+    long long b = sb_d2ll(p.m);
+    int ex = (int)((b >> 52) & 0x7ff);
+    if (ex != 0 && ex != 0x7ff) {
+        p.e += ex - 1023;
+        p.m = sb_ll2d((b & ~(0x7ffLL << 52)) | (1023LL << 52));
+    }
+}
+SB_DEV double prod_log(const Prod &p) { return log(p.m) + (double)p.e * SB_LN2; }
+
+// -----------------------------------------------------------------------------------------
 // per-CTA replica of the group-indexed state, and the run context
 // -----------------------------------------------------------------------------------------
 struct Rep {
-    int32_t *counts;  double *tabP, *tabT;            // committed [G_tot, F, S]
-    int32_t *c_counts; double *c_tabP, *c_tabT;       // candidate rows (valid where dirty[g])
-    int32_t *dneg, *dpos;                             // [G_tot, F, S] observations removed / added by the proposal
+    int32_t *counts;                                  // [G_tot, F, S] current counts (candidate while a proposal is open)
+    int32_t *nn;                                      // [G_tot, F]    sum_s counts
+    int32_t *dcnt;                                    // [G_tot, F, S] net change of the open proposal (zero between steps)
+    double *rP, *rT;                                  // [G_tot, F]    1 / (sum alpha + n),  1 / (sum tempered base + n / T)
+    double *bsT;                                      // [G_tot, F]    sum_s (u + (alpha - u) / Tp)
+    double *llgf;                                     // [G_tot, F]    Dirichlet-categorical term of (group, feature)
+    double *bk_llgf, *bk_rP, *bk_rT;                  // backups of the dirty rows (undo)
     int32_t *H[2];                                    // [n_pat*2, F, C]; H[hcur] committed, the other one candidate
     double *w1, *wp, *wq, *lw;                        // [n_pat*2, F, C] weight tables
-    double *lh, *c_lh;                                // [G_tot] per-group log-likelihood
+    double *tab0, *tab1;                              // [n_combos, F, S] pass tables (build_tables)
+    const uint8_t *xblk;                              // the CTA's own block of observation rows, or null
+    int xlo, xhi;
+    double *lh, *bk_lh;                               // [G_tot] per-group log-likelihood
     double *geo_agg, *geo_val, *c_geo_agg, *c_geo_val;// [K]
     float *W;                                         // [F, C]
     int32_t *sizes, *ssz;                             // [K] committed / candidate cluster sizes
     uint8_t *dirty;                                   // [G_tot]
+    int *dlist;                                       // [G_tot] dirty rows of the open proposal
     uint8_t *selbuf;                                  // [N] which source copy becomes the committed one, per changed object
-    int hcur;
 };
 
 enum { CHG_NONE = 0, CHG_ONE, CHG_WIDE };
 
-struct Run {
-    const SbProblem *P;
+// What is uniform over the CTA and constant while a chain is being advanced lives once per CTA
+// in shared memory (RunC); only the few mutable scalars of the step stay in registers (Run).
+// (Keeping all of it per thread spills ~2 KB per thread to local memory, which the shared
+// memory carve-out leaves no L1 for.)
+struct RunC {
     SbShared st;
     Rep rp;
+    // problem constants and per-object state staged in shared memory where they fit (else the
+    // pointers address the global copies; mcl / mcombo / mosel are null then)
+    const double *alpha, *asum;  // [A_rows, F, S], [A_rows, F]
+    const uint64_t *applm;       // [F] bit s set <=> state s applicable
+    const int32_t *combo_rows, *combo_pat;
+    int16_t *mcl;                // [N] replica of the cluster membership
+    uint16_t *mcombo;            // [N]
+    uint8_t *mosel;              // [N] replica of osel
     SbSlot *slot;
-    Draws D;
-    double T, Tp, invT, invTp, p_grow;
-    int sfp;
-    int tsize, rank, par, vpar, use_cluster;
+    double opw[SB_N_OPS];
     unsigned long long *bar;
-    unsigned long long epoch;
     double *tred;      // [2][tsize][SB_REDW] team reduction scratch
-    double *sred;      // smem [32 * SB_REDW]
+    double *sred;      // smem [2][32 * SB_REDW]
     int *sint;         // smem [96]
     int *slist;        // smem [32] small list of changed objects
     int *smem_mem;     // smem member list (geo)
     double *smem_best; // smem Prim keys (geo)
     int smem_cap;
+};
+
+struct Run {
+    const SbProblem *P;
+    RunC *c;
+    Draws D;
+    double T, Tp, invT, invTp, p_grow;
+    int sfp;
+    int tsize, rank, par, vpar, spar, use_cluster, hcur;
+    unsigned long long epoch;
+    int nd;            // number of dirty rows of the open proposal
     // candidate membership view
     int chg_mode, chg_o, chg_new, chg_k;
     // committed posterior terms: kept in registers by every thread (uniform across the team)
     double ll, pr_size, pr_geo, pr_w, pr_src;
     long long i_step;
     int err;
+    long long pt; int cur_op;     // phase profiling (debug builds)
 };
 
 // layout of the always-in-shared-memory part (host and device agree through this function)
-struct FixedSmem { unsigned sred, best, lh, c_lh, geo, sint, slist, sizes, ssz, mem, W, dirty, end; };
+struct FixedSmem { unsigned runc, sred, best, lh, bk_lh, geo, sint, slist, sizes, ssz, mem, W, dlist, dirty, end; };
 SB_HD FixedSmem sb_fixed_smem(int G, int K, int F, int C, int cap, unsigned base) {
     FixedSmem o; unsigned b = (base + 15u) & ~15u;
-    o.sred = b; b += 32 * SB_REDW * 8;
+    o.runc = b; b += (unsigned)((sizeof(RunC) + 15) & ~(size_t)15);
+    o.sred = b; b += 2 * 32 * SB_REDW * 8;
     o.best = b; b += (unsigned)cap * 8;
     o.lh = b; b += (unsigned)G * 8;
-    o.c_lh = b; b += (unsigned)G * 8;
+    o.bk_lh = b; b += (unsigned)G * 8;
     o.geo = b; b += (unsigned)K * 8 * 4;
     o.sint = b; b += 96 * 4;
     o.slist = b; b += 32 * 4;
@@ -188,6 +272,7 @@ SB_HD FixedSmem sb_fixed_smem(int G, int K, int F, int C, int cap, unsigned base
     o.ssz = b; b += (unsigned)K * 4;
     o.mem = b; b += (unsigned)cap * 4;
     o.W = b; b += (unsigned)F * C * 4;
+    o.dlist = b; b += (unsigned)G * 4;
     o.dirty = b; b += (unsigned)G;
     o.end = (b + 15u) & ~15u;
     return o;
@@ -206,15 +291,16 @@ SB_DEV void team_sync(Run &R) {
         R.epoch++;
         if (sb_tid() == 0) {
             sb_threadfence();
-            sb_atomic_add_u64(R.bar, 1ull);
+            sb_atomic_add_u64(R.c->bar, 1ull);
             unsigned long long target = R.epoch * (unsigned long long)R.tsize;
-            while (sb_ld_acquire_u64(R.bar) < target) sb_spin();
+            while (sb_ld_acquire_u64(R.c->bar) < target) sb_spin();
             sb_threadfence();
         }
         sb_cta_sync();
     }
 }
 
+// butterfly all-reduce: every lane ends with the bitwise identical result (a + b == b + a)
 SB_DEV double warp_sum(double v) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += sb_shfl_f64(v, sb_lane() ^ off);
@@ -230,38 +316,51 @@ SB_DEV double warp_min(double v) {
     for (int off = 16; off > 0; off >>= 1) v = fmin(v, sb_shfl_f64(v, sb_lane() ^ off));
     return v;
 }
+SB_DEV Prod warp_prod_reduce(Prod p) {     // mantissas are in [1, 2): 32 of them cannot overflow
+    prod_renorm(p);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        p.m *= sb_shfl_f64(p.m, sb_lane() ^ off);
+        p.e += sb_shfl_i32(p.e, sb_lane() ^ off);
+    }
+    prod_renorm(p);
+    return p;
+}
 
-// CTA-wide sum of K values per thread; fixed order, result in every thread.
+// CTA-wide sum of K values per thread; fixed tree, result in every thread.  One barrier:
+// the per-warp partials alternate between two buffers.
 template <int K, bool PROD = false>
 SB_DEV void block_sum(Run &R, double (&v)[K]) {
+    double *buf = R.c->sred + R.spar * (32 * SB_REDW);
+    R.spar ^= 1;
 #pragma unroll
     for (int k = 0; k < K; k++) v[k] = PROD ? warp_prod(v[k]) : warp_sum(v[k]);
     if (sb_lane() == 0)
-        for (int k = 0; k < K; k++) R.sred[sb_warp() * SB_REDW + k] = v[k];
+        for (int k = 0; k < K; k++) buf[sb_warp() * SB_REDW + k] = v[k];
     sb_cta_sync();
-    int nw = sb_nwarps();
+    const int nw = sb_nwarps();
+#pragma unroll
     for (int k = 0; k < K; k++) {
-        double t = PROD ? 1.0 : 0.0;
-        for (int w = 0; w < nw; w++) { if (PROD) t *= R.sred[w * SB_REDW + k]; else t += R.sred[w * SB_REDW + k]; }
-        v[k] = t;
+        double t = sb_lane() < nw ? buf[sb_lane() * SB_REDW + k] : (PROD ? 1.0 : 0.0);
+        v[k] = PROD ? warp_prod(t) : warp_sum(t);
     }
-    sb_cta_sync();
 }
 
-// team-wide sum (one barrier); result identical in every thread of the team.
+// team-wide sum (one team barrier); result identical in every thread of the team.
 template <int K, bool PROD = false>
 SB_DEV void team_sum(Run &R, double (&v)[K]) {
     block_sum<K, PROD>(R, v);
     if (R.tsize == 1) return;
-    double *buf = R.tred + (size_t)R.par * R.tsize * SB_REDW;
+    double *buf = R.c->tred + (size_t)R.par * R.tsize * SB_REDW;
     R.par ^= 1;
     if (sb_tid() == 0)
         for (int k = 0; k < K; k++) buf[R.rank * SB_REDW + k] = v[k];
     team_sync(R);
+#pragma unroll
     for (int k = 0; k < K; k++) {
         double t = PROD ? 1.0 : 0.0;
-        for (int r = 0; r < R.tsize; r++) { if (PROD) t *= buf[r * SB_REDW + k]; else t += buf[r * SB_REDW + k]; }
-        v[k] = t;
+        for (int r = sb_lane(); r < R.tsize; r += 32) { if (PROD) t *= buf[r * SB_REDW + k]; else t += buf[r * SB_REDW + k]; }
+        v[k] = PROD ? warp_prod(t) : warp_sum(t);
     }
 }
 
@@ -274,17 +373,20 @@ SB_DEV void team_range(const Run &R, int n, int &lo, int &hi) {
 // Inverse-CDF draw over val[0..n): first i with cumsum(val)[i] / total > u (numpy's
 // Generator.choice(p=...), oracle/draws.py:cdf_pick).  val must be fully written by its
 // owners; contains one team barrier.  Returns the index (or -1 if total is not > 0).
-SB_DEV int team_pick(Run &R, const double *val, int n, double u, double &total) {
+// extra[0..1] are summed over the team on the way (free ride on the same barrier).
+SB_DEV int team_pick(Run &R, const double *val, int n, double u, double &total, double *extra = nullptr) {
     int lo, hi; team_range(R, n, lo, hi);
-    double s[1] = {0.0};
+    double s[3] = {0.0, extra ? extra[0] : 0.0, extra ? extra[1] : 0.0};
     for (int i = lo + sb_tid(); i < hi; i += sb_nthr()) s[0] += val[i];
-    block_sum<1>(R, s);
-    double *buf = R.tred + (size_t)R.par * R.tsize * SB_REDW;
+    block_sum<3>(R, s);
+    double *buf = R.c->tred + (size_t)R.par * R.tsize * SB_REDW;
     R.par ^= 1;
-    if (sb_tid() == 0) buf[R.rank * SB_REDW] = s[0];
+    if (sb_tid() == 0) { buf[R.rank * SB_REDW] = s[0]; buf[R.rank * SB_REDW + 1] = s[1]; buf[R.rank * SB_REDW + 2] = s[2]; }
     team_sync(R);
     total = 0.0;
-    for (int r = 0; r < R.tsize; r++) total += buf[r * SB_REDW];
+    double e0 = 0.0, e1 = 0.0;
+    for (int r = 0; r < R.tsize; r++) { total += buf[r * SB_REDW]; e0 += buf[r * SB_REDW + 1]; e1 += buf[r * SB_REDW + 2]; }
+    if (extra) { extra[0] = e0; extra[1] = e1; }
     if (!(total > 0.0)) return -1;
     double target = u * total;
     int B = (n + R.tsize - 1) / R.tsize;
@@ -319,10 +421,10 @@ SB_DEV int team_pick(Run &R, const double *val, int n, double u, double &total) 
             if (found < 0) found = last;
         }
         found = sb_shfl_i32(found, sel_lane);
-        if (lane == 0) R.sint[64] = found;
+        if (lane == 0) R.c->sint[64] = found;
     }
     sb_cta_sync();
-    int o = R.sint[64];
+    int o = R.c->sint[64];
     sb_cta_sync();
     return o;
 }
@@ -335,7 +437,7 @@ SB_DEV int team_compact(Run &R, int n, int32_t *list, Pred pred) {
     double c[1] = {0.0};
     for (int i = lo + sb_tid(); i < hi; i += sb_nthr()) c[0] += pred(i) ? 1.0 : 0.0;
     block_sum<1>(R, c);
-    double *buf = R.tred + (size_t)R.par * R.tsize * SB_REDW;
+    double *buf = R.c->tred + (size_t)R.par * R.tsize * SB_REDW;
     R.par ^= 1;
     if (sb_tid() == 0) buf[R.rank * SB_REDW] = c[0];
     team_sync(R);
@@ -346,10 +448,10 @@ SB_DEV int team_compact(Run &R, int n, int32_t *list, Pred pred) {
         int i = c0 + sb_tid();
         bool p = i < hi && pred(i);
         unsigned bal = sb_ballot(p);
-        if (sb_lane() == 0) R.sint[sb_warp()] = sb_popc(bal);
+        if (sb_lane() == 0) R.c->sint[sb_warp()] = sb_popc(bal);
         sb_cta_sync();
         int wpre = 0, tot = 0;
-        for (int w = 0; w < nw; w++) { int v = R.sint[w]; if (w < sb_warp()) wpre += v; tot += v; }
+        for (int w = 0; w < nw; w++) { int v = R.c->sint[w]; if (w < sb_warp()) wpre += v; tot += v; }
         if (p) list[running + wpre + sb_popc(bal & ((1u << sb_lane()) - 1u))] = i;
         running += tot;
         sb_cta_sync();
@@ -358,31 +460,55 @@ SB_DEV int team_compact(Run &R, int n, int32_t *list, Pred pred) {
     return total;
 }
 
+// Items [lo, hi) of the CTA, interleaved over its warps: every item is first processed by
+// its whole warp (`warp_fn`, warp-uniform, may shuffle; returns an Acc to every lane), then
+// lane i finishes item i of the batch on its own (`lane_fn`, no shuffles): the
+// transcendental tail of 32 items runs lane-parallel instead of 32 times.
+template <class Acc, class WarpFn, class LaneFn>
+SB_DEV void batch_items(int lo, int hi, WarpFn warp_fn, LaneFn lane_fn) {
+    const int gw = sb_warp(), nw = sb_nwarps(), lane = sb_lane();
+    for (int i0 = lo + gw; i0 < hi; i0 += nw * 32) {
+        Acc mine = Acc(); bool have = false;      // value-initialised: an indeterminate `mine` lets nvcc fold the lane select away
+        for (int i = 0; i < 32; i++) {
+            int it = i0 + nw * i;
+            if (it >= hi) break;
+            Acc a = warp_fn(it);
+            if (lane == i) { mine = a; have = true; }
+        }
+        if (have) lane_fn(i0 + nw * lane, mine);
+    }
+}
+
 // -----------------------------------------------------------------------------------------
-// views: committed (0) or candidate (1) state
+// views: committed (0) or candidate (1) membership
 // -----------------------------------------------------------------------------------------
+SB_DEV int m_cl(const Run &R, int o) { return R.c->mcl ? (int)R.c->mcl[o] : R.c->st.cluster_of[o]; }
+SB_DEV int m_osel(const Run &R, int o) { return R.c->mosel ? (int)R.c->mosel[o] : (int)R.c->st.osel[o]; }
+SB_DEV int m_combo(const Run &R, int o) { return R.c->mcombo ? (int)R.c->mcombo[o] : sb_ldg(R.P->combo_id + o); }
+SB_DEV int m_pat(const Run &R, int o) { return R.c->combo_pat[m_combo(R, o)]; }
 SB_DEV int cl_of(const Run &R, int o, int view) {
-    int c = R.st.cluster_of[o];
+    int c = m_cl(R, o);
     if (!view || R.chg_mode == CHG_NONE) return c;
     if (R.chg_mode == CHG_ONE) return o == R.chg_o ? R.chg_new : c;
-    if (c < 0 || c == R.chg_k) return R.st.flag_a[o] ? R.chg_k : -1;      // CHG_WIDE
+    if (c < 0 || c == R.chg_k) return R.c->st.flag_a[o] ? R.chg_k : -1;      // CHG_WIDE
     return c;
 }
-SB_DEV const double *rowP(const Run &R, int g, int view, size_t FS) {
-    return ((view && R.rp.dirty[g]) ? R.rp.c_tabP : R.rp.tabP) + (size_t)g * FS;
-}
-SB_DEV const double *rowT(const Run &R, int g, int view, size_t FS) {
-    return ((view && R.rp.dirty[g]) ? R.rp.c_tabT : R.rp.tabT) + (size_t)g * FS;
-}
-SB_DEV int conf_group(const SbProblem &P, int c, int o) {   // stacked group row of object o in component c >= 1, or -1
+SB_DEV int conf_group_g(const SbProblem &P, int c, int o) {   // stacked group row of object o in component c >= 1, or -1
     int gid = sb_ldg(P.conf_gid + (size_t)(c - 1) * P.N + o);
     return gid < 0 ? -1 : P.goff[c] + gid;
 }
-SB_DEV double pow_inv(double v, double inv, bool unit) { return unit ? v : pow(v, inv); }
+SB_DEV int conf_group(const Run &R, int c, int o) { return R.c->combo_rows[(size_t)m_combo(R, o) * R.P->n_conf + c - 1]; }
+SB_DEV const uint8_t *x_row(const Run &R, int o) {
+    if (R.c->rp.xblk && o >= R.c->rp.xlo && o < R.c->rp.xhi) return R.c->rp.xblk + (size_t)(o - R.c->rp.xlo) * R.P->ldx;
+    return R.P->x + (size_t)o * R.P->ldx;
+}
+// v^(1/T): exp(log v / T) is within a few ulp of pow and a third of its instructions
+SB_DEV double pow_inv(double v, double inv, bool unit) { return unit ? v : (v > 0.0 ? exp(inv * log(v)) : 0.0); }
 
 // heat_binary_probability (sbayes/util.py:1457-1469)
 SB_DEV double heat(const Run &R, double p) {
-    double a = pow_inv(p, R.invT, R.T == 1.0), b = pow_inv(1.0 - p, R.invT, R.T == 1.0);
+    if (R.T == 1.0) return p / (p + (1.0 - p));
+    double a = pow_inv(p, R.invT, false), b = pow_inv(1.0 - p, R.invT, false);
     return a / (a + b);
 }
 SB_DEV double sb_expit(double z) { return z >= 0 ? 1.0 / (1.0 + exp(-z)) : exp(z) / (1.0 + exp(z)); }
@@ -397,61 +523,82 @@ SB_DEV double geo_prob_fn(const SbProblem &P, double x) {
 }
 
 // -----------------------------------------------------------------------------------------
-// group rows: counts -> plain / tempered table, Dirichlet-categorical log-likelihood
-// (sbayes/sampling/conditionals.py:105-122,174-179; sbayes/util.py:1373-1394;
-//  sbayes/model/likelihood.py:65-101).  CTA-local: the rows g_list[0..n_rows) are
-// processed by groups of warps, several rows at a time.  With `cand` the new counts are
-// committed - dneg + dpos (delta rows are cleared) and go to the candidate arrays; else
-// the committed counts are used and the committed tables / likelihoods are written.
+// effect tables as functions of the counts (sbayes/sampling/conditionals.py:105-122,174-179):
+//   plain    p[g,f,s]  = (alpha + n_s) / (sum alpha + n)
+//   tempered pT[g,f,s] = (u + (alpha - u)/Tp + n_s/T) / (sum_s(u + (alpha - u)/Tp) + n/T)
+// The reciprocals of the denominators are kept per (group, feature) in rP / rT.
 // -----------------------------------------------------------------------------------------
-SB_DEV void group_rows(Run &R, const int *g_list, int n_rows, bool cand) {
+// the K cluster rows share one concentration row when the host found them identical (dedup)
+SB_DEV int arow(const SbProblem &P, int g) { return g < P.K ? (P.dedup ? 0 : g) : g - P.arow_off; }
+SB_DEV double alpha_at(const Run &R, int g, int f, int s) { return R.c->alpha[((size_t)arow(*R.P, g) * R.P->F + f) * R.P->S + s]; }
+SB_DEV double asum_at(const Run &R, int g, int f) { return R.c->asum[(size_t)arow(*R.P, g) * R.P->F + f]; }
+SB_DEV double unif_at(const Run &R, int f, int s) {
+    return R.P->use_mask ? (double)((R.c->applm[f] >> s) & 1ull) : sb_ldg(R.P->unif + (size_t)f * R.P->S + s);
+}
+SB_DEV double num_P(const Run &R, int g, int f, int s) {
+    return alpha_at(R, g, f, s) + (double)R.c->rp.counts[((size_t)g * R.P->F + f) * R.P->S + s];
+}
+SB_DEV double num_T(const Run &R, int g, int f, int s) {
+    double a = alpha_at(R, g, f, s), u = unif_at(R, f, s);
+    return u + (a - u) * R.invTp + (double)R.c->rp.counts[((size_t)g * R.P->F + f) * R.P->S + s] * R.invT;
+}
+SB_DEV double entry_P(const Run &R, int g, int f, int x) { return num_P(R, g, f, x) * R.c->rp.rP[(size_t)g * R.P->F + f]; }
+SB_DEV double entry_T(const Run &R, int g, int f, int x) { return num_T(R, g, f, x) * R.c->rp.rT[(size_t)g * R.P->F + f]; }
+// tempered entry with a freshly computed denominator (rT is stale while a proposal is being applied)
+SB_DEV double entry_T_fresh(const Run &R, int g, int f, int x) {
+    size_t gf = (size_t)g * R.P->F + f;
+    return num_T(R, g, f, x) / (R.c->rp.bsT[gf] + (double)R.c->rp.nn[gf] * R.invT);
+}
+
+// lgamma(z + d) - lgamma(z) for an integer step d (z > 0, z + d > 0)
+SB_DEV double lgamma_diff(double z, int d) {
+    if (d == 0) return 0.0;
+    if (d > 8 || d < -8) return lgamma(z + (double)d) - lgamma(z);
+    double p = 1.0;
+    if (d > 0) { for (int i = 0; i < d; i++) p *= z + (double)i; return log(p); }
+    for (int i = 1; i <= -d; i++) p *= z - (double)i;
+    return -log(p);
+}
+
+// per-(group, feature) state of whole rows from the counts: totals, reciprocals, the
+// Dirichlet-categorical term (sbayes/util.py:1373-1394; sbayes/model/likelihood.py:65-101).
+// CTA-local; rows g_list[0..n_rows) (null: all rows).
+SB_DEV void rows_full(Run &R, const int *g_list, int n_rows) {
     const SbProblem &P = *R.P;
     const int F = P.F, S = P.S;
-    const int nw = sb_nwarps();
-    int wpr = (F + 31) / 32; if (wpr > nw) wpr = nw;        // warps per row
-    const int rpw = nw / wpr;                                 // rows per wave
-    const int wrow = sb_warp() / wpr, wlane = (sb_warp() % wpr) * 32 + sb_lane();
-    int32_t *cnt_out = cand ? R.rp.c_counts : R.rp.counts;
-    double *tp_out = cand ? R.rp.c_tabP : R.rp.tabP, *tt_out = cand ? R.rp.c_tabT : R.rp.tabT;
-    double *lh_out = cand ? R.rp.c_lh : R.rp.lh;
-    for (int r0 = 0; r0 < n_rows; r0 += rpw) {
-        const int j = r0 + wrow;
-        double acc = 0.0;
-        if (wrow < rpw && j < n_rows) {
-            const int g = g_list ? g_list[j] : j;
-            const size_t base = (size_t)g * F * S;
-            for (int f = wlane; f < F; f += wpr * 32) {
-                const size_t b = base + (size_t)f * S;
-                double n = 0.0, sp = 0.0, stt = 0.0, ser = 0.0;
-                for (int s = 0; s < S; s++) {
-                    int cnt = R.rp.counts[b + s];
-                    if (cand) {
-                        cnt = cnt - R.rp.dneg[b + s] + R.rp.dpos[b + s];
-                        R.rp.dneg[b + s] = 0; R.rp.dpos[b + s] = 0;
-                        cnt_out[b + s] = cnt;
-                    }
-                    double a = sb_ldg(P.alpha + b + s), u = sb_ldg(P.unif + (size_t)f * S + s);
-                    double vp = (double)cnt + a;
-                    double vt = u + (a - u) / R.Tp + (double)cnt / R.T;
-                    tp_out[b + s] = vp; tt_out[b + s] = vt;
-                    n += (double)cnt; sp += vp; stt += vt;
-                    if (a > 0.0) ser += lgamma((double)cnt + a);
-                }
-                for (int s = 0; s < S; s++) { tp_out[b + s] = tp_out[b + s] / sp; tt_out[b + s] = tt_out[b + s] / stt; }
-                size_t gf = (size_t)g * F + f;
-                acc += sb_ldg(P.dcc + gf) - lgamma(n + sb_ldg(P.asum + gf)) + ser;
-            }
+    for (int idx = sb_tid(); idx < n_rows * F; idx += sb_nthr()) {
+        const int g = g_list ? g_list[idx / F] : idx / F, f = idx % F;
+        const size_t gf = (size_t)g * F + f, b = gf * S;
+        int n = 0; double ser = 0.0, bs = 0.0;
+        for (int s = 0; s < S; s++) {
+            int cnt = R.c->rp.counts[b + s];
+            double a = alpha_at(R, g, f, s), u = unif_at(R, f, s);
+            n += cnt; bs += u + (a - u) * R.invTp;
+            if (a > 0.0) ser += lgamma((double)cnt + a);
         }
-        acc = warp_sum(acc);
-        if (sb_lane() == 0) R.sred[sb_warp() * SB_REDW] = acc;
-        sb_cta_sync();
-        if (sb_tid() < rpw && r0 + sb_tid() < n_rows) {
-            double t = 0.0;
-            for (int w = 0; w < wpr; w++) t += R.sred[(sb_tid() * wpr + w) * SB_REDW];
-            lh_out[g_list ? g_list[r0 + sb_tid()] : r0 + sb_tid()] = t;
-        }
-        sb_cta_sync();
+        R.c->rp.nn[gf] = n; R.c->rp.bsT[gf] = bs;
+        R.c->rp.rP[gf] = 1.0 / (asum_at(R, g, f) + (double)n);
+        R.c->rp.rT[gf] = 1.0 / (bs + (double)n * R.invT);
+        R.c->rp.llgf[gf] = sb_ldg(P.dcc + (size_t)arow(P, g) * F + f) - lgamma((double)n + asum_at(R, g, f)) + ser;
     }
+    sb_cta_sync();
+}
+// lh[g] = sum_f llgf[g, f] for the listed rows (warp per row, fixed tree)
+SB_DEV void rows_lh(Run &R, const int *g_list, int n_rows) {
+    const int F = R.P->F;
+    for (int i = sb_warp(); i < n_rows; i += sb_nwarps()) {
+        const int g = g_list ? g_list[i] : i;
+        double s = 0.0;
+        for (int f = sb_lane(); f < F; f += 32) s += R.c->rp.llgf[(size_t)g * F + f];
+        s = warp_sum(s);
+        if (sb_lane() == 0) R.c->rp.lh[g] = s;
+    }
+    sb_cta_sync();
+}
+SB_DEV double ll_total(const Run &R) {          // every warp on its own; identical result everywhere
+    double s = 0.0;
+    for (int g = sb_lane(); g < R.P->G_tot; g += 32) s += R.c->rp.lh[g];
+    return warp_sum(s);
 }
 
 // weight tables for every (confounder pattern p, in-a-cluster bit z), CTA-local:
@@ -465,20 +612,20 @@ SB_DEV void weight_tables(Run &R) {
     const bool unitTp = R.Tp == 1.0;
     for (int i = sb_tid(); i < rows; i += sb_nthr()) {
         int f = i % F, pz = i / F, z = pz & 1, bits = P.pat_bits[pz >> 1];
-        double t1 = 0.0, tp = 0.0, w64[SB_MAXC], wpw[SB_MAXC];
-        for (int c = 0; c < C; c++) {
+        double t1 = 0.0, tp = 0.0, w64[SB_UC], wpw[SB_UC];
+        SB_FOR_C(c, C) {
             double h = c == 0 ? (double)z : (double)((bits >> c) & 1);
-            double w = (double)R.rp.W[f * C + c];
-            w64[c] = h * w; wpw[c] = h * pow_inv(w, R.invTp, unitTp);
+            double w = (double)R.c->rp.W[f * C + c];
+            w64[c] = h * w; wpw[c] = h * (unitTp ? w : pow(w, R.invTp));
             t1 += w64[c]; tp += wpw[c];
         }
         size_t o = (size_t)i * C;
-        for (int c = 0; c < C; c++) {
+        SB_FOR_C(c, C) {
             double a = t1 > 0.0 ? w64[c] / t1 : 0.0;
-            R.rp.w1[o + c] = a;
-            R.rp.wp[o + c] = pow_inv(a, R.invTp, unitTp);
-            R.rp.wq[o + c] = tp > 0.0 ? wpw[c] / tp : 0.0;
-            R.rp.lw[o + c] = log(a);
+            R.c->rp.w1[o + c] = a;
+            R.c->rp.wp[o + c] = unitTp ? a : pow(a, R.invTp);
+            R.c->rp.wq[o + c] = tp > 0.0 ? wpw[c] / tp : 0.0;
+            R.c->rp.lw[o + c] = log(a);
         }
     }
     sb_cta_sync();
@@ -492,7 +639,7 @@ SB_DEV double source_prior_from_hist(Run &R, const int32_t *H) {
     double a[1] = {0.0};
     for (int i = sb_tid(); i < n; i += sb_nthr()) {
         int h = H[i];
-        if (h != 0) a[0] += (double)h * R.rp.lw[i];
+        if (h != 0) a[0] += (double)h * R.c->rp.lw[i];
     }
     block_sum<1>(R, a);
     return a[0];
@@ -507,11 +654,20 @@ SB_DEV double weights_prior_row(const SbProblem &P, const float *Wrow, int f) {
     }
     return -sb_ldg(P.wlnB + f) + t;
 }
+SB_DEV double weights_prior_row_reg(const SbProblem &P, const float (&Wrow)[SB_UC], int f) {
+    if (P.wprior_uniform) return 0.0 - sb_ldg(P.wlnB + f);
+    double t = 0.0;
+    SB_FOR_C(c, P.C) {
+        double a = sb_ldg(P.alpha_w + (size_t)f * P.C + c);
+        if (a != 1.0) t += (a - 1.0) * log((double)Wrow[c]);
+    }
+    return -sb_ldg(P.wlnB + f) + t;
+}
 SB_DEV double weights_prior_total(Run &R) {   // WeightsPrior.__call__ (prior.py:522-551); whole CTA
     const SbProblem &P = *R.P;
     if (P.wprior_uniform) return 0.0;
     double a[1] = {0.0};
-    for (int f = sb_tid(); f < P.F; f += sb_nthr()) a[0] += weights_prior_row(P, R.rp.W + (size_t)f * P.C, f);
+    for (int f = sb_tid(); f < P.F; f += sb_nthr()) a[0] += weights_prior_row(P, R.c->rp.W + (size_t)f * P.C, f);
     block_sum<1>(R, a);
     return a[0];
 }
@@ -533,9 +689,10 @@ SB_DEV double size_prior_of(const SbProblem &P, const int *sizes) {
 }
 SB_DEV double size_prior_cta(Run &R, const int *sizes) {    // whole CTA; result in every thread
     if (R.P->size_prior == 0) return 0.0;
-    if (sb_tid() == 0) R.sred[0] = size_prior_of(*R.P, sizes);
     sb_cta_sync();
-    double v = R.sred[0];
+    if (sb_tid() == 0) R.c->sred[0] = size_prior_of(*R.P, sizes);
+    sb_cta_sync();
+    double v = R.c->sred[0];
     sb_cta_sync();
     return v;
 }
@@ -547,37 +704,38 @@ SB_DEV double size_prior_cta(Run &R, const int *sizes) {    // whole CTA; result
 SB_DEV void geo_cluster(Run &R, int k, int view, double &agg_out, double &val_out) {
     const SbProblem &P = *R.P;
     int m = 0;
+    sb_cta_sync();
     if (sb_tid() == 0) {
         for (int o = 0; o < P.N; o++)
-            if (cl_of(R, o, view) == k) { if (m < R.smem_cap) R.smem_mem[m] = o; m++; }
-        R.sint[65] = m;
+            if (cl_of(R, o, view) == k) { if (m < R.c->smem_cap) R.c->smem_mem[m] = o; m++; }
+        R.c->sint[65] = m;
     }
     sb_cta_sync();
-    m = R.sint[65];
+    m = R.c->sint[65];
     sb_cta_sync();
-    if (m > R.smem_cap) { R.err = 3; m = R.smem_cap; }
+    if (m > R.c->smem_cap) { R.err = 3; m = R.c->smem_cap; }
     double sum = 0.0, mx = 0.0; int cnt = 0;
     if (m > 1) {
         for (int i = sb_tid(); i < m; i += sb_nthr())
-            R.smem_best[i] = i == 0 ? -1.0 : P.cost[(size_t)R.smem_mem[0] * P.N + R.smem_mem[i]];
+            R.c->smem_best[i] = i == 0 ? -1.0 : P.cost[(size_t)R.c->smem_mem[0] * P.N + R.c->smem_mem[i]];
         sb_cta_sync();
         for (int it = 0; it < m - 1; it++) {
             if (sb_tid() == 0) {      // clusters under a geo prior are small: serial argmin is fine
                 int bj = -1; double bv = SB_INF;
-                for (int i = 0; i < m; i++) { double b = R.smem_best[i]; if (b >= 0.0 && (bj < 0 || b < bv)) { bj = i; bv = b; } }
-                R.sint[66] = bj;
-                R.sred[0] = bv;
+                for (int i = 0; i < m; i++) { double b = R.c->smem_best[i]; if (b >= 0.0 && (bj < 0 || b < bv)) { bj = i; bv = b; } }
+                R.c->sint[66] = bj;
+                R.c->sred[0] = bv;
             }
             sb_cta_sync();
-            int j = R.sint[66]; double e = R.sred[0];
+            int j = R.c->sint[66]; double e = R.c->sred[0];
             sb_cta_sync();
             if (j < 0) break;
             if (e != 0.0 && e < SB_INF) { sum += e; if (cnt == 0 || e > mx) mx = e; cnt++; }
             for (int i = sb_tid(); i < m; i += sb_nthr()) {
-                if (i == j) R.smem_best[i] = -1.0;
-                else if (R.smem_best[i] >= 0.0) {
-                    double c = P.cost[(size_t)R.smem_mem[j] * P.N + R.smem_mem[i]];
-                    if (c < R.smem_best[i]) R.smem_best[i] = c;
+                if (i == j) R.c->smem_best[i] = -1.0;
+                else if (R.c->smem_best[i] >= 0.0) {
+                    double c = P.cost[(size_t)R.c->smem_mem[j] * P.N + R.c->smem_mem[i]];
+                    if (c < R.c->smem_best[i]) R.c->smem_best[i] = c;
                 }
             }
             sb_cta_sync();
@@ -596,7 +754,7 @@ SB_DEV double geo_delta(Run &R, int o, int k, int view, int m_size) {
     for (int j = sb_lane(); j < P.N; j += 32)
         if (cl_of(R, j, view) == k) mn = fmin(mn, P.cost[(size_t)j * P.N + o]);
     mn = warp_min(mn);
-    double before = (view && R.rp.dirty[k]) ? R.rp.c_geo_agg[k] : R.rp.geo_agg[k], after;
+    double before = (view && R.c->rp.dirty[k]) ? R.c->rp.c_geo_agg[k] : R.c->rp.geo_agg[k], after;
     double m = (double)m_size;
     if (P.geo_agg == 0) after = (mn + m * before) / (1.0 + m);
     else if (P.geo_agg == 1) after = mn + before;
@@ -605,86 +763,154 @@ SB_DEV double geo_delta(Run &R, int o, int k, int view, int m_size) {
 }
 
 // -----------------------------------------------------------------------------------------
-// cluster-membership marginals of one object against cluster k, whole warp:
+// cluster-membership marginals of objects against cluster k
 //   s_z = sum_f log sum_c l[o,f,c] * w_z[o,f,c]   (before the 1/T power)
-// compute_cluster_posterior / compute_raw_cluster_probs (operators.py:1035-1095,1420-1472)
+// compute_cluster_posterior / compute_raw_cluster_probs (operators.py:1035-1095,1420-1472).
+// l[.,.,0] is the tempered table of cluster k (to the power 1/T in the wide operator), the
+// other columns are the plain tables of the object's confounder groups.
 // -----------------------------------------------------------------------------------------
-SB_DEV void cluster_marginals(Run &R, int o, int k, int view, bool wide, double &s0, double &s1) {
+struct Marg { Prod p0, p1; double geo; int on; };
+
+// tables over combos: tab0[j,f,x] = sum_{c>=1} l_c w0_c,  tab1[j,f,x] = l_0 w1_0 + sum_{c>=1} l_c w1_c.  CTA-local.
+SB_DEV void build_tables(Run &R, int k, bool wide) {
     const SbProblem &P = *R.P;
     const int F = P.F, S = P.S, C = P.C;
-    const size_t FS = (size_t)F * S;
-    const double *rowK = rowT(R, k, view, FS);
-    const double *rowC[SB_MAXC];
-    for (int c = 1; c < C; c++) {
-        int g = conf_group(P, c, o);
-        rowC[c] = g < 0 ? nullptr : rowP(R, g, view, FS);
-    }
-    int pat = sb_ldg(P.pat_id + o);
-    const double *w0 = R.rp.wq + (size_t)(pat * 2 + 0) * F * C;
-    const double *w1 = R.rp.wq + (size_t)(pat * 2 + 1) * F * C;
-    const uint8_t *xr = P.x + (size_t)o * P.ldx;
     const bool powT = wide && R.T != 1.0;
-    double a0s = 0.0, a1s = 0.0;
-    for (int f = sb_lane(); f < F; f += 32) {
-        int x = sb_ldg(xr + f);
-        if (x == SB_NA_U8) continue;
-        double l0 = rowK[(size_t)f * S + x];
-        if (powT) l0 = pow(l0, R.invT);
-        double a0 = 0.0, a1 = l0 * w1[f * C];
-        for (int c = 1; c < C; c++) {
-            if (!rowC[c]) continue;
-            double l = rowC[c][(size_t)f * S + x];
-            a0 += l * w0[f * C + c];
-            a1 += l * w1[f * C + c];
+    for (int idx = sb_tid(); idx < P.n_combos * F; idx += sb_nthr()) {
+        const int j = idx / F, f = idx % F;
+        const int pat = R.c->combo_pat[j];
+        const double *w0 = R.c->rp.wq + ((size_t)(pat * 2 + 0) * F + f) * C;
+        const double *w1 = R.c->rp.wq + ((size_t)(pat * 2 + 1) * F + f) * C;
+        int gC[SB_UC]; double rC[SB_UC];
+        SB_FOR_C1(c, C) {
+            gC[c] = R.c->combo_rows[(size_t)j * P.n_conf + c - 1];
+            rC[c] = gC[c] >= 0 ? R.c->rp.rP[(size_t)gC[c] * F + f] : 0.0;
         }
-        a0s += log(a0); a1s += log(a1);
+        const double rk = R.c->rp.rT[(size_t)k * F + f], w10 = w1[0];
+        double *t0 = R.c->rp.tab0 + ((size_t)j * F + f) * S, *t1 = R.c->rp.tab1 + ((size_t)j * F + f) * S;
+        for (int x = 0; x < S; x++) {
+            double l0 = num_T(R, k, f, x) * rk;
+            if (powT) l0 = pow_inv(l0, R.invT, false);
+            double a0 = 0.0, a1 = l0 * w10;
+            SB_FOR_C1(c, C) {
+                if (gC[c] >= 0) {
+                    double l = num_P(R, gC[c], f, x) * rC[c];
+                    a0 += l * w0[c]; a1 += l * w1[c];
+                }
+            }
+            t0[x] = a0; t1[x] = a1;
+        }
     }
-    s0 = warp_sum(a0s); s1 = warp_sum(a1s);
+    sb_cta_sync();
 }
 
-// AlterCluster.compute_cluster_posterior (operators.py:1035-1073), whole warp -> every lane
-SB_DEV double cluster_posterior(Run &R, int o, int k, int view, bool gibbsish, bool use_geo, int m_size) {
-    if (R.sfp || !gibbsish) return 0.5;
-    double s0, s1;
-    cluster_marginals(R, o, k, view, false, s0, s1);
+// whole warp -> every lane.  TABLE: gather from tab0 / tab1 (must be built for this k / wide).
+template <bool TABLE>
+SB_DEV void obj_marginals(const Run &R, int o, int k, bool wide, Prod &p0, Prod &p1) {
+    const SbProblem &P = *R.P;
+    const int F = P.F, S = P.S, C = P.C;
+    const uint32_t *xw = (const uint32_t *)x_row(R, o);
+    const int nwords = P.ldx >> 2;
+    p0 = prod_one(); p1 = prod_one();
+    if (TABLE) {
+        const int j = m_combo(R, o);
+        const double *t0 = R.c->rp.tab0 + (size_t)j * F * S, *t1 = R.c->rp.tab1 + (size_t)j * F * S;
+        for (int w = sb_lane(); w < nwords; w += 32) {
+            uint32_t word = xw[w];
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                int x = (word >> (8 * b)) & 0xFF;
+                if (x == SB_NA_U8) continue;
+                int e = (4 * w + b) * S + x;
+                p0.m *= t0[e]; p1.m *= t1[e];
+            }
+            prod_renorm(p0); prod_renorm(p1);
+        }
+    } else {
+        int gC[SB_UC];
+        SB_FOR_C1(c, C) gC[c] = conf_group(R, c, o);
+        const int pat = m_pat(R, o);
+        const double *w0 = R.c->rp.wq + (size_t)(pat * 2 + 0) * F * C;
+        const double *w1 = R.c->rp.wq + (size_t)(pat * 2 + 1) * F * C;
+        const bool powT = wide && R.T != 1.0;
+        for (int w = sb_lane(); w < nwords; w += 32) {
+            uint32_t word = xw[w];
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                int x = (word >> (8 * b)) & 0xFF;
+                if (x == SB_NA_U8) continue;
+                int f = 4 * w + b;
+                double l0 = entry_T(R, k, f, x);
+                if (powT) l0 = pow_inv(l0, R.invT, false);
+                double a0 = 0.0, a1 = l0 * w1[f * C];
+                SB_FOR_C1(c, C) {
+                    if (gC[c] >= 0) {
+                        double l = entry_P(R, gC[c], f, x);
+                        a0 += l * w0[f * C + c]; a1 += l * w1[f * C + c];
+                    }
+                }
+                p0.m *= a0; p1.m *= a1;
+            }
+            prod_renorm(p0); prod_renorm(p1);
+        }
+    }
+    p0 = warp_prod_reduce(p0); p1 = warp_prod_reduce(p1);
+}
+
+// whether a pass over about n_obj objects (split over the team) should gather from tables
+// (built redundantly by every CTA); uniform across the team
+SB_DEV bool pass_uses_tables(const Run &R, long long n_obj) {
+    const SbProblem &P = *R.P;
+    return P.use_tables && n_obj * 3 > (long long)P.n_combos * P.S * 2 * R.tsize;
+}
+
+// AlterCluster.compute_cluster_posterior (operators.py:1035-1073) from the marginals (one lane)
+SB_DEV double posterior_tail(const Run &R, const Marg &a, bool flat, bool use_geo) {
+    if (flat) return 0.5;
+    double s0 = prod_log(a.p0), s1 = prod_log(a.p1);
     double d = s1 * R.invT - s0 * R.invT;
-    if (use_geo && R.P->geo) d = (s1 * R.invT + geo_delta(R, o, k, view, m_size) * R.invTp) - s0 * R.invT;
+    if (use_geo) d = (s1 * R.invT + a.geo * R.invTp) - s0 * R.invT;
     double post = sb_expit(d);
     return (post + SB_SMOOTH) / (1.0 + 2.0 * SB_SMOOTH);
 }
 
-// get_jump_lh (operators.py:1679-1722) for one member o of k_src, whole warp
-SB_DEV double jump_prob(Run &R, int o, int k_src, int k_tgt, int view) {
+// get_jump_lh (operators.py:1679-1722) for one member o of k_src, whole warp: products of
+// (E_conf + w_0 p_src) and (E_conf + w_0 p_tgt) over the features, tempered tables throughout
+SB_DEV void jump_marginals(const Run &R, int o, int k_src, int k_tgt, Prod &ps, Prod &pj) {
     const SbProblem &P = *R.P;
-    const int F = P.F, S = P.S, C = P.C;
-    const size_t FS = (size_t)F * S;
-    const double *rowS = rowT(R, k_src, view, FS);
-    const double *rowG = rowT(R, k_tgt, view, FS);
-    const double *rowC[SB_MAXC];
-    for (int c = 1; c < C; c++) {
-        int g = conf_group(P, c, o);
-        rowC[c] = g < 0 ? nullptr : rowT(R, g, view, FS);
+    const int F = P.F, C = P.C;
+    int gC[SB_UC];
+    SB_FOR_C1(c, C) gC[c] = conf_group(R, c, o);
+    const int pat = m_pat(R, o);
+    const double *wh = R.c->rp.wq + (size_t)(pat * 2 + 1) * F * C;
+    const uint32_t *xw = (const uint32_t *)x_row(R, o);
+    const int nwords = P.ldx >> 2;
+    ps = prod_one(); pj = prod_one();
+    for (int w = sb_lane(); w < nwords; w += 32) {
+        uint32_t word = xw[w];
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            int x = (word >> (8 * b)) & 0xFF;
+            if (x == SB_NA_U8) continue;
+            int f = 4 * w + b;
+            double conf = 0.0;
+            SB_FOR_C1(c, C)
+                if (gC[c] >= 0) conf += wh[f * C + c] * entry_T(R, gC[c], f, x);
+            ps.m *= conf + wh[f * C] * entry_T(R, k_src, f, x);
+            pj.m *= conf + wh[f * C] * entry_T(R, k_tgt, f, x);
+        }
+        prod_renorm(ps); prod_renorm(pj);
     }
-    int pat = sb_ldg(P.pat_id + o);
-    const double *wh = R.rp.wq + (size_t)(pat * 2 + 1) * F * C;
-    const uint8_t *xr = P.x + (size_t)o * P.ldx;
-    double ls = 0.0, lj = 0.0;
-    for (int f = sb_lane(); f < F; f += 32) {
-        int x = sb_ldg(xr + f);
-        if (x == SB_NA_U8) continue;
-        double conf = 0.0;
-        for (int c = 1; c < C; c++)
-            if (rowC[c]) conf += wh[f * C + c] * rowC[c][(size_t)f * S + x];
-        ls += log(conf + wh[f * C] * rowS[(size_t)f * S + x]);
-        lj += log(conf + wh[f * C] * rowG[(size_t)f * S + x]);
-    }
-    ls = warp_sum(ls); lj = warp_sum(lj);
-    double lh_stay = exp(ls * R.invT) + SB_EPS32, lh_jump = exp(lj * R.invT) + SB_EPS32;
+    ps = warp_prod_reduce(ps); pj = warp_prod_reduce(pj);
+}
+SB_DEV double jump_tail(const Run &R, const Prod &ps, const Prod &pj) {
+    double lh_stay = exp(prod_log(ps) * R.invT) + SB_EPS32, lh_jump = exp(prod_log(pj) * R.invT) + SB_EPS32;
     return lh_jump / (lh_jump + lh_stay);
 }
 
 // -----------------------------------------------------------------------------------------
-// proposal bookkeeping
+// proposal bookkeeping: a proposal edits the replica in place (counts, totals, histogram
+// copy, per-(group, feature) terms of the touched rows) and is undone on a reject
 // -----------------------------------------------------------------------------------------
 struct Prop {
     int changed;        // 0 => direct reject before anything was touched
@@ -705,138 +931,230 @@ SB_DEV Prop prop_init(int changed, double lq, double lqb) {
 // mark the group rows object o leaves or joins
 SB_DEV void mark_object(Run &R, int o) {
     const SbProblem &P = *R.P;
-    int a = R.st.cluster_of[o], b = cl_of(R, o, 1);
-    if (a >= 0) R.rp.dirty[a] = 1;
-    if (b >= 0) R.rp.dirty[b] = 1;
-    for (int c = 1; c < P.C; c++) { int g = conf_group(P, c, o); if (g >= 0) R.rp.dirty[g] = 1; }
+    int a = m_cl(R, o), b = cl_of(R, o, 1);
+    if (a >= 0) R.c->rp.dirty[a] = 1;
+    if (b >= 0) R.c->rp.dirty[b] = 1;
+    for (int c = 1; c < P.C; c++) { int g = conf_group(R, c, o); if (g >= 0) R.c->rp.dirty[g] = 1; }
 }
-
 // group row an observation of object o assigned to component c counts towards
 SB_DEV int obs_group(const Run &R, int o, int c, int view) {
-    return c == 0 ? cl_of(R, o, view) : conf_group(*R.P, c, o);
+    return c == 0 ? cl_of(R, o, view) : conf_group(R, c, o);
+}
+SB_DEV void count_add(Run &R, int g, int f, int x, int d) {
+    const size_t gf = (size_t)g * R.P->F + f;
+    sb_atomic_add_i32(R.c->rp.counts + gf * R.P->S + x, d);
+    sb_atomic_add_i32(R.c->rp.dcnt + gf * R.P->S + x, d);
+    sb_atomic_add_i32(R.c->rp.nn + gf, d);
 }
 
-// tempered table entry of row g at (f, x) with the proposal's own observations removed
-// (component_likelihood_given_unchanged, operators.py:863-928)
-SB_DEV double unchanged_entry(const Run &R, int g, int f, int x) {
+// opens a proposal over the M objects S[]: candidate histogram, dirty rows + their backups.
+// Ends with a barrier.  Returns the candidate histogram.
+SB_DEV int32_t *proposal_open(Run &R, int M, const int *S) {
     const SbProblem &P = *R.P;
-    const size_t b = ((size_t)g * P.F + f) * P.S;
-    double sum = 0.0, at = 0.0;
-    for (int s = 0; s < P.S; s++) {
-        double a = sb_ldg(P.alpha + b + s), u = sb_ldg(P.unif + (size_t)f * P.S + s);
-        double v = u + (a - u) / R.Tp + (double)(R.rp.counts[b + s] - R.rp.dneg[b + s]) / R.T;
-        sum += v; if (s == x) at = v;
-    }
-    return at / sum;
-}
-
-// candidate copy of the source histogram
-SB_DEV int32_t *hist_begin(Run &R) {
-    const SbProblem &P = *R.P;
-    const int nH = P.n_pat * 2 * P.F * P.C;
-    const int32_t *h = R.rp.H[R.rp.hcur];
-    int32_t *hc = R.rp.H[R.rp.hcur ^ 1];
+    const int nH = P.n_pat * 2 * P.F * P.C, F = P.F;
+    const int32_t *h = R.c->rp.H[R.hcur];
+    int32_t *hc = R.c->rp.H[R.hcur ^ 1];
     for (int i = sb_tid(); i < nH; i += sb_nthr()) hc[i] = h[i];
+    for (int m = sb_tid(); m < M; m += sb_nthr()) { mark_object(R, S[m]); R.c->rp.selbuf[m] = m_osel(R, S[m]) ^ 1; }
+    sb_cta_sync();
+    if (sb_warp() == 0) {
+        int n = 0;
+        for (int b = 0; b < P.G_tot; b += 32) {
+            int g = b + sb_lane();
+            bool d = g < P.G_tot && R.c->rp.dirty[g];
+            unsigned bal = sb_ballot(d);
+            if (d) R.c->rp.dlist[n + sb_popc(bal & ((1u << sb_lane()) - 1u))] = g;
+            n += sb_popc(bal);
+        }
+        if (sb_lane() == 0) R.c->sint[67] = n;
+    }
+    sb_cta_sync();
+    R.nd = R.c->sint[67];
+    for (int idx = sb_tid(); idx < R.nd * F; idx += sb_nthr()) {
+        const size_t gf = (size_t)R.c->rp.dlist[idx / F] * F + idx % F;
+        R.c->rp.bk_llgf[gf] = R.c->rp.llgf[gf]; R.c->rp.bk_rP[gf] = R.c->rp.rP[gf]; R.c->rp.bk_rT[gf] = R.c->rp.rT[gf];
+    }
+    for (int i = sb_tid(); i < R.nd; i += sb_nthr()) R.c->rp.bk_lh[R.c->rp.dlist[i]] = R.c->rp.lh[R.c->rp.dlist[i]];
+    sb_cta_sync();
     return hc;
 }
 
-// candidate rows of every dirty group, source prior of the candidate histogram, geo prior
-// of the dirty clusters.  CTA-local (every CTA does the same on its replica).
-SB_DEV void candidate_rows(Run &R, Prop &pr, bool geo_clusters) {
+// after the counts of the dirty rows were edited: update the per-(group, feature) terms of
+// the entries that changed and the per-group likelihoods.  CTA-local, ends with a barrier.
+SB_DEV void proposal_rows(Run &R) {
     const SbProblem &P = *R.P;
-    // dirty list in shared memory (reuses the member-list area; G_tot <= capacity is checked by the host)
-    if (sb_tid() == 0) {
-        int n = 0;
-        for (int g = 0; g < P.G_tot; g++) if (R.rp.dirty[g]) R.smem_mem[n++] = g;
-        R.sint[67] = n;
+    const int F = P.F, S = P.S;
+    sb_cta_sync();
+    for (int idx = sb_tid(); idx < R.nd * F; idx += sb_nthr()) {
+        const int g = R.c->rp.dlist[idx / F], f = idx % F;
+        const size_t gf = (size_t)g * F + f, b = gf * S;
+        int D = 0; bool any = false; double delta = 0.0;
+        for (int s = 0; s < S; s++) {
+            int d = R.c->rp.dcnt[b + s];
+            if (d == 0) continue;
+            any = true; D += d;
+            double a = alpha_at(R, g, f, s);
+            if (a > 0.0) delta += lgamma_diff((double)(R.c->rp.counts[b + s] - d) + a, d);
+        }
+        if (!any) continue;
+        if (D != 0) {
+            const int n = R.c->rp.nn[gf];
+            const double as = asum_at(R, g, f);
+            delta -= lgamma_diff((double)(n - D) + as, D);
+            R.c->rp.rP[gf] = 1.0 / (as + (double)n);
+            R.c->rp.rT[gf] = 1.0 / (R.c->rp.bsT[gf] + (double)n * R.invT);
+        }
+        R.c->rp.llgf[gf] += delta;
     }
     sb_cta_sync();
-    const int nd = R.sint[67];
-    group_rows(R, R.smem_mem, nd, true);
-    pr.sp_new = source_prior_from_hist(R, R.rp.H[R.rp.hcur ^ 1]);
-    double geo = 0.0;
-    if (P.geo) {
-        for (int k = 0; k < P.K; k++) {
-            if (geo_clusters && R.rp.dirty[k]) {
-                double a, v; geo_cluster(R, k, 1, a, v);
-                if (sb_tid() == 0) { R.rp.c_geo_agg[k] = a; R.rp.c_geo_val[k] = v; }
-                geo += v;
-            } else {
-                if (R.rp.dirty[k] && sb_tid() == 0) { R.rp.c_geo_agg[k] = R.rp.geo_agg[k]; R.rp.c_geo_val[k] = R.rp.geo_val[k]; }
-                geo += R.rp.geo_val[k];
-            }
+    rows_lh(R, R.c->rp.dlist, R.nd);
+}
+
+// closes the proposal: keep (accept) or undo (reject) the edits of the dirty rows
+SB_DEV void proposal_close(Run &R, bool accept) {
+    const SbProblem &P = *R.P;
+    const int F = P.F, S = P.S;
+    sb_cta_sync();      // every warp has read the candidate likelihoods (ll_total)
+    for (int idx = sb_tid(); idx < R.nd * F; idx += sb_nthr()) {
+        const int g = R.c->rp.dlist[idx / F], f = idx % F;
+        const size_t gf = (size_t)g * F + f, b = gf * S;
+        int D = 0;
+        for (int s = 0; s < S; s++) {
+            int d = R.c->rp.dcnt[b + s];
+            if (d == 0) continue;
+            D += d;
+            if (!accept) R.c->rp.counts[b + s] -= d;
+            R.c->rp.dcnt[b + s] = 0;
         }
-        sb_cta_sync();
+        if (!accept) {
+            if (D != 0) R.c->rp.nn[gf] -= D;
+            R.c->rp.llgf[gf] = R.c->rp.bk_llgf[gf]; R.c->rp.rP[gf] = R.c->rp.bk_rP[gf]; R.c->rp.rT[gf] = R.c->rp.bk_rT[gf];
+        }
     }
-    pr.geo_new = geo;
+    for (int i = sb_tid(); i < R.nd; i += sb_nthr()) {
+        const int g = R.c->rp.dlist[i];
+        if (!accept) R.c->rp.lh[g] = R.c->rp.bk_lh[g];
+        else if (P.geo && g < P.K) { R.c->rp.geo_agg[g] = R.c->rp.c_geo_agg[g]; R.c->rp.geo_val[g] = R.c->rp.c_geo_val[g]; }
+        R.c->rp.dirty[g] = 0;
+    }
+    R.nd = 0;
+    sb_cta_sync();
+}
+
+// geo prior of the candidate membership (dirty clusters re-evaluated)
+SB_DEV double candidate_geo(Run &R, bool recompute) {
+    const SbProblem &P = *R.P;
+    if (!P.geo) return 0.0;
+    double geo = 0.0;
+    for (int k = 0; k < P.K; k++) {
+        if (recompute && R.c->rp.dirty[k]) {
+            double a, v; geo_cluster(R, k, 1, a, v);
+            if (sb_tid() == 0) { R.c->rp.c_geo_agg[k] = a; R.c->rp.c_geo_val[k] = v; }
+            geo += v;
+        } else {
+            if (R.c->rp.dirty[k] && sb_tid() == 0) { R.c->rp.c_geo_agg[k] = R.c->rp.geo_agg[k]; R.c->rp.c_geo_val[k] = R.c->rp.geo_val[k]; }
+            geo += R.c->rp.geo_val[k];
+        }
+    }
+    sb_cta_sync();
+    return geo;
+}
+
+// sample_categorical (sbayes/preprocessing.py:224-256): first c with u < cumsum(q)[c] / sum(q)
+SB_DEV int categorical(const double (&q)[SB_UC], int C, double u) {
+    double cum = 0.0, last = 0.0;
+    SB_FOR_C(c, C) last += q[c];
+    int nw = 0; bool got = false;
+    SB_FOR_C(c, C) { cum += q[c]; if (!got && u < cum / last) { nw = c; got = true; } }
+    return nw;
+}
+SB_DEV double pick_c(const double (&q)[SB_UC], int C, int i) {     // q[i] without a dynamic register index
+    double v = 0.0;
+    SB_FOR_C(c, C) if (c == i) v = q[c];
+    return v;
 }
 
 // ClusterOperator.gibbs_sample_source / ClusterJump.gibbs_sample_source_jump
 // (operators.py:796-849,1775-1827) for the M changed objects S[0..M).  CTA-local: every
-// CTA resamples all M objects (identical draws), updates its replica and writes the same
-// candidate source rows.  Leaves candidate rows (counts, tables, lh, geo) and the
-// candidate histogram; returns log_q, log_q_back of the source draw.
+// CTA resamples all M objects (identical draws), edits its replica and writes the same
+// candidate source rows.  Returns log_q, log_q_back of the source draw; leaves the
+// candidate rows, the candidate histogram and pr.sp_new / pr.geo_new.
 SB_DEV void resample_sources(Run &R, Prop &pr, int M, const int *S, int k_new, int k_old, bool jump, double &lq, double &lqb) {
     const SbProblem &P = *R.P;
     const int F = P.F, C = P.C;
     const long long items = (long long)M * F;
-    int32_t *Hc = hist_begin(R);
-    for (int m = sb_tid(); m < M; m += sb_nthr()) { mark_object(R, S[m]); R.rp.selbuf[m] = R.st.osel[S[m]] ^ 1; }
-    sb_cta_sync();
-    // R1: remove the objects' own observations (dneg), H -= old
+    PH(R, 5);
+    int32_t *Hc = proposal_open(R, M, S);
+    PH(R, 6);
+    // R1: remove the objects' own observations; H -= old
     for (long long it = sb_tid(); it < items; it += sb_nthr()) {
         int m = (int)(it / F), f = (int)(it % F), o = S[m];
         int x = sb_ldg(P.x + (size_t)o * P.ldx + f);
         if (x == SB_NA_U8) continue;
-        int c = R.st.src[R.st.osel[o]][(size_t)o * P.ldx + f];
+        int c = R.c->st.src[m_osel(R, o)][(size_t)o * P.ldx + f];
         int g = obs_group(R, o, c, 0);
-        int pat = sb_ldg(P.pat_id + o), z_old = R.st.cluster_of[o] >= 0;
-        if (g >= 0) sb_atomic_add_i32(R.rp.dneg + ((size_t)g * F + f) * P.S + x, 1);
+        int pat = m_pat(R, o), z_old = m_cl(R, o) >= 0;
+        if (g >= 0) count_add(R, g, f, x, -1);
         sb_atomic_add_i32(Hc + ((size_t)(pat * 2 + z_old) * F + f) * C + c, -1);
     }
     sb_cta_sync();
-    // R2: conditional source distribution, draw, add the new observations (dpos), H += new
+    PH(R, 7);
+    // R2: conditional source distribution given the unchanged observations, draw
     const bool unitT = R.T == 1.0;
-    double acc[2] = {0.0, 0.0};
+    double acc[3] = {0.0, 0.0, 0.0};
     for (long long it = sb_tid(); it < items; it += sb_nthr()) {
         int m = (int)(it / F), f = (int)(it % F), o = S[m];
         int x = sb_ldg(P.x + (size_t)o * P.ldx + f);
-        uint8_t *sn = R.st.src[R.st.osel[o] ^ 1] + (size_t)o * P.ldx;
+        uint8_t *sn = R.c->st.src[m_osel(R, o) ^ 1] + (size_t)o * P.ldx;
         if (x == SB_NA_U8) { sn[f] = SB_NA_U8; continue; }
-        int pat = sb_ldg(P.pat_id + o), z_old = R.st.cluster_of[o] >= 0, z_new = cl_of(R, o, 1) >= 0;
-        const double *tw = jump ? R.rp.w1 : R.rp.wp;
+        int pat = m_pat(R, o), z_old = m_cl(R, o) >= 0, z_new = cl_of(R, o, 1) >= 0;
+        const double *tw = jump ? R.c->rp.w1 : R.c->rp.wp;
         const double *wf = tw + ((size_t)(pat * 2 + z_new) * F + f) * C;
         const double *wb = tw + ((size_t)(pat * 2 + (jump ? z_new : z_old)) * F + f) * C;
-        double q[SB_MAXC], qb[SB_MAXC], tot = 0.0, totb = 0.0;
-        for (int c = 0; c < C; c++) {
+        double q[SB_UC], qb[SB_UC], tot = 0.0, totb = 0.0;
+        SB_FOR_C(c, C) {
             double l = 1.0, lo = 1.0;
             if (!R.sfp) {
-                int g = c == 0 ? k_new : conf_group(P, c, o);
-                l = g < 0 ? 0.0 : pow_inv(unchanged_entry(R, g, f, x), R.invT, unitT);
+                int g = c == 0 ? k_new : conf_group(R, c, o);
+                l = g < 0 ? 0.0 : pow_inv(entry_T_fresh(R, g, f, x), R.invT, unitT);
                 lo = l;
-                if (jump && c == 0) lo = pow_inv(unchanged_entry(R, k_old, f, x), R.invT, unitT);
+                if (jump && c == 0) lo = pow_inv(entry_T_fresh(R, k_old, f, x), R.invT, unitT);
             }
             q[c] = wf[c] * l; qb[c] = wb[c] * lo;
             tot += q[c]; totb += qb[c];
         }
-        if (!R.sfp) { for (int c = 0; c < C; c++) { q[c] /= tot; qb[c] /= totb; } }
-        // sample_categorical (sbayes/preprocessing.py:224-256)
-        double u = draw_uniform(R.D, SITE_GIBBS, (uint32_t)((size_t)m * F + f));
-        double cum = 0.0, last = 0.0;
-        for (int c = 0; c < C; c++) last += q[c];
-        int nw = 0; bool got = false;
-        for (int c = 0; c < C; c++) { cum += q[c]; if (!got && u < cum / last) { nw = c; got = true; } }
-        int c_old = R.st.src[R.st.osel[o]][(size_t)o * P.ldx + f];
-        acc[0] += log(q[nw]); acc[1] += log(qb[c_old]);
+        if (!R.sfp) { SB_FOR_C(c, C) { q[c] /= tot; qb[c] /= totb; } }
+        int nw = categorical(q, C, draw_uniform(R.D, SITE_GIBBS, (uint32_t)((size_t)m * F + f)));
+        int c_old = R.c->st.src[m_osel(R, o)][(size_t)o * P.ldx + f];
+        acc[0] += log(pick_c(q, C, nw)); acc[1] += log(pick_c(qb, C, c_old));
+        acc[2] += R.c->rp.lw[((size_t)(pat * 2 + z_new) * F + f) * C + nw] - R.c->rp.lw[((size_t)(pat * 2 + z_old) * F + f) * C + c_old];
         sn[f] = (uint8_t)nw;
+#ifdef SB_DEBUG_PRINT
+        if (R.i_step == 1 && R.rank == 0) printf("R2 m=%d f=%d o=%d x=%d c_old=%d nw=%d q=%.6f %.6f %.6f qb=%.6f %.6f %.6f z=%d%d nn=%d %d\n", m, f, o, x, c_old, nw, q[0], q[1], q[2], qb[0], qb[1], qb[2], z_old, z_new, R.c->rp.nn[(size_t)k_new * F + f], R.c->rp.nn[(size_t)conf_group(R, 1, o) * F + f]);
+#endif
+    }
+    sb_cta_sync();
+    PH(R, 8);
+    // R3: add the new observations; H += new
+    for (long long it = sb_tid(); it < items; it += sb_nthr()) {
+        int m = (int)(it / F), f = (int)(it % F), o = S[m];
+        int x = sb_ldg(P.x + (size_t)o * P.ldx + f);
+        if (x == SB_NA_U8) continue;
+        int nw = R.c->st.src[m_osel(R, o) ^ 1][(size_t)o * P.ldx + f];
+        int pat = m_pat(R, o), z_new = cl_of(R, o, 1) >= 0;
         int g = obs_group(R, o, nw, 1);
-        if (g >= 0) sb_atomic_add_i32(R.rp.dpos + ((size_t)g * F + f) * P.S + x, 1);
+        if (g >= 0) count_add(R, g, f, x, 1);
         sb_atomic_add_i32(Hc + ((size_t)(pat * 2 + z_new) * F + f) * C + nw, 1);
     }
-    block_sum<2>(R, acc);
+    block_sum<3>(R, acc);
     lq = acc[0]; lqb = acc[1];
+    pr.sp_new = R.pr_src + acc[2];
     pr.src_changed = 1;
-    candidate_rows(R, pr, true);
+    PH(R, 9);
+    proposal_rows(R);
+    PH(R, 10);
+    pr.geo_new = candidate_geo(R, true);
+    PH(R, 11);
 }
 
 // neighbours of a cluster on the CSR adjacency (sbayes/util.py:121-143)
@@ -861,102 +1179,130 @@ SB_DEV void grow_candidates(Run &R, int k, int nb, int view) {
     const SbProblem &P = *R.P;
     int lo, hi; team_range(R, P.N, lo, hi);
     if (nb == NB_TWOSTEP) {
-        for (int o = lo + sb_tid(); o < hi; o += sb_nthr()) R.st.flag_a[o] = touches_cluster(R, o, k, view);
+        for (int o = lo + sb_tid(); o < hi; o += sb_nthr()) R.c->st.flag_a[o] = touches_cluster(R, o, k, view);
         team_sync(R);
     }
     for (int o = lo + sb_tid(); o < hi; o += sb_nthr()) {
         bool freeo = cl_of(R, o, view) < 0, c = freeo;
         if (freeo && nb == NB_DIRECT) c = touches_cluster(R, o, k, view);
-        if (freeo && nb == NB_TWOSTEP) c = touches_flag(R, o, R.st.flag_a);
-        R.st.flag_b[o] = c;
+        if (freeo && nb == NB_TWOSTEP) c = touches_flag(R, o, R.c->st.flag_a);
+        R.c->st.flag_b[o] = c;
     }
     sb_cta_sync();
 }
 
 SB_DEV void candidate_sizes(Run &R, int k0, int v0, int k1 = -1, int v1 = 0) {
     const SbProblem &P = *R.P;
-    for (int i = sb_tid(); i < P.K; i += sb_nthr()) R.rp.ssz[i] = i == k0 ? v0 : (i == k1 ? v1 : R.rp.sizes[i]);
+    for (int i = sb_tid(); i < P.K; i += sb_nthr()) R.c->rp.ssz[i] = i == k0 ? v0 : (i == k1 ? v1 : R.c->rp.sizes[i]);
     sb_cta_sync();
+}
+SB_DEV int n_free(const Run &R) {
+    int occ = 0;
+    for (int k = 0; k < R.P->K; k++) occ += R.c->rp.sizes[k];
+    return R.P->N - occ;
 }
 
 // -----------------------------------------------------------------------------------------
 // AlterCluster grow / shrink (operators.py:969-1249)
 // -----------------------------------------------------------------------------------------
+// posterior-derived value of the CTA's objects selected by `sel(o)`: v(o) = fn(posterior(o));
+// lane_out(o, v) receives the values.  One pass; tables are built if it pays.
+template <class Sel, class Out>
+SB_DEV void posterior_pass(Run &R, int k, int view, bool flat, bool use_geo, int m_size, long long n_obj, Sel sel, Out lane_out) {
+    const SbProblem &P = *R.P;
+    int lo, hi; team_range(R, P.N, lo, hi);
+    const bool geo = use_geo && P.geo && !flat;
+    const bool tables = !flat && pass_uses_tables(R, n_obj);
+    if (tables) build_tables(R, k, false);
+    PH(R, 20);
+    batch_items<Marg>(lo, hi,
+        [&](int o) {
+            Marg a; a.on = sel(o) ? 1 : 0; a.geo = 0.0; a.p0 = prod_one(); a.p1 = prod_one();
+            if (a.on && !flat) {
+                if (tables) obj_marginals<true>(R, o, k, false, a.p0, a.p1);
+                else obj_marginals<false>(R, o, k, false, a.p0, a.p1);
+                if (geo) a.geo = geo_delta(R, o, k, view, m_size);
+            }
+            return a;
+        },
+        [&](int o, const Marg &a) { lane_out(o, a.on != 0, a.on ? posterior_tail(R, a, flat, geo) : 0.0); });
+    sb_cta_sync();
+    PH(R, 21);
+}
+
 SB_DEV Prop op_alter_cluster(Run &R, bool gibbsish, bool use_geo, int nb) {
     const SbProblem &P = *R.P;
     Prop pr = prop_init(0, 0.0, -SB_INF);
     int k = draw_index(R.D, SITE_CLUSTER, 0, P.K);
-    int size = R.rp.sizes[k];
+    int size = R.c->rp.sizes[k];
     double extra = 0.0; bool grow;
     if (size == P.min_size) { grow = true; extra = -log(2.0); }
     else if (size == P.max_size) { grow = false; extra = -log(2.0); }
     else grow = draw_uniform(R.D, SITE_GROW) < R.p_grow;
-    int lo, hi; team_range(R, P.N, lo, hi);
-    const int gw = sb_warp(), nw = sb_nwarps();
-    double *val = R.st.val[R.vpar];
+    const bool flat = R.sfp || !gibbsish;
+    double *val = R.c->st.val[R.vpar];
+    const int free_now = n_free(R);
 
     if (grow) {
-        grow_candidates(R, k, nb, 0);
-        double cnt[1] = {0.0};
-        for (int o = lo + gw; o < hi; o += nw) {
-            double v = 0.0;
-            if (R.st.flag_b[o]) { v = heat(R, cluster_posterior(R, o, k, 0, gibbsish, use_geo, size)); if (sb_lane() == 0) cnt[0] += 1.0; }
-            if (sb_lane() == 0) val[o] = v;
-        }
-        team_sum<1>(R, cnt);
-        if (cnt[0] == 0.0 || size == P.max_size) return pr;
+        if (nb != NB_EVERYWHERE) grow_candidates(R, k, nb, 0);      // everywhere: every free object is a candidate
+        PH(R, 2);
+        double ex[2] = {0.0, 0.0};
+        posterior_pass(R, k, 0, flat, use_geo, size, free_now, [&](int o) { return nb == NB_EVERYWHERE ? m_cl(R, o) < 0 : R.c->st.flag_b[o] != 0; },
+                       [&](int o, bool on, double post) { val[o] = on ? heat(R, post) : 0.0; if (on) ex[0] += 1.0;
+#ifdef SB_DEBUG_PRINT
+                           if (R.i_step == 1 && R.c->slot->cfg.seed == 100) printf("FWD o=%d on=%d cl=%d flag=%d warp=%d lane=%d\n", o, (int)on, m_cl(R, o), (int)R.c->st.flag_b[o], sb_warp(), sb_lane());
+#endif
+                       });
         double total;
-        int o = team_pick(R, val, P.N, draw_uniform(R.D, SITE_OBJECT), total);
+        int o = team_pick(R, val, P.N, draw_uniform(R.D, SITE_OBJECT), total, ex);
+        PH(R, 4);
         R.vpar ^= 1;
+        if (ex[0] == 0.0 || size == P.max_size) return pr;
         if (o < 0) return pr;
         double lq_obj = log(val[o] / total);
         pr.changed = 1; pr.M = 1;
         R.chg_mode = CHG_ONE; R.chg_o = o; R.chg_new = k;
-        if (sb_tid() == 0) R.slist[0] = o;
-        pr.S = R.slist;
+        if (sb_tid() == 0) R.c->slist[0] = o;
+        pr.S = R.c->slist;
         candidate_sizes(R, k, size + 1);
         double lqs, lqbs;
-        resample_sources(R, pr, 1, R.slist, k, k, false, lqs, lqbs);
+        resample_sources(R, pr, 1, R.c->slist, k, k, false, lqs, lqbs);
         // back: remove o again, p_remove ~ 1 - posterior over the members of the grown cluster
         double s[2] = {0.0, 0.0};
-        for (int j = lo + gw; j < hi; j += nw) {
-            if (cl_of(R, j, 1) != k) continue;
-            double v = 1.0 - heat(R, cluster_posterior(R, j, k, 1, gibbsish, use_geo, size + 1));
-            if (sb_lane() == 0) { s[0] += v; if (j == o) s[1] = v; }
-        }
+        posterior_pass(R, k, 1, flat, use_geo, size + 1, size + 1, [&](int j) { return cl_of(R, j, 1) == k; },
+                       [&](int j, bool on, double post) { if (on) { double v = 1.0 - heat(R, post); s[0] += v; if (j == o) s[1] = v; } });
         team_sum<2>(R, s);
+        PH(R, 13);
         double lqb_obj = log(s[1] / s[0]);
         pr.lq = lq_obj + lqs + log(R.p_grow);
         pr.lqb = lqb_obj + lqbs + log(1.0 - R.p_grow) + extra;
+#ifdef SB_DEBUG_PRINT
+        if (sb_tid() == 0 && R.rank == 0) printf("grow k=%d o=%d ncand=%g total=%g lq_obj=%g lqs=%g lqbs=%g lqb_obj=%g\n", k, o, ex[0], total, lq_obj, lqs, lqbs, lqb_obj);
+#endif
     } else {
         if (size == P.min_size) return pr;
-        for (int o = lo + gw; o < hi; o += nw) {
-            double v = 0.0;
-            if (R.st.cluster_of[o] == k) v = 1.0 - heat(R, cluster_posterior(R, o, k, 0, gibbsish, use_geo, size));
-            if (sb_lane() == 0) val[o] = v;
-        }
-        sb_cta_sync();
+        posterior_pass(R, k, 0, flat, use_geo, size, size, [&](int o) { return m_cl(R, o) == k; },
+                       [&](int o, bool on, double post) { val[o] = on ? 1.0 - heat(R, post) : 0.0; });
         double total;
         int o = team_pick(R, val, P.N, draw_uniform(R.D, SITE_OBJECT), total);
+        PH(R, 4);
         R.vpar ^= 1;
         if (o < 0) return pr;
         double lq_obj = log(val[o] / total);
         pr.changed = 1; pr.M = 1;
         R.chg_mode = CHG_ONE; R.chg_o = o; R.chg_new = -1;
-        if (sb_tid() == 0) R.slist[0] = o;
-        pr.S = R.slist;
+        if (sb_tid() == 0) R.c->slist[0] = o;
+        pr.S = R.c->slist;
         candidate_sizes(R, k, size - 1);
         double lqs, lqbs;
-        resample_sources(R, pr, 1, R.slist, k, k, false, lqs, lqbs);
+        resample_sources(R, pr, 1, R.c->slist, k, k, false, lqs, lqbs);
         // back: grow by o again
-        grow_candidates(R, k, nb, 1);
+        if (nb != NB_EVERYWHERE) grow_candidates(R, k, nb, 1);
         double s[3] = {0.0, 0.0, 0.0};
-        for (int j = lo + gw; j < hi; j += nw) {
-            if (!R.st.flag_b[j]) continue;
-            double v = heat(R, cluster_posterior(R, j, k, 1, gibbsish, use_geo, size - 1));
-            if (sb_lane() == 0) { s[0] += v; if (j == o) { s[1] = v; s[2] = 1.0; } }
-        }
+        posterior_pass(R, k, 1, flat, use_geo, size - 1, free_now + 1, [&](int j) { return nb == NB_EVERYWHERE ? cl_of(R, j, 1) < 0 : R.c->st.flag_b[j] != 0; },
+                       [&](int j, bool on, double post) { if (on) { double v = heat(R, post); s[0] += v; if (j == o) { s[1] = v; s[2] = 1.0; } } });
         team_sum<3>(R, s);
+        PH(R, 13);
         if (s[2] == 0.0) { pr.force_reject = 1; return pr; }   // o is not a grow candidate of the shrunk cluster
         double lqb_obj = log(s[1] / s[0]);
         pr.lq = lq_obj + lqs + log(1.0 - R.p_grow);
@@ -974,19 +1320,29 @@ SB_DEV void wide_probs(Run &R, double *p, int k, int n_av, int view, bool use_ge
     const SbProblem &P = *R.P;
     const double eps = 0.01 / (double)P.N;
     int lo, hi; team_range(R, n_av, lo, hi);
-    const int gw = sb_warp(), nw = sb_nwarps();
-    for (int i = lo + gw; i < hi; i += nw) {
-        int o = R.st.list_b[i];
-        double raw = 0.5;
-        if (!R.sfp) {
-            double s0, s1;
-            cluster_marginals(R, o, k, view, true, s0, s1);
-            double m0 = exp(s0 * R.invT), m1 = exp(s1 * R.invT);
-            if (use_geo && P.geo) m1 = m1 * exp(geo_delta(R, o, k, view, size_k) * R.invTp / SB_GEO_SCALER);
-            raw = m1 / (m0 + m1 + SB_EPS32);
-        }
-        if (sb_lane() == 0) p[i] = raw + SB_EPS32;
-    }
+    const bool geo = use_geo && P.geo && !R.sfp;
+    const bool tables = !R.sfp && pass_uses_tables(R, n_av);
+    if (tables) build_tables(R, k, true);
+    batch_items<Marg>(lo, hi,
+        [&](int i) {
+            Marg a; a.on = 1; a.geo = 0.0; a.p0 = prod_one(); a.p1 = prod_one();
+            if (!R.sfp) {
+                int o = R.c->st.list_b[i];
+                if (tables) obj_marginals<true>(R, o, k, true, a.p0, a.p1);
+                else obj_marginals<false>(R, o, k, true, a.p0, a.p1);
+                if (geo) a.geo = geo_delta(R, o, k, view, size_k);
+            }
+            return a;
+        },
+        [&](int i, const Marg &a) {
+            double raw = 0.5;
+            if (!R.sfp) {
+                double m0 = exp(prod_log(a.p0) * R.invT), m1 = exp(prod_log(a.p1) * R.invT);
+                if (geo) m1 = m1 * exp(a.geo * R.invTp / SB_GEO_SCALER);
+                raw = m1 / (m0 + m1 + SB_EPS32);
+            }
+            p[i] = raw + SB_EPS32;
+        });
     sb_cta_sync();
     double s[1];
     s[0] = 0.0; for (int i = lo + sb_tid(); i < hi; i += sb_nthr()) s[0] += p[i];
@@ -998,7 +1354,7 @@ SB_DEV void wide_probs(Run &R, double *p, int k, int n_av, int view, bool use_ge
     double s2 = s[0], old_size = (double)size_k;
     s[0] = 0.0;
     for (int i = lo + sb_tid(); i < hi; i += sb_nthr()) {
-        double mem = cl_of(R, R.st.list_b[i], view) == k ? 1.0 : 0.0;
+        double mem = cl_of(R, R.c->st.list_b[i], view) == k ? 1.0 : 0.0;
         double v = (1.0 - SB_W_STAY) * (p[i] / s2) + SB_W_STAY * (mem / old_size);
         p[i] = v; s[0] += v;
     }
@@ -1021,9 +1377,9 @@ SB_DEV Prop op_alter_cluster_wide(Run &R, bool use_geo) {
     const SbProblem &P = *R.P;
     Prop pr = prop_init(0, 0.0, -SB_INF);
     int k = draw_index(R.D, SITE_CLUSTER, 0, P.K);
-    int size = R.rp.sizes[k];
-    int n_av = team_compact(R, P.N, R.st.list_b, [&](int o) { int c = R.st.cluster_of[o]; return c < 0 || c == k; });
-    double *p = R.st.val[R.vpar];
+    int size = R.c->rp.sizes[k];
+    int n_av = team_compact(R, P.N, R.c->st.list_b, [&](int o) { int c = m_cl(R, o); return c < 0 || c == k; });
+    double *p = R.c->st.val[R.vpar];
     wide_probs(R, p, k, n_av, 0, use_geo, size);
     int lo, hi; team_range(R, n_av, lo, hi);
     // redraw until the membership changes (operators.py:1515-1517)
@@ -1031,10 +1387,10 @@ SB_DEV Prop op_alter_cluster_wide(Run &R, bool use_geo) {
     for (int attempt = 0;; attempt++) {
         st[0] = 0.0; st[1] = 0.0; st[2] = 0.0;
         for (int i = lo + sb_tid(); i < hi; i += sb_nthr()) {
-            int o = R.st.list_b[i];
+            int o = R.c->st.list_b[i];
             bool nm = draw_uniform_f32(R.D, SITE_WIDE, (uint32_t)i, attempt) < p[i];
-            bool old = R.st.cluster_of[o] == k;
-            R.st.flag_a[o] = nm;
+            bool old = m_cl(R, o) == k;
+            R.c->st.flag_a[o] = nm;
             st[0] += nm != old ? 1.0 : 0.0; st[1] += nm ? 1.0 : 0.0;
         }
         team_sum<3>(R, st);
@@ -1046,8 +1402,8 @@ SB_DEV Prop op_alter_cluster_wide(Run &R, bool use_geo) {
     // forward probability
     double a[1] = {0.0}, b[1] = {1.0};
     for (int i = lo + sb_tid(); i < hi; i += sb_nthr()) {
-        int o = R.st.list_b[i];
-        bool nm = R.st.flag_a[o], old = R.st.cluster_of[o] == k;
+        int o = R.c->st.list_b[i];
+        bool nm = R.c->st.flag_a[o], old = m_cl(R, o) == k;
         a[0] += log(nm ? p[i] : 1.0 - p[i]);
         b[0] *= old ? p[i] : 1.0 - p[i];
     }
@@ -1055,20 +1411,20 @@ SB_DEV Prop op_alter_cluster_wide(Run &R, bool use_geo) {
     team_sum<1, true>(R, b);
     double lq = a[0] - log(1.0 - b[0]);
     // the list of flipped objects (object ids, increasing)
-    int M = team_compact(R, n_av, R.st.list_a, [&](int i) { int o = R.st.list_b[i]; return (bool)R.st.flag_a[o] != (R.st.cluster_of[o] == k); });
-    for (int m = R.rank * sb_nthr() + sb_tid(); m < M; m += R.tsize * sb_nthr()) R.st.list_a[m] = R.st.list_b[R.st.list_a[m]];
+    int M = team_compact(R, n_av, R.c->st.list_a, [&](int i) { int o = R.c->st.list_b[i]; return (bool)R.c->st.flag_a[o] != (m_cl(R, o) == k); });
+    for (int m = R.rank * sb_nthr() + sb_tid(); m < M; m += R.tsize * sb_nthr()) R.c->st.list_a[m] = R.c->st.list_b[R.c->st.list_a[m]];
     team_sync(R);
     R.chg_mode = CHG_WIDE; R.chg_k = k;
     candidate_sizes(R, k, n_new);
-    pr.changed = 1; pr.M = M; pr.S = R.st.list_a;
+    pr.changed = 1; pr.M = M; pr.S = R.c->st.list_a;
     double lqs, lqbs;
-    resample_sources(R, pr, M, R.st.list_a, k, k, false, lqs, lqbs);
+    resample_sources(R, pr, M, R.c->st.list_a, k, k, false, lqs, lqbs);
     // backward probability from the new state
     wide_probs(R, p, k, n_av, 1, use_geo, n_new);
     a[0] = 0.0; b[0] = 1.0;
     for (int i = lo + sb_tid(); i < hi; i += sb_nthr()) {
-        int o = R.st.list_b[i];
-        bool nm = R.st.flag_a[o], old = R.st.cluster_of[o] == k;
+        int o = R.c->st.list_b[i];
+        bool nm = R.c->st.flag_a[o], old = m_cl(R, o) == k;
         a[0] += log(old ? p[i] : 1.0 - p[i]);
         b[0] *= nm ? p[i] : 1.0 - p[i];
     }
@@ -1082,40 +1438,48 @@ SB_DEV Prop op_alter_cluster_wide(Run &R, bool use_geo) {
 // -----------------------------------------------------------------------------------------
 // ClusterJump (operators.py:1668-1827)
 // -----------------------------------------------------------------------------------------
+struct JumpAcc { Prod ps, pj; int on; };
+
 SB_DEV Prop op_cluster_jump(Run &R) {
     const SbProblem &P = *R.P;
     Prop pr = prop_init(0, 0.0, -SB_INF);
     int k_src, k_tgt;
     draw_pair(R.D, SITE_JUMP, P.K, k_src, k_tgt);
-    if (R.rp.sizes[k_src] <= P.min_size || R.rp.sizes[k_tgt] >= P.max_size) return pr;
+    if (R.c->rp.sizes[k_src] <= P.min_size || R.c->rp.sizes[k_tgt] >= P.max_size) return pr;
     int lo, hi; team_range(R, P.N, lo, hi);
-    const int gw = sb_warp(), nw = sb_nwarps();
-    double *val = R.st.val[R.vpar];
-    for (int o = lo + gw; o < hi; o += nw) {
-        double v = 0.0;
-        if (R.st.cluster_of[o] == k_src) v = jump_prob(R, o, k_src, k_tgt, 0);
-        if (sb_lane() == 0) val[o] = v;
-    }
+    double *val = R.c->st.val[R.vpar];
+    batch_items<JumpAcc>(lo, hi,
+        [&](int o) {
+            JumpAcc a; a.on = m_cl(R, o) == k_src; a.ps = prod_one(); a.pj = prod_one();
+            if (a.on) jump_marginals(R, o, k_src, k_tgt, a.ps, a.pj);
+            return a;
+        },
+        [&](int o, const JumpAcc &a) { val[o] = a.on ? jump_tail(R, a.ps, a.pj) : 0.0; });
     sb_cta_sync();
+    PH(R, 18);
     double total;
     int o = team_pick(R, val, P.N, draw_uniform(R.D, SITE_OBJECT), total);
+    PH(R, 4);
     R.vpar ^= 1;
     if (o < 0) return pr;
     double lq_obj = log(val[o] / total);
     pr.changed = 1; pr.M = 1;
     R.chg_mode = CHG_ONE; R.chg_o = o; R.chg_new = k_tgt;
-    if (sb_tid() == 0) R.slist[0] = o;
-    pr.S = R.slist;
-    candidate_sizes(R, k_src, R.rp.sizes[k_src] - 1, k_tgt, R.rp.sizes[k_tgt] + 1);
+    if (sb_tid() == 0) R.c->slist[0] = o;
+    pr.S = R.c->slist;
+    candidate_sizes(R, k_src, R.c->rp.sizes[k_src] - 1, k_tgt, R.c->rp.sizes[k_tgt] + 1);
     double lqs, lqbs;
-    resample_sources(R, pr, 1, R.slist, k_tgt, k_src, true, lqs, lqbs);
+    resample_sources(R, pr, 1, R.c->slist, k_tgt, k_src, true, lqs, lqbs);
     double s[2] = {0.0, 0.0};
-    for (int j = lo + gw; j < hi; j += nw) {
-        if (cl_of(R, j, 1) != k_tgt) continue;
-        double v = jump_prob(R, j, k_tgt, k_src, 1);
-        if (sb_lane() == 0) { s[0] += v; if (j == o) s[1] = v; }
-    }
+    batch_items<JumpAcc>(lo, hi,
+        [&](int j) {
+            JumpAcc a; a.on = cl_of(R, j, 1) == k_tgt; a.ps = prod_one(); a.pj = prod_one();
+            if (a.on) jump_marginals(R, j, k_tgt, k_src, a.ps, a.pj);
+            return a;
+        },
+        [&](int j, const JumpAcc &a) { if (a.on) { double v = jump_tail(R, a.ps, a.pj); s[0] += v; if (j == o) s[1] = v; } });
     team_sum<2>(R, s);
+    PH(R, 19);
     pr.lq = lq_obj + lqs;
     pr.lqb = log(s[1] / s[0]) + lqbs;
     return pr;
@@ -1125,22 +1489,21 @@ SB_DEV Prop op_cluster_jump(Run &R) {
 // GibbsSampleSource (operators.py:423-579)
 // -----------------------------------------------------------------------------------------
 // calculate_source_posterior (operators.py:554-574) of object o at feature f -> q[c] (normalised)
-SB_DEV void source_posterior(const Run &R, int o, int f, int x, int view, int k_o, int pat, int z, double *q) {
+SB_DEV void source_posterior(const Run &R, int o, int f, int x, int k_o, int pat, int z, double (&q)[SB_UC]) {
     const SbProblem &P = *R.P;
     const int C = P.C;
-    const size_t FS = (size_t)P.F * P.S;
-    const double *w = R.rp.wp + ((size_t)(pat * 2 + z) * P.F + f) * C;
+    const double *w = R.c->rp.wp + ((size_t)(pat * 2 + z) * P.F + f) * C;
     const bool unitT = R.T == 1.0;
     double tot = 0.0;
-    for (int c = 0; c < C; c++) {
+    SB_FOR_C(c, C) {
         double l = 1.0;
         if (!R.sfp) {
-            int g = c == 0 ? k_o : conf_group(P, c, o);
-            l = g < 0 ? 0.0 : pow_inv(rowP(R, g, view, FS)[(size_t)f * P.S + x], R.invT, unitT);
+            int g = c == 0 ? k_o : conf_group(R, c, o);
+            l = g < 0 ? 0.0 : pow_inv(entry_P(R, g, f, x), R.invT, unitT);
         }
         q[c] = l * w[c]; tot += q[c];
     }
-    for (int c = 0; c < C; c++) q[c] /= tot;
+    SB_FOR_C(c, C) q[c] /= tot;
 }
 
 SB_DEV Prop op_gibbs_source(Run &R, bool groups_mode) {
@@ -1149,10 +1512,11 @@ SB_DEV Prop op_gibbs_source(Run &R, bool groups_mode) {
     Prop pr = prop_init(1, 0.0, 0.0);
     // --- select_object_subset (operators.py:461-494) -> S[0..M)
     int M = 0;
-    const int *S = R.slist;
+    const int *S = R.c->slist;
+    sb_cta_sync();
     if (N <= SB_SRC_MIN) {
         M = N;
-        if (sb_tid() < N) R.slist[sb_tid()] = sb_tid();
+        if (sb_tid() < N) R.c->slist[sb_tid()] = sb_tid();
         sb_cta_sync();
     } else {
         int pop = N, kmax = SB_SRC_MAX_RANDOM < N ? SB_SRC_MAX_RANDOM : N;
@@ -1165,8 +1529,8 @@ SB_DEV Prop op_gibbs_source(Run &R, bool groups_mode) {
             identity = false;
             if (ci == C - 1) {
                 int g = draw_index(R.D, SITE_COMPONENT, 1, P.K);
-                pop = team_compact(R, N, R.st.list_b, [&](int o) { return R.st.cluster_of[o] == g; });
-                popl = R.st.list_b;
+                pop = team_compact(R, N, R.c->st.list_b, [&](int o) { return m_cl(R, o) == g; });
+                popl = R.c->st.list_b;
             } else {
                 int g = draw_index(R.D, SITE_COMPONENT, 1, P.conf_ng[ci]);
                 int row = P.goff[ci + 1] - P.K + g;
@@ -1176,12 +1540,12 @@ SB_DEV Prop op_gibbs_source(Run &R, bool groups_mode) {
         }
         if (!identity && pop <= kmax) {
             M = pop;
-            if (sb_tid() < M) R.slist[sb_tid()] = popl[sb_tid()];
+            if (sb_tid() < M) R.c->slist[sb_tid()] = popl[sb_tid()];
         } else {
             M = kmax;
             // uniform k-subset: Floyd's algorithm over ranks, then sort (oracle/draws.py:subset_of)
             if (sb_tid() == 0) {
-                int ch[32];
+                int *ch = R.c->slist;
                 if (R.D.tv) {
                     for (int j = 0; j < M; j++) ch[j] = (int)R.D.tv[R.D.toff[SITE_SUBSET] + j];   // object ids
                 } else {
@@ -1195,61 +1559,72 @@ SB_DEV Prop op_gibbs_source(Run &R, bool groups_mode) {
                     if (!identity) for (int j = 0; j < M; j++) ch[j] = popl[ch[j]];
                 }
                 for (int a = 1; a < M; a++) { int v = ch[a], b = a - 1; while (b >= 0 && ch[b] > v) { ch[b + 1] = ch[b]; b--; } ch[b + 1] = v; }
-                for (int j = 0; j < M; j++) R.slist[j] = ch[j];
             }
         }
         sb_cta_sync();
     }
     pr.M = M; pr.S = S;
     R.chg_mode = CHG_NONE;
-    for (int i = sb_tid(); i < P.K; i += sb_nthr()) R.rp.ssz[i] = R.rp.sizes[i];
+    for (int i = sb_tid(); i < P.K; i += sb_nthr()) R.c->rp.ssz[i] = R.c->rp.sizes[i];
     const long long items = (long long)M * F;
-    int32_t *Hc = hist_begin(R);
-    for (int m = sb_tid(); m < M; m += sb_nthr()) { mark_object(R, S[m]); R.rp.selbuf[m] = R.st.osel[S[m]] ^ 1; }
-    sb_cta_sync();
-    // --- G1: forward conditional, draw, counts delta
-    double acc[1] = {0.0};
+    PH(R, 14);
+    int32_t *Hc = proposal_open(R, M, S);
+    PH(R, 6);
+    // --- G1: forward conditional from the committed tables, draw
+    double acc[2] = {0.0, 0.0};
     for (long long it = sb_tid(); it < items; it += sb_nthr()) {
         int m = (int)(it / F), f = (int)(it % F), o = S[m];
         int x = sb_ldg(P.x + (size_t)o * P.ldx + f);
-        uint8_t *sn = R.st.src[R.st.osel[o] ^ 1] + (size_t)o * P.ldx;
+        uint8_t *sn = R.c->st.src[m_osel(R, o) ^ 1] + (size_t)o * P.ldx;
         if (x == SB_NA_U8) { sn[f] = SB_NA_U8; continue; }
-        int k_o = R.st.cluster_of[o], pat = sb_ldg(P.pat_id + o), z = k_o >= 0;
-        double q[SB_MAXC];
-        source_posterior(R, o, f, x, 0, k_o, pat, z, q);
-        double u = draw_uniform(R.D, SITE_GIBBS, (uint32_t)((size_t)m * F + f));
-        double cum = 0.0, last = 0.0;
-        for (int c = 0; c < C; c++) last += q[c];
-        int nw = 0; bool got = false;
-        for (int c = 0; c < C; c++) { cum += q[c]; if (!got && u < cum / last) { nw = c; got = true; } }
-        int c_old = R.st.src[R.st.osel[o]][(size_t)o * P.ldx + f];
-        acc[0] += log(q[nw]);
+        int k_o = m_cl(R, o), pat = m_pat(R, o), z = k_o >= 0;
+        double q[SB_UC];
+        source_posterior(R, o, f, x, k_o, pat, z, q);
+        int nw = categorical(q, C, draw_uniform(R.D, SITE_GIBBS, (uint32_t)((size_t)m * F + f)));
+        int c_old = R.c->st.src[m_osel(R, o)][(size_t)o * P.ldx + f];
+        acc[0] += log(pick_c(q, C, nw));
+        const double *lw = R.c->rp.lw + ((size_t)(pat * 2 + z) * F + f) * C;
+        if (nw != c_old) acc[1] += lw[nw] - lw[c_old];
         sn[f] = (uint8_t)nw;
-        if (nw != c_old) {
-            int g0 = c_old == 0 ? k_o : conf_group(P, c_old, o), g1 = nw == 0 ? k_o : conf_group(P, nw, o);
-            if (g0 >= 0) sb_atomic_add_i32(R.rp.dneg + ((size_t)g0 * F + f) * P.S + x, 1);
-            if (g1 >= 0) sb_atomic_add_i32(R.rp.dpos + ((size_t)g1 * F + f) * P.S + x, 1);
-            sb_atomic_add_i32(Hc + ((size_t)(pat * 2 + z) * F + f) * C + c_old, -1);
-            sb_atomic_add_i32(Hc + ((size_t)(pat * 2 + z) * F + f) * C + nw, 1);
-        }
     }
-    block_sum<1>(R, acc);
-    pr.lq = acc[0];
-    pr.src_changed = 1;
-    candidate_rows(R, pr, false);
-    // --- G2: backward conditional from the new tables, evaluated at the old sources
-    acc[0] = 0.0;
+    sb_cta_sync();
+    PH(R, 15);
+    // --- counts delta (after every forward read of the tables)
     for (long long it = sb_tid(); it < items; it += sb_nthr()) {
         int m = (int)(it / F), f = (int)(it % F), o = S[m];
         int x = sb_ldg(P.x + (size_t)o * P.ldx + f);
         if (x == SB_NA_U8) continue;
-        int k_o = R.st.cluster_of[o], pat = sb_ldg(P.pat_id + o), z = k_o >= 0;
-        double q[SB_MAXC];
-        source_posterior(R, o, f, x, R.sfp ? 0 : 1, k_o, pat, z, q);
-        acc[0] += log(q[R.st.src[R.st.osel[o]][(size_t)o * P.ldx + f]]);
+        int nw = R.c->st.src[m_osel(R, o) ^ 1][(size_t)o * P.ldx + f], c_old = R.c->st.src[m_osel(R, o)][(size_t)o * P.ldx + f];
+        if (nw == c_old) continue;
+        int k_o = m_cl(R, o), pat = m_pat(R, o), z = k_o >= 0;
+        int g0 = c_old == 0 ? k_o : conf_group(R, c_old, o), g1 = nw == 0 ? k_o : conf_group(R, nw, o);
+        if (g0 >= 0) count_add(R, g0, f, x, -1);
+        if (g1 >= 0) count_add(R, g1, f, x, 1);
+        sb_atomic_add_i32(Hc + ((size_t)(pat * 2 + z) * F + f) * C + c_old, -1);
+        sb_atomic_add_i32(Hc + ((size_t)(pat * 2 + z) * F + f) * C + nw, 1);
     }
-    block_sum<1>(R, acc);
-    pr.lqb = acc[0];
+    block_sum<2>(R, acc);
+    pr.lq = acc[0];
+    pr.sp_new = R.pr_src + acc[1];
+    pr.src_changed = 1;
+    PH(R, 16);
+    proposal_rows(R);
+    PH(R, 10);
+    pr.geo_new = candidate_geo(R, false);
+    // --- G2: backward conditional from the new tables, evaluated at the old sources
+    double bq[1] = {0.0};
+    for (long long it = sb_tid(); it < items; it += sb_nthr()) {
+        int m = (int)(it / F), f = (int)(it % F), o = S[m];
+        int x = sb_ldg(P.x + (size_t)o * P.ldx + f);
+        if (x == SB_NA_U8) continue;
+        int k_o = m_cl(R, o), pat = m_pat(R, o), z = k_o >= 0;
+        double q[SB_UC];
+        source_posterior(R, o, f, x, k_o, pat, z, q);
+        bq[0] += log(pick_c(q, C, R.c->st.src[m_osel(R, o)][(size_t)o * P.ldx + f]));
+    }
+    block_sum<1>(R, bq);
+    PH(R, 17);
+    pr.lqb = bq[0];
     pr.need_sync = 1;
     return pr;
 }
@@ -1269,7 +1644,7 @@ SB_DEV Prop op_gibbs_weights(Run &R) {
     int i1, i2;
     draw_pair(R.D, SITE_WPAIR, C, i1, i2);
     R.chg_mode = CHG_NONE;
-    const int32_t *H = R.rp.H[R.rp.hcur];
+    const int32_t *H = R.c->rp.H[R.hcur];
     for (int f = sb_tid(); f < F; f += sb_nthr()) {
         // counts of sources over the objects that have both components (operators.py:648-656)
         double c1 = sb_ldg(P.alpha_w + (size_t)f * C + i1), c2 = sb_ldg(P.alpha_w + (size_t)f * C + i2);
@@ -1284,47 +1659,50 @@ SB_DEV Prop op_gibbs_weights(Run &R) {
         double a = 1.0 + c2 / R.Tp, b = 1.0 + c1 / R.Tp;
         double a2 = draw_beta(R.D, a, b, (uint32_t)f);
         // float32 arithmetic of resample_weight_for_two_components (operators.py:664-672)
-        float Wo[SB_MAXC], Wn[SB_MAXC];
-        for (int c = 0; c < C; c++) { Wo[c] = R.rp.W[f * C + c]; Wn[c] = Wo[c]; }
-        float w02 = Wo[i1] + Wo[i2];
-        Wn[i1] = (float)((1.0 - a2) * (double)w02);
-        Wn[i2] = (float)(a2 * (double)w02);
+        float Wo[SB_UC], Wn[SB_UC], wo1 = 0.f, wo2 = 0.f;
+        SB_FOR_C(c, C) { Wo[c] = R.c->rp.W[f * C + c]; Wn[c] = Wo[c]; if (c == i1) wo1 = Wo[c]; if (c == i2) wo2 = Wo[c]; }
+        float w02 = wo1 + wo2;
+        SB_FOR_C(c, C) { if (c == i1) Wn[c] = (float)((1.0 - a2) * (double)w02); if (c == i2) Wn[c] = (float)(a2 * (double)w02); }
         float s = 0.0f;
-        for (int c = 0; c < C; c++) s = s + Wn[c];
-        for (int c = 0; c < C; c++) Wn[c] = Wn[c] / s;
-        double a2_old = (double)(Wo[i2] / w02);
+        SB_FOR_C(c, C) s = s + Wn[c];
+        SB_FOR_C(c, C) Wn[c] = Wn[c] / s;
+        double a2_old = (double)(wo2 / w02);
         double lq = beta_logpdf_nolnB(a2, a, b), lqb = beta_logpdf_nolnB(a2_old, a, b);
         // per-feature target: source likelihood + pointwise weights prior (operators.py:617-623,678-686)
         double lp_old = 0.0, lp_new = 0.0;
         for (int pz = 0; pz < P.n_pat * 2; pz++) {
             int bits = P.pat_bits[pz >> 1], z = pz & 1;
             const int32_t *h = H + ((size_t)pz * F + f) * C;
-            const double *lwo = R.rp.lw + ((size_t)pz * F + f) * C;
+            const double *lwo = R.c->rp.lw + ((size_t)pz * F + f) * C;
             double tot = 0.0;
-            for (int c = 0; c < C; c++) { double hc = c == 0 ? (double)z : (double)((bits >> c) & 1); tot += hc * (double)Wn[c]; }
-            for (int c = 0; c < C; c++) {
-                if (h[c] == 0) continue;
-                double hc = c == 0 ? (double)z : (double)((bits >> c) & 1);
-                lp_old += (double)h[c] * lwo[c];
-                lp_new += (double)h[c] * log(hc * (double)Wn[c] / tot);
+            SB_FOR_C(c, C) { double hc = c == 0 ? (double)z : (double)((bits >> c) & 1); tot += hc * (double)Wn[c]; }
+            SB_FOR_C(c, C) {
+                if (h[c] != 0) {
+                    double hc = c == 0 ? (double)z : (double)((bits >> c) & 1);
+                    lp_old += (double)h[c] * lwo[c];
+                    lp_new += (double)h[c] * log(hc * (double)Wn[c] / tot);
+                }
             }
         }
-        lp_old += weights_prior_row(P, Wo, f);
-        lp_new += weights_prior_row(P, Wn, f);
+        lp_old += weights_prior_row_reg(P, Wo, f);
+        lp_new += weights_prior_row_reg(P, Wn, f);
         double p_acc = exp((lp_new - lp_old + lqb - lq) / R.Tp);
         bool acc = draw_uniform_f32(R.D, SITE_WACCEPT, (uint32_t)f, 0) < p_acc;
-        if (acc) for (int c = 0; c < C; c++) R.rp.W[f * C + c] = Wn[c];
+        if (acc) SB_FOR_C(c, C) R.c->rp.W[f * C + c] = Wn[c];
     }
     sb_cta_sync();
+    PH(R, 22);
     weight_tables(R);
+    PH(R, 23);
     pr.sp_new = source_prior_from_hist(R, H);
     pr.wp_new = weights_prior_total(R);
+    PH(R, 24);
     return pr;
 }
 
 // -----------------------------------------------------------------------------------------
 // full (uncached) evaluation of a state: count rebuild + histogram (distributed, HBM
-// atomics) + tables + likelihood + priors (per replica).
+// atomics) + per-(group, feature) terms + likelihood + priors (per replica).
 // recalculate_feature_counts (sbayes/sampling/counts.py:35-52),
 // Likelihood.__call__ (likelihood.py:47-63), Prior.__call__ (prior.py:74-88).
 // -----------------------------------------------------------------------------------------
@@ -1334,52 +1712,51 @@ SB_DEV void rebuild_state(Run &R) {
     const size_t nG = (size_t)P.G_tot * F * S;
     const int nH = P.n_pat * 2 * F * C;
     const int stride = R.tsize * sb_nthr(), t0 = R.rank * sb_nthr() + sb_tid();
-    for (size_t i = t0; i < nG; i += stride) R.st.counts[i] = 0;
-    for (int i = t0; i < nH; i += stride) R.st.H[i] = 0;
-    for (int k = t0; k < P.K; k += stride) R.st.sizes[k] = 0;
+    for (size_t i = t0; i < nG; i += stride) R.c->st.counts[i] = 0;
+    for (int i = t0; i < nH; i += stride) R.c->st.H[i] = 0;
+    for (int k = t0; k < P.K; k += stride) R.c->st.sizes[k] = 0;
     team_sync(R);
     // histogram pass: warp per object, lanes over features (coalesced byte reads)
     int lo, hi; team_range(R, N, lo, hi);
     for (int o = lo + sb_warp(); o < hi; o += sb_nwarps()) {
-        int k = R.st.cluster_of[o], pat = sb_ldg(P.pat_id + o), z = k >= 0;
-        int gC[SB_MAXC]; gC[0] = k;
-        for (int c = 1; c < C; c++) gC[c] = conf_group(P, c, o);
+        int k = m_cl(R, o), pat = m_pat(R, o), z = k >= 0;
+        int gC[SB_UC]; gC[0] = k;
+        SB_FOR_C1(c, C) gC[c] = conf_group(R, c, o);
         const uint8_t *xr = P.x + (size_t)o * P.ldx;
-        const uint8_t *so = R.st.src[R.st.osel[o]] + (size_t)o * P.ldx;
+        const uint8_t *so = R.c->st.src[m_osel(R, o)] + (size_t)o * P.ldx;
         for (int f = sb_lane(); f < F; f += 32) {
             int x = sb_ldg(xr + f);
             if (x == SB_NA_U8) continue;
             int c = so[f];
             if (c >= C) { R.err = 2; continue; }
-            int g = gC[c];
-            if (g >= 0) sb_atomic_add_i32(R.st.counts + ((size_t)g * F + f) * S + x, 1);
-            sb_atomic_add_i32(R.st.H + ((size_t)(pat * 2 + z) * F + f) * C + c, 1);
+            int g = -1;
+            SB_FOR_C(cc, C) if (cc == c) g = gC[cc];
+            if (g >= 0) sb_atomic_add_i32(R.c->st.counts + ((size_t)g * F + f) * S + x, 1);
+            sb_atomic_add_i32(R.c->st.H + ((size_t)(pat * 2 + z) * F + f) * C + c, 1);
         }
-        if (sb_lane() == 0 && k >= 0) sb_atomic_add_i32(R.st.sizes + k, 1);
+        if (sb_lane() == 0 && k >= 0) sb_atomic_add_i32(R.c->st.sizes + k, 1);
     }
     team_sync(R);
     // every CTA fills its replica
-    for (size_t i = sb_tid(); i < nG; i += sb_nthr()) { R.rp.counts[i] = R.st.counts[i]; R.rp.dneg[i] = 0; R.rp.dpos[i] = 0; }
-    for (int i = sb_tid(); i < nH; i += sb_nthr()) R.rp.H[0][i] = R.st.H[i];
-    for (int i = sb_tid(); i < F * C; i += sb_nthr()) R.rp.W[i] = R.st.W[i];
-    for (int k = sb_tid(); k < P.K; k += sb_nthr()) { R.rp.sizes[k] = R.st.sizes[k]; R.rp.ssz[k] = R.st.sizes[k]; }
-    for (int g = sb_tid(); g < P.G_tot; g += sb_nthr()) R.rp.dirty[g] = 0;
-    R.rp.hcur = 0; R.chg_mode = CHG_NONE;
+    for (size_t i = sb_tid(); i < nG; i += sb_nthr()) { R.c->rp.counts[i] = R.c->st.counts[i]; R.c->rp.dcnt[i] = 0; }
+    for (int i = sb_tid(); i < nH; i += sb_nthr()) R.c->rp.H[0][i] = R.c->st.H[i];
+    for (int i = sb_tid(); i < F * C; i += sb_nthr()) R.c->rp.W[i] = R.c->st.W[i];
+    for (int k = sb_tid(); k < P.K; k += sb_nthr()) { R.c->rp.sizes[k] = R.c->st.sizes[k]; R.c->rp.ssz[k] = R.c->st.sizes[k]; }
+    for (int g = sb_tid(); g < P.G_tot; g += sb_nthr()) R.c->rp.dirty[g] = 0;
+    R.hcur = 0; R.chg_mode = CHG_NONE; R.nd = 0;
     sb_cta_sync();
-    group_rows(R, nullptr, P.G_tot, false);
+    rows_full(R, nullptr, P.G_tot);
+    rows_lh(R, nullptr, P.G_tot);
     weight_tables(R);
-    double v[1] = {0.0};
-    for (int g = sb_tid(); g < P.G_tot; g += sb_nthr()) v[0] += R.rp.lh[g];
-    block_sum<1>(R, v);
-    R.ll = R.sfp ? 0.0 : v[0];
-    R.pr_src = source_prior_from_hist(R, R.rp.H[0]);
+    R.ll = R.sfp ? 0.0 : ll_total(R);
+    R.pr_src = source_prior_from_hist(R, R.c->rp.H[0]);
     R.pr_w = weights_prior_total(R);
-    R.pr_size = size_prior_cta(R, R.rp.sizes);
+    R.pr_size = size_prior_cta(R, R.c->rp.sizes);
     R.pr_geo = 0.0;
     if (P.geo) {
         for (int k = 0; k < P.K; k++) {
             double a, g; geo_cluster(R, k, 0, a, g);
-            if (sb_tid() == 0) { R.rp.geo_agg[k] = a; R.rp.geo_val[k] = g; }
+            if (sb_tid() == 0) { R.c->rp.geo_agg[k] = a; R.c->rp.geo_val[k] = g; }
             R.pr_geo += g;
         }
         sb_cta_sync();
@@ -1401,12 +1778,14 @@ SB_DEV void mcmc_step(Run &R, sb_step_record *rec) {
     if (R.D.tv) op = (int)R.D.tv[R.D.toff[SITE_OP]];
     else {
         double u = draw_uniform(R.D, SITE_OP), cum = 0.0, tot = 0.0;
-        for (int i = 0; i < SB_N_OPS; i++) tot += R.slot->cfg.op_weights[i];
+        for (int i = 0; i < SB_N_OPS; i++) tot += R.c->opw[i];
         op = SB_N_OPS - 1;
-        for (int i = 0; i < SB_N_OPS; i++) { cum += R.slot->cfg.op_weights[i]; if (cum / tot > u) { op = i; break; } }
+        for (int i = 0; i < SB_N_OPS; i++) { cum += R.c->opw[i]; if (cum / tot > u) { op = i; break; } }
     }
     Prop pr;
     const bool geo = P.geo != 0;
+    R.cur_op = op; R.pt = t_begin;
+    PH(R, 1);
     if (op <= OP_GIBBSISH_GEO) {
         // the five AlterCluster variants of the schedule (operators.py:50-124)
         const bool gibbsish = op >= OP_GIBBSISH;
@@ -1417,18 +1796,16 @@ SB_DEV void mcmc_step(Run &R, sb_step_record *rec) {
     else if (op == OP_JUMP) pr = op_cluster_jump(R);
     else if (op == OP_SRC_RANDOM || op == OP_SRC_GROUPS) pr = op_gibbs_source(R, op == OP_SRC_GROUPS);
     else pr = op_gibbs_weights(R);
+    PH(R, 29);
     // candidate posterior (mcmc_chain.py:201-202)
     double ll_new = R.ll, p_size = R.pr_size, p_geo = R.pr_geo, p_w = R.pr_w, p_src = R.pr_src;
     const bool touched = pr.changed != 0;
     if (touched && op == OP_WEIGHTS) { p_src = pr.sp_new; p_w = pr.wp_new; }
     else if (touched) {
-        double v[1] = {0.0};
-        for (int g = sb_tid(); g < P.G_tot; g += sb_nthr()) v[0] += R.rp.dirty[g] ? R.rp.c_lh[g] : R.rp.lh[g];
-        block_sum<1>(R, v);
-        ll_new = R.sfp ? 0.0 : v[0];
+        ll_new = R.sfp ? 0.0 : ll_total(R);
         p_src = pr.sp_new;
         if (P.geo) p_geo = pr.geo_new;
-        p_size = size_prior_cta(R, R.rp.ssz);
+        p_size = size_prior_cta(R, R.c->rp.ssz);
     }
     double prior_new = p_size + p_geo + p_w + p_src;
     double lq = pr.lq, lqb = pr.lqb;
@@ -1451,45 +1828,34 @@ SB_DEV void mcmc_step(Run &R, sb_step_record *rec) {
         rec->prior_new = (touched && !pr.force_reject) ? prior_new : R.pr_size + R.pr_geo + R.pr_w + R.pr_src;
         rec->mh_ratio = ratio; rec->log_u = log_u;
     }
+    PH(R, 30);
     if (touched && op != OP_WEIGHTS) {
         if (pr.need_sync && accept) team_sync(R);     // a fast CTA's commit must not overtake a slow CTA's reads
-        const size_t FS = (size_t)P.F * P.S;
         if (accept) {
             // object-indexed state in HBM: every CTA writes the same values
             for (int m = sb_tid(); m < pr.M; m += sb_nthr()) {
                 int o = pr.S[m];
                 int nc = cl_of(R, o, 1);
-                if (pr.src_changed) R.st.osel[o] = R.rp.selbuf[m];
-                R.st.cluster_of[o] = nc;
+                if (pr.src_changed) { R.c->st.osel[o] = R.c->rp.selbuf[m]; if (R.c->mosel) R.c->mosel[o] = R.c->rp.selbuf[m]; }
+                R.c->st.cluster_of[o] = nc;
+                if (R.c->mcl) R.c->mcl[o] = (int16_t)nc;
             }
-            // replica: copy the candidate rows over the committed ones
-            for (int g = 0; g < P.G_tot; g++) {
-                if (!R.rp.dirty[g]) continue;
-                const size_t b = (size_t)g * FS;
-                for (size_t i = sb_tid(); i < FS; i += sb_nthr()) {
-                    R.rp.counts[b + i] = R.rp.c_counts[b + i];
-                    R.rp.tabP[b + i] = R.rp.c_tabP[b + i];
-                    R.rp.tabT[b + i] = R.rp.c_tabT[b + i];
-                }
-                if (sb_tid() == 0) {
-                    R.rp.lh[g] = R.rp.c_lh[g];
-                    if (P.geo && g < P.K) { R.rp.geo_agg[g] = R.rp.c_geo_agg[g]; R.rp.geo_val[g] = R.rp.c_geo_val[g]; }
-                }
-            }
-            for (int k = sb_tid(); k < P.K; k += sb_nthr()) R.rp.sizes[k] = R.rp.ssz[k];
-            if (pr.src_changed) R.rp.hcur ^= 1;
+            for (int k = sb_tid(); k < P.K; k += sb_nthr()) R.c->rp.sizes[k] = R.c->rp.ssz[k];
+            if (pr.src_changed) R.hcur ^= 1;
         }
-        sb_cta_sync();
-        for (int g = sb_tid(); g < P.G_tot; g += sb_nthr()) R.rp.dirty[g] = 0;
-        sb_cta_sync();
+        proposal_close(R, accept);
     }
     if (accept) {
         R.ll = ll_new; R.pr_size = p_size; R.pr_geo = p_geo; R.pr_w = p_w; R.pr_src = p_src;
         if (!(isfinite(R.ll) && isfinite(prior_new))) R.err = 1;     // mcmc_chain.py:231-236
     }
+    PH(R, 31);
+#if defined(SB_PHASE_PROF) && !defined(SB_HOSTSIM)
+    if (R.rank == 0 && sb_tid() == 0) g_phase_n[op]++;
+#endif
     if (R.rank == 0 && sb_tid() == 0) {
-        if (accept) R.slot->accepts[op]++; else R.slot->rejects[op]++;
-        R.slot->cycles[op] += sb_clock() - t_begin;
+        if (accept) R.c->slot->accepts[op]++; else R.c->slot->rejects[op]++;
+        R.c->slot->cycles[op] += sb_clock() - t_begin;
     }
 }
 
@@ -1499,46 +1865,96 @@ SB_DEV void mcmc_step(Run &R, sb_step_record *rec) {
 SB_DEV void setup_replica(Run &R, const SbLaunch &L, char *smem, char *glob) {
     const SbProblem &P = L.P;
     const SbPlace &pl = L.place;
-    auto at = [&](int a) -> char * { return pl.in_smem[a] ? smem + pl.smem_off[a] : glob + pl.glob_off[a]; };
-    R.rp.wq = (double *)at(A_WQ); R.rp.tabT = (double *)at(A_TABT); R.rp.tabP = (double *)at(A_TABP);
-    R.rp.H[0] = (int32_t *)at(A_H0); R.rp.H[1] = (int32_t *)at(A_H1); R.rp.lw = (double *)at(A_LW);
-    R.rp.counts = (int32_t *)at(A_COUNTS); R.rp.wp = (double *)at(A_WP); R.rp.w1 = (double *)at(A_W1);
-    R.rp.dneg = (int32_t *)at(A_DNEG); R.rp.dpos = (int32_t *)at(A_DPOS);
-    R.rp.c_counts = (int32_t *)(glob + pl.cand_off[0]);
-    R.rp.c_tabP = (double *)(glob + pl.cand_off[1]);
-    R.rp.c_tabT = (double *)(glob + pl.cand_off[2]);
-    R.rp.selbuf = (uint8_t *)(glob + pl.sel_off);
     FixedSmem fx = sb_fixed_smem(P.G_tot, P.K, P.F, P.C, L.smem_members, pl.fixed_off);
-    R.sred = (double *)(smem + fx.sred); R.smem_best = (double *)(smem + fx.best);
-    R.rp.lh = (double *)(smem + fx.lh); R.rp.c_lh = (double *)(smem + fx.c_lh);
-    double *geo = (double *)(smem + fx.geo);
-    R.rp.geo_agg = geo; R.rp.geo_val = geo + P.K; R.rp.c_geo_agg = geo + 2 * P.K; R.rp.c_geo_val = geo + 3 * P.K;
-    R.sint = (int *)(smem + fx.sint); R.slist = (int *)(smem + fx.slist);
-    R.rp.sizes = (int32_t *)(smem + fx.sizes); R.rp.ssz = (int32_t *)(smem + fx.ssz);
-    R.smem_mem = (int *)(smem + fx.mem);
-    R.rp.W = (float *)(smem + fx.W); R.rp.dirty = (uint8_t *)(smem + fx.dirty);
-    R.smem_cap = L.smem_members;
+    RunC *c = (RunC *)(smem + fx.runc);
+    R.c = c;
+    int lo, hi; team_range(R, P.N, lo, hi);
+    if (sb_tid() == 0) {
+        auto at = [&](int a) -> char * { return pl.in_smem[a] ? smem + pl.smem_off[a] : glob + pl.glob_off[a]; };
+        Rep &rp = c->rp;
+        rp.tab0 = (double *)at(A_TAB0); rp.tab1 = (double *)at(A_TAB1);
+        rp.wq = (double *)at(A_WQ); rp.lw = (double *)at(A_LW);
+        rp.wp = pl.alias_w ? rp.wq : (double *)at(A_WP); rp.w1 = pl.alias_w ? rp.wq : (double *)at(A_W1);
+        c->alpha = pl.in_smem[A_ALPHA] ? (const double *)(smem + pl.smem_off[A_ALPHA]) : P.alpha;
+        c->asum = pl.in_smem[A_ASUM] ? (const double *)(smem + pl.smem_off[A_ASUM]) : P.asum;
+        c->applm = pl.in_smem[A_APPLM] ? (const uint64_t *)(smem + pl.smem_off[A_APPLM]) : P.applm;
+        c->combo_rows = pl.in_smem[A_COMBOT] ? (const int32_t *)(smem + pl.smem_off[A_COMBOT]) : P.combo_rows;
+        c->combo_pat = pl.in_smem[A_COMBOT] ? (const int32_t *)(smem + pl.smem_off[A_COMBOT]) + (size_t)P.n_combos * P.n_conf : P.combo_pat;
+        c->mcl = pl.in_smem[A_MCL] ? (int16_t *)(smem + pl.smem_off[A_MCL]) : nullptr;
+        c->mcombo = pl.in_smem[A_MCOMBO] ? (uint16_t *)(smem + pl.smem_off[A_MCOMBO]) : nullptr;
+        c->mosel = pl.in_smem[A_MOSEL] ? (uint8_t *)(smem + pl.smem_off[A_MOSEL]) : nullptr;
+        rp.counts = (int32_t *)at(A_COUNTS); rp.nn = (int32_t *)at(A_NN); rp.dcnt = (int32_t *)at(A_DCNT);
+        rp.rT = (double *)at(A_RT); rp.rP = (double *)at(A_RP); rp.bsT = (double *)at(A_BST);
+        rp.llgf = (double *)at(A_LLGF);
+        rp.bk_llgf = (double *)at(A_BK_LLGF); rp.bk_rP = (double *)at(A_BK_RP); rp.bk_rT = (double *)at(A_BK_RT);
+        rp.H[0] = (int32_t *)at(A_H0); rp.H[1] = (int32_t *)at(A_H1);
+        rp.selbuf = (uint8_t *)(glob + pl.sel_off);
+        c->sred = (double *)(smem + fx.sred); c->smem_best = (double *)(smem + fx.best);
+        rp.lh = (double *)(smem + fx.lh); rp.bk_lh = (double *)(smem + fx.bk_lh);
+        double *geo = (double *)(smem + fx.geo);
+        rp.geo_agg = geo; rp.geo_val = geo + P.K; rp.c_geo_agg = geo + 2 * P.K; rp.c_geo_val = geo + 3 * P.K;
+        c->sint = (int *)(smem + fx.sint); c->slist = (int *)(smem + fx.slist);
+        rp.sizes = (int32_t *)(smem + fx.sizes); rp.ssz = (int32_t *)(smem + fx.ssz);
+        c->smem_mem = (int *)(smem + fx.mem);
+        rp.W = (float *)(smem + fx.W); rp.dlist = (int *)(smem + fx.dlist); rp.dirty = (uint8_t *)(smem + fx.dirty);
+        c->smem_cap = L.smem_members;
+        const bool xb = pl.xblk_rows > 0 && pl.in_smem[A_XBLK];
+        rp.xblk = xb ? (const uint8_t *)at(A_XBLK) : nullptr; rp.xlo = xb ? lo : 0; rp.xhi = xb ? hi : 0;
+    }
+    sb_cta_sync();
+    // stage the problem constants that were given room in shared memory
+    if (pl.in_smem[A_ALPHA]) { double *d = (double *)c->alpha; for (size_t i = sb_tid(); i < (size_t)P.A_rows * P.F * P.S; i += sb_nthr()) d[i] = sb_ldg(P.alpha + i); }
+    if (pl.in_smem[A_ASUM]) { double *d = (double *)c->asum; for (size_t i = sb_tid(); i < (size_t)P.A_rows * P.F; i += sb_nthr()) d[i] = sb_ldg(P.asum + i); }
+    if (pl.in_smem[A_APPLM]) { uint64_t *d = (uint64_t *)c->applm; for (int i = sb_tid(); i < P.F; i += sb_nthr()) d[i] = sb_ldg(P.applm + i); }
+    if (pl.in_smem[A_COMBOT]) {
+        int32_t *d = (int32_t *)c->combo_rows;
+        const int nr = P.n_combos * P.n_conf;
+        for (int i = sb_tid(); i < nr; i += sb_nthr()) d[i] = sb_ldg(P.combo_rows + i);
+        for (int i = sb_tid(); i < P.n_combos; i += sb_nthr()) d[nr + i] = sb_ldg(P.combo_pat + i);
+    }
+    if (c->mcombo) for (int o = sb_tid(); o < P.N; o += sb_nthr()) c->mcombo[o] = (uint16_t)sb_ldg(P.combo_id + o);
+    sb_cta_sync();
+    // the CTA's own block of observation rows
+    if (c->rp.xblk) {
+        uint32_t *dst = (uint32_t *)c->rp.xblk;
+        const uint32_t *srcw = (const uint32_t *)(P.x + (size_t)lo * P.ldx);
+        const int nwords = (hi - lo) * (P.ldx >> 2);
+        for (int i = sb_tid(); i < nwords; i += sb_nthr()) dst[i] = srcw[i];
+        sb_cta_sync();
+    }
 }
 
-SB_KERNEL_BIG sb_run_kernel(SbLaunch L) {
+SB_KERNEL_BIG sb_run_kernel(const SB_GRID_CONSTANT SbLaunch L) {
     Run R;
     R.P = &L.P;
-    R.tsize = L.team; R.rank = sb_cta() % L.team; R.par = 0; R.vpar = 0; R.epoch = 0; R.use_cluster = L.use_cluster;
+    R.tsize = L.team; R.rank = sb_cta() % L.team; R.par = 0; R.vpar = 0; R.spar = 0; R.epoch = 0; R.use_cluster = L.use_cluster;
+    R.hcur = 0; R.nd = 0; R.pt = 0; R.cur_op = 0;
     const int team_id = sb_cta() / L.team, n_teams = sb_ncta() / L.team;
-    R.bar = L.bars + team_id;
-    R.tred = L.tred + (size_t)team_id * 2 * L.team * SB_REDW;
-    setup_replica(R, L, sb_smem(), L.rep_base + (size_t)sb_cta() * L.place.rep_bytes);
+    setup_replica(R, L, sb_smem(), L.rep_base + (size_t)sb_cta() * L.rep_stride);
+    if (sb_tid() == 0) {
+        R.c->bar = L.bars + team_id;
+        R.c->tred = L.tred + (size_t)team_id * 2 * L.team * SB_REDW;
+    }
     for (int s = team_id; s < L.n_slots; s += n_teams) {
-        R.slot = L.slots + s;
-        if (!R.slot->active) continue;
-        R.st = L.states[R.slot->state];
-        const sb_chain_cfg &cfg = R.slot->cfg;
+        SbSlot *slot = L.slots + s;
+        if (!slot->active) continue;
+        sb_cta_sync();
+        if (sb_tid() == 0) {
+            R.c->slot = slot;
+            R.c->st = L.states[slot->state];
+            for (int i = 0; i < SB_N_OPS; i++) R.c->opw[i] = slot->cfg.op_weights[i];
+        }
+        sb_cta_sync();
+        if (R.c->mcl) for (int o = sb_tid(); o < L.P.N; o += sb_nthr()) R.c->mcl[o] = (int16_t)R.c->st.cluster_of[o];
+        if (R.c->mosel) for (int o = sb_tid(); o < L.P.N; o += sb_nthr()) R.c->mosel[o] = R.c->st.osel[o];
+        sb_cta_sync();
+        const sb_chain_cfg &cfg = slot->cfg;
         R.T = cfg.temperature; R.Tp = cfg.prior_temperature; R.invT = 1.0 / R.T; R.invTp = 1.0 / R.Tp;
         R.p_grow = cfg.p_grow; R.sfp = cfg.sample_from_prior;
         R.D.k0 = (uint32_t)(cfg.seed & 0xFFFFFFFFull); R.D.k1 = (uint32_t)(cfg.seed >> 32);
         R.D.tv = L.tape.vals; R.D.toff = nullptr; R.D.tlen = nullptr; R.D.wide_n = 0; R.D.step = 0;
         R.err = 0;
-        R.i_step = (long long)R.st.post[5];
+        R.i_step = (long long)R.c->st.post[5];
         rebuild_state(R);
         for (long long it = 0; it < L.n_steps; it++) {
             if (L.tape.vals) {
@@ -1551,12 +1967,12 @@ SB_KERNEL_BIG sb_run_kernel(SbLaunch L) {
         if (R.rank == 0) {
             // export copies of the replica for the host
             const size_t nG = (size_t)L.P.G_tot * L.P.F * L.P.S;
-            for (size_t i = sb_tid(); i < nG; i += sb_nthr()) R.st.counts[i] = R.rp.counts[i];
-            for (int i = sb_tid(); i < L.P.F * L.P.C; i += sb_nthr()) R.st.W[i] = R.rp.W[i];
+            for (size_t i = sb_tid(); i < nG; i += sb_nthr()) R.c->st.counts[i] = R.c->rp.counts[i];
+            for (int i = sb_tid(); i < L.P.F * L.P.C; i += sb_nthr()) R.c->st.W[i] = R.c->rp.W[i];
             if (sb_tid() == 0) {
-                R.st.post[0] = R.ll; R.st.post[1] = R.pr_size; R.st.post[2] = R.pr_geo; R.st.post[3] = R.pr_w;
-                R.st.post[4] = R.pr_src; R.st.post[5] = (double)R.i_step;
-                if (R.err) R.slot->err = R.err;
+                R.c->st.post[0] = R.ll; R.c->st.post[1] = R.pr_size; R.c->st.post[2] = R.pr_geo; R.c->st.post[3] = R.pr_w;
+                R.c->st.post[4] = R.pr_src; R.c->st.post[5] = (double)R.i_step;
+                if (R.err) slot->err = R.err;
             }
         }
         team_sync(R);
@@ -1569,3 +1985,4 @@ SB_KERNEL sb_export_kernel(SbProblem P, SbShared st, uint8_t *src_out) {
     const size_t t0 = (size_t)sb_cta() * sb_nthr() + sb_tid(), stride = (size_t)sb_ncta() * sb_nthr();
     for (size_t i = t0; i < nS; i += stride) { int o = (int)(i / P.ldx); src_out[i] = st.src[st.osel[o]][i]; }
 }
+}  // namespace SB_NS

@@ -6,7 +6,8 @@
 //   * sb_counts_mma_kernel    int8 tensor-core contraction (membership one-hot x masked state
 //                             one-hot), operands expanded in shared memory from the packed bytes
 #pragma once
-#include "sb_core.cuh"
+#include "sb_platform.cuh"
+#include "sb_types.h"
 
 SB_HD size_t sb_counts_hist_smem(const SbProblem &) { return 0; }
 
@@ -17,7 +18,7 @@ SB_KERNEL sb_counts_hist_kernel(SbProblem P, SbShared st, int32_t *counts) {
     for (int o = sb_cta() * nw + sb_warp(); o < P.N; o += sb_ncta() * nw) {
         int gC[SB_MAXC];
         gC[0] = st.cluster_of[o];
-        for (int c = 1; c < C; c++) gC[c] = conf_group(P, c, o);
+        for (int c = 1; c < C; c++) { int gid = sb_ldg(P.conf_gid + (size_t)(c - 1) * P.N + o); gC[c] = gid < 0 ? -1 : P.goff[c] + gid; }
         const uint8_t *xr = P.x + (size_t)o * P.ldx;
         const uint8_t *so = st.src[st.osel[o]] + (size_t)o * P.ldx;
         for (int f = sb_lane(); f < F; f += 32) {

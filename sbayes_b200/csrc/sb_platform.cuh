@@ -6,7 +6,10 @@
 // (test builds only, see tests/hostsim/hostsim.h) the same wrappers bind to a fibre
 // emulator so the control flow can be checked without a GPU.
 #pragma once
-#define SB_BLOCK 512   /* threads per CTA of the step kernel (product build) */
+#ifndef SB_BLOCK
+#define SB_BLOCK 512
+#endif
+//   /* threads per CTA of the step kernel (product build) */
 #include <stdint.h>
 #include <math.h>
 
@@ -16,6 +19,7 @@
 #define SB_HD inline
 #define SB_KERNEL static void
 #define SB_KERNEL_BIG static void
+#define SB_GRID_CONSTANT
 #define SB_RESTRICT
 SB_DEV int sb_tid() { return hostsim::tid(); }
 SB_DEV int sb_nthr() { return hostsim::nthr(); }
@@ -42,12 +46,15 @@ SB_DEV int sb_popc(unsigned v) { return __builtin_popcount(v); }
 SB_DEV int sb_ffs(unsigned v) { return __builtin_ffs((int)v); }
 SB_DEV int sb_clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 template <class T> SB_DEV T sb_ldg(const T *p) { return *p; }
+SB_DEV long long sb_d2ll(double v) { long long u; memcpy(&u, &v, 8); return u; }
+SB_DEV double sb_ll2d(long long u) { double v; memcpy(&v, &u, 8); return v; }
 #else
 #include <cuda_runtime.h>
 #define SB_DEV __device__ __forceinline__
 #define SB_HD __host__ __device__ __forceinline__
 #define SB_KERNEL __global__ void
 #define SB_KERNEL_BIG __global__ void __launch_bounds__(SB_BLOCK, 1)
+#define SB_GRID_CONSTANT __grid_constant__
 #define SB_RESTRICT __restrict__
 SB_DEV int sb_tid() { return threadIdx.x; }
 SB_DEV int sb_nthr() { return blockDim.x; }
@@ -75,6 +82,8 @@ SB_DEV int sb_popc(unsigned v) { return __popc(v); }
 SB_DEV int sb_ffs(unsigned v) { return __ffs((int)v); }
 SB_DEV int sb_clz(unsigned v) { return __clz((int)v); }
 template <class T> SB_DEV T sb_ldg(const T *p) { return __ldg(p); }
+SB_DEV long long sb_d2ll(double v) { return __double_as_longlong(v); }
+SB_DEV double sb_ll2d(long long u) { return __longlong_as_double(u); }
 #endif
 
 SB_DEV int sb_lane() { return sb_tid() & 31; }

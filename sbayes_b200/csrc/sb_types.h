@@ -4,7 +4,9 @@
 #include <stdint.h>
 #include "../../include/sbayes_b200.h"
 
+#ifndef SB_MAXC
 #define SB_MAXC SB_MAX_COMPONENTS
+#endif
 #define SB_MAXK 1024         // clusters (sizes are staged in shared memory)
 #define SB_REDW 8            // doubles per CTA in a team reduction
 #define SB_NA_U8 255
@@ -32,10 +34,14 @@ struct SbProblem {
     const int32_t *conf_gid;     // [n_conf, N]
     const uint8_t *pat_id;       // [N] index of the object's confounder has-pattern
     const int32_t *pat_bits;     // [n_pat] bit c set <=> object is in a group of component c (c >= 1)
-    const double *alpha;         // [G_tot, F, S]
-    const double *asum;          // [G_tot, F]  sum_s alpha
-    const double *dcc;           // [G_tot, F]  lgamma(sum alpha) - sum_{alpha>0} lgamma(alpha)
+    // concentration rows: row of group g is arow(g); with dedup the K cluster rows (identical
+    // by construction, sbayes/model/prior.py:438-455) are stored once
+    int dedup, arow_off, A_rows, use_mask;
+    const double *alpha;         // [A_rows, F, S]
+    const double *asum;          // [A_rows, F]  sum_s alpha
+    const double *dcc;           // [A_rows, F]  lgamma(sum alpha) - sum_{alpha>0} lgamma(alpha)
     const double *unif;          // [F, S] 1.0 on applicable states
+    const uint64_t *applm;       // [F] the same as a bit mask (S <= 64)
     const double *alpha_w;       // [F, C]
     const double *wlnB;          // [F] log multivariate beta of alpha_w[f, :]
     const double *cost;          // [N, N] or null
@@ -43,6 +49,12 @@ struct SbProblem {
     const int32_t *adj_idx;
     const int32_t *cg_ptr;       // [sum conf groups + 1] CSR: members of every confounder group (sorted)
     const int32_t *cg_idx;
+    // distinct tuples of confounder groups ("combos"): objects of one combo share every
+    // confounder table row, so proposal passes can gather from per-combo tables
+    int n_combos, use_tables;
+    const int32_t *combo_id;     // [N]
+    const int32_t *combo_rows;   // [n_combos, n_conf] stacked group row or -1
+    const int32_t *combo_pat;    // [n_combos] has-pattern index
 };
 
 // ---------------------------------------------------------------------------------------
@@ -51,12 +63,14 @@ struct SbProblem {
 // (1) SbShared: what the whole team of CTAs that advances the chain shares, in HBM: the
 //     object-indexed arrays.  Source rows exist twice; osel[o] says which copy is committed,
 //     the other one receives the candidate of the running proposal (commit = set osel).
-// (2) SbRep: every CTA of the team keeps a *private replica* of the group-indexed state
-//     (counts, effect tables, per-group likelihoods, weight tables, the (pattern, feature,
-//     component) histogram, cluster sizes).  Replicas live in shared memory where they fit
-//     and in a private slice of HBM otherwise (SbPlace, decided by the host).  All CTAs
-//     apply the same proposal to their replica, so nothing group-indexed ever has to be
-//     exchanged inside a step; only sums over objects cross CTAs.
+// (2) Rep (sb_core.cuh): every CTA of the team keeps a *private replica* of the
+//     group-indexed state (counts, per-(group, feature) totals / reciprocals /
+//     log-likelihood terms, weight tables, the (pattern, feature, component) histogram,
+//     cluster sizes, the per-combo pass tables).  Replicas live in shared memory where they
+//     fit and in a private slice of HBM otherwise (SbPlace, decided by the host).  All CTAs
+//     apply the same proposal to their replica *in place* and undo it on a reject, so
+//     nothing group-indexed ever has to be exchanged inside a step; only sums over objects
+//     cross CTAs.
 // ---------------------------------------------------------------------------------------
 struct SbShared {
     int32_t *cluster_of;         // [N] committed membership, -1 = none
@@ -72,18 +86,20 @@ struct SbShared {
     double *post;                // [8] committed posterior terms {ll, size, geo, weights, source, i_step}
 };
 
-// replica arrays that may live in shared memory
-enum { A_WQ = 0, A_TABT, A_TABP, A_H0, A_H1, A_LW, A_COUNTS, A_WP, A_W1, A_DNEG, A_DPOS, A_N };
+// replica arrays that may live in shared memory (placement priority = enum order)
+enum { A_TAB0 = 0, A_TAB1, A_COUNTS, A_NN, A_RT, A_RP, A_WQ, A_ALPHA, A_MCL, A_MCOMBO, A_MOSEL, A_COMBOT, A_APPLM, A_XBLK,
+       A_WP, A_W1, A_LW, A_H0, A_H1, A_DCNT, A_LLGF, A_ASUM, A_BST, A_BK_LLGF, A_BK_RP, A_BK_RT, A_N };
 
 struct SbPlace {
     int in_smem[A_N];
     unsigned smem_off[A_N];      // byte offset inside the dynamic shared memory (if in_smem)
     size_t glob_off[A_N];        // byte offset inside the CTA's private HBM slice
-    size_t cand_off[3];          // candidate rows: counts, tabP, tabT (always in the HBM slice)
     size_t sel_off;              // selbuf [N]
     size_t rep_bytes;            // size of one CTA's private HBM slice
     unsigned fixed_off;          // start of the always-in-smem small arrays
     unsigned smem_bytes;         // total dynamic shared memory
+    int xblk_rows;               // objects per CTA block cached in A_XBLK (0 = not cached)
+    int alias_w;                 // every chain has prior temperature 1: wp == w1 == wq, stored once
 };
 
 struct SbSlot {
@@ -105,6 +121,7 @@ struct SbLaunch {
     unsigned long long *bars;    // [n_teams] barrier counters (zeroed before launch)
     double *tred;                // [n_teams, 2, team, SB_REDW]
     char *rep_base;              // [grid] private HBM slices of the CTAs
+    size_t rep_stride;
     SbPlace place;
     sb_tape tape;                // device pointers; vals == null => Philox
     sb_step_record *records;     // [n_slots, n_steps] or null

@@ -120,3 +120,12 @@ def test_mc3_swap_matches_oracle():
         ctx.run(20)
     finally:
         ctx.close()
+
+
+def test_philox_lockstep_six_components():
+    """more than 4 mixture components: the wide instantiation of the step kernel."""
+    from test_hostsim_parity import _many_confounders
+    prob = _many_confounders(3)
+    cfgs = [ChainConfig(seed=7), ChainConfig(temperature=1.15, prior_temperature=1.05, seed=8)]
+    st0 = [synth.initial_state(prob, seed=40 + i, objects_per_cluster=4) for i in range(2)]
+    parity.philox_lockstep(prob, st0, cfgs, 200, team=2)

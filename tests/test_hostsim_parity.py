@@ -31,3 +31,29 @@ def test_emulated_philox_lockstep(lib):
     cfgs = [ChainConfig(seed=100), ChainConfig(temperature=1.2, prior_temperature=1.1, seed=101)]
     st0 = [synth.initial_state(prob, seed=5 + i, objects_per_cluster=5) for i in range(2)]
     parity.philox_lockstep(prob, st0, cfgs, 120, lib=lib, team=2)
+
+
+def _many_confounders(n_conf_extra=3):
+    """universal + family + extra partitions: C = 3 + n_conf_extra mixture components (the wide
+    instantiation of the step kernel, more than 4 components)."""
+    import numpy as np
+    prob, _ = synth.make_problem(N=40, F=8, S=3, K=2, n_fam=3, seed=21, max_size=15)
+    rng = np.random.default_rng(3)
+    for i in range(n_conf_extra):
+        gid = rng.integers(-1, 3, size=prob.N).astype(np.int32)
+        for g in range(3):
+            gid[g + 3 * i] = g
+        prob.conf_gid.append(gid)
+        prob.conf_ngroups.append(3)
+        prob.alpha_conf.append(np.broadcast_to(prob.applicable.astype(np.float64), (3, prob.F, prob.S)).copy())
+        prob.conf_names.append(f"extra{i}")
+    prob.alpha_w = np.ones((prob.F, prob.C))
+    return prob
+
+
+def test_emulated_lockstep_six_components(lib):
+    prob = _many_confounders(3)
+    assert prob.C == 6
+    cfgs = [ChainConfig(seed=7), ChainConfig(temperature=1.15, prior_temperature=1.05, seed=8)]
+    st0 = [synth.initial_state(prob, seed=40 + i, objects_per_cluster=4) for i in range(2)]
+    parity.philox_lockstep(prob, st0, cfgs, 100, lib=lib, team=2)
