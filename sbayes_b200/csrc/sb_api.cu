@@ -314,7 +314,7 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
         long long want = ((long long)N * F + 8191) / 8192;
         long long cap_per_chain = std::max(1, capacity / std::max(1, std::min(n_chains, capacity)));
         team = (int)std::max(1LL, std::min(want, cap_per_chain));
-        if (team > 16 && want <= 32) team = 16;
+        if (want > 8 && want <= 32 && cap_per_chain >= 16) team = 16;   // a full 16-CTA cluster measured fastest (profiles/r1e_team_sweep)
     }
     if (team > capacity) team = capacity;
     c->team = team;

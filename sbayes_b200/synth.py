@@ -75,18 +75,27 @@ def make_problem(N: int, F: int, S: int, K: int, n_fam: int, seed: int, na_frac:
     p_conf = [dirichlet_rows(0.4, (g, F)) for g in conf_ng]
 
     has = np.stack([true_cluster >= 0] + [g >= 0 for g in conf_gid], axis=1)
-    w = has[:, None, :] * W_true[None]
-    w = w / w.sum(axis=-1, keepdims=True)
-    comp = (rng.random((N, F, 1)) < np.cumsum(w, axis=-1)).argmax(axis=-1)
-    x = np.zeros((N, F), dtype=np.uint8)
-    f_idx = np.arange(F)
-    for c in range(C):
-        gid = true_cluster if c == 0 else conf_gid[c - 1]
-        table = p_cluster if c == 0 else p_conf[c - 1]
-        rows = table[np.where(gid >= 0, gid, 0)]            # [N,F,S]
-        draw = (rng.random((N, F, 1)) < np.cumsum(rows, axis=-1)).argmax(axis=-1)
-        x = np.where(comp == c, draw, x).astype(np.uint8)
-    x[rng.random((N, F)) < na_frac] = NA
+    def draw_block(sl):
+        """features of the objects in `sl` from the explicit mixture"""
+        n = has[sl].shape[0]
+        w = has[sl][:, None, :] * W_true[None]
+        w = w / w.sum(axis=-1, keepdims=True)
+        comp = (rng.random((n, F, 1)) < np.cumsum(w, axis=-1)).argmax(axis=-1)
+        xb = np.zeros((n, F), dtype=np.uint8)
+        for c in range(C):
+            gid = (true_cluster if c == 0 else conf_gid[c - 1])[sl]
+            table = p_cluster if c == 0 else p_conf[c - 1]
+            rows = table[np.where(gid >= 0, gid, 0)]            # [n,F,S]
+            draw = (rng.random((n, F, 1)) < np.cumsum(rows, axis=-1)).argmax(axis=-1)
+            xb = np.where(comp == c, draw, xb).astype(np.uint8)
+        xb[rng.random((n, F)) < na_frac] = NA
+        return xb
+
+    if N * F * S <= (1 << 24):
+        x = draw_block(slice(0, N))
+    else:   # large shapes (BASELINE configs 4 and 5): blocks of objects bound the [n,F,S] temporaries
+        blk = max(1, (1 << 22) // (F * S))
+        x = np.concatenate([draw_block(slice(a, min(N, a + blk))) for a in range(0, N, blk)], axis=0)
 
     geo = None
     if geo_cost_based:
@@ -117,8 +126,16 @@ def initial_state(prob: Problem, seed: int, objects_per_cluster: int = 10) -> Ch
         cluster_of[perm[k * size:(k + 1) * size]] = k
     W = rng.dirichlet(np.ones(C), size=F).astype(np.float32)
     has = np.stack([cluster_of >= 0] + [g >= 0 for g in prob.conf_gid], axis=1)
-    w = has[:, None, :] * W[None].astype(np.float64)
-    w = w / w.sum(axis=-1, keepdims=True)
-    src = (rng.random((N, F, 1)) < np.cumsum(w, axis=-1)).argmax(axis=-1).astype(np.uint8)
+
+    def draw_block(sl):
+        w = has[sl][:, None, :] * W[None].astype(np.float64)
+        w = w / w.sum(axis=-1, keepdims=True)
+        return (rng.random((w.shape[0], F, 1)) < np.cumsum(w, axis=-1)).argmax(axis=-1).astype(np.uint8)
+
+    if N * F * C <= (1 << 24):
+        src = draw_block(slice(0, N))
+    else:
+        blk = max(1, (1 << 22) // (F * C))
+        src = np.concatenate([draw_block(slice(a, min(N, a + blk))) for a in range(0, N, blk)], axis=0)
     src[prob.x == NA] = NA
     return ChainState(cluster_of=cluster_of, W=W, src=src, counts=None)
