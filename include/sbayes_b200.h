@@ -21,6 +21,9 @@
  *   sb_eval              Model.likelihood(sample, caching=False) + Model.prior(sample,
  *                        caching=False) (sbayes/model/model.py:47-51,
  *                        sbayes/model/likelihood.py:47-101, sbayes/model/prior.py:74-88)
+ *   sb_eval_batch/_stats/_terms  the same for every chain at once as stand-alone kernels
+ *                        (recalculate_feature_counts sbayes/sampling/counts.py:35-52,
+ *                         Likelihood.__call__ likelihood.py:47-101, Prior.__call__ prior.py:74-88)
  *   sb_run               MCMCChain.run / MCMCChain.step for every chain of the ctx
  *                        (sbayes/sampling/mcmc_chain.py:128-255) including the ten scheduled
  *                        operators (sbayes/sampling/operators.py:423-1827)
@@ -110,6 +113,17 @@ int sb_set_state(sb_ctx *ctx, int chain, const int32_t *cluster_of, const float 
 int sb_get_state(sb_ctx *ctx, int chain, int32_t *cluster_of, float *W, uint8_t *src, int32_t *counts);
 int sb_eval(sb_ctx *ctx, int chain, sb_posterior_t *out);          /* full uncached evaluation */
 int sb_posterior(sb_ctx *ctx, int chain, sb_posterior_t *out);     /* cached values of the current state */
+/* Stand-alone full evaluation of EVERY chain of the ctx (HBM-bound statistics pass + terms):
+ * sb_eval_batch = sb_eval_stats + sb_eval_terms.  out[n_chains]; ms2 (may be NULL) receives the
+ * device time in ms of {statistics pass, terms}.  With the objects of a large matrix sharded over
+ * GPUs, every rank runs sb_eval_stats on its shard, all-reduces the int32 block returned by
+ * sb_stats_buffer, and calls sb_eval_terms(n_global = objects of the whole problem); the source
+ * prior it returns is the shard's partial sum (sbayes_b200/shard.py). */
+int sb_eval_batch(sb_ctx *ctx, sb_posterior_t *out, float *ms2);
+int sb_eval_stats(sb_ctx *ctx, float *ms);
+int sb_eval_set_mode(sb_ctx *ctx, int mode);   /* statistics pass: 0 shared-memory histogram, 1 int8 tcgen05 contraction */
+int sb_eval_terms(sb_ctx *ctx, int64_t n_global, sb_posterior_t *out, float *ms);
+int sb_stats_buffer(sb_ctx *ctx, uint64_t *dev_ptr, int64_t *n_int32, int64_t *stride, int64_t *layout3);
 int sb_run(sb_ctx *ctx, int64_t n_steps, const sb_tape *tape, sb_step_record *records);
 int sb_run_async(sb_ctx *ctx, int64_t n_steps);                     /* enqueue only; sb_sync waits */
 int sb_sync(sb_ctx *ctx);

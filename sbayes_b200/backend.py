@@ -58,7 +58,8 @@ RECORD_DTYPE = np.dtype([("op", "<i4"), ("accept", "<i4"), ("changed", "<i4"), (
 
 EXPORTS = ["sb_create", "sb_destroy", "sb_last_error", "sb_chain_config", "sb_set_state", "sb_get_state", "sb_eval",
            "sb_posterior", "sb_run", "sb_run_async", "sb_sync", "sb_op_stats", "sb_swap", "sb_get_slots",
-           "sb_set_slots", "sb_counts_rebuild_mma", "sb_counts_rebuild_hist", "sb_info", "sb_stream"]
+           "sb_set_slots", "sb_counts_rebuild_mma", "sb_counts_rebuild_hist", "sb_info", "sb_stream",
+           "sb_eval_batch", "sb_eval_stats", "sb_eval_terms", "sb_stats_buffer", "sb_eval_set_mode"]
 
 
 def _bind(lib):
@@ -85,6 +86,11 @@ def _bind(lib):
     lib.sb_info.argtypes = [vp, vp]
     lib.sb_stream.argtypes = [vp]
     lib.sb_stream.restype = u64
+    lib.sb_eval_batch.argtypes = [vp, vp, vp]
+    lib.sb_eval_stats.argtypes = [vp, vp]
+    lib.sb_eval_terms.argtypes = [vp, i64, vp, vp]
+    lib.sb_stats_buffer.argtypes = [vp, vp, vp, vp, vp]
+    lib.sb_eval_set_mode.argtypes = [vp, i32]
     return lib
 
 
@@ -202,6 +208,43 @@ class DeviceContext:
         out = _Posterior()
         self._ck(self.lib.sb_eval(self.h, chain, C.byref(out)))
         return {k: getattr(out, k) for k, _ in _Posterior._fields_}
+
+    @staticmethod
+    def _posts(arr) -> list:
+        return [{k: getattr(o, k) for k, _ in _Posterior._fields_} for o in arr]
+
+    def eval_batch(self, timing: bool = False):
+        """Uncached likelihood + prior of EVERY chain with the stand-alone evaluation kernels
+        (statistics pass over the packed observations + terms).  Returns a list of dicts, and
+        with timing=True also the device times in ms of (statistics pass, terms)."""
+        out = (_Posterior * self.n_chains)()
+        ms = np.zeros(2, np.float32)
+        self._ck(self.lib.sb_eval_batch(self.h, C.cast(out, C.c_void_p), _ptr(ms) if timing else None))
+        res = self._posts(out)
+        return (res, (float(ms[0]), float(ms[1]))) if timing else res
+
+    def eval_set_mode(self, mode: str):
+        """Statistics pass of eval_batch / eval_stats: "hist" (shared-memory histogram) or "mma"
+        (int8 tcgen05 contraction)."""
+        self._ck(self.lib.sb_eval_set_mode(self.h, {"hist": 0, "mma": 1}[mode]))
+
+    def eval_stats(self) -> float:
+        """Statistics pass only (counts, source histogram, cluster sizes of every chain)."""
+        ms = np.zeros(1, np.float32)
+        self._ck(self.lib.sb_eval_stats(self.h, _ptr(ms)))
+        return float(ms[0])
+
+    def eval_terms(self, n_global: int = 0) -> list:
+        """Posterior terms from the statistics currently held by the ctx."""
+        out = (_Posterior * self.n_chains)()
+        self._ck(self.lib.sb_eval_terms(self.h, int(n_global), C.cast(out, C.c_void_p), None))
+        return self._posts(out)
+
+    def stats_buffer(self):
+        """(device address, int32 elements, per-state stride, (n_counts, n_hist, n_sizes))."""
+        ptr, n, stride, lay = C.c_uint64(), C.c_int64(), C.c_int64(), (C.c_int64 * 3)()
+        self._ck(self.lib.sb_stats_buffer(self.h, C.byref(ptr), C.byref(n), C.byref(stride), C.cast(lay, C.c_void_p)))
+        return int(ptr.value), int(n.value), int(stride.value), tuple(int(v) for v in lay)
 
     def posterior(self, chain: int) -> dict:
         out = _Posterior()

@@ -26,6 +26,7 @@
 #undef SB_UC
 #undef SB_NS
 #include "sb_counts.cuh"
+#include "sb_eval.cuh"
 using uc4::FixedSmem; using uc4::sb_fixed_smem; using uc4::Draws; using uc4::Philox4; using uc4::philox4x32_10; using uc4::u01_double;
 using uc4::sb_export_kernel;
 
@@ -59,6 +60,16 @@ struct sb_ctx {
     double *d_tred = nullptr;
     uint8_t *d_src_tmp = nullptr;
     int32_t *d_counts_tmp = nullptr;
+    // stand-alone evaluation (sb_eval.cuh): the int32 statistics of all states are one block
+    int32_t *d_stats = nullptr;
+    size_t stats_stride = 0;          // int32 per state: counts | H | sizes, padded to 16 B
+    SbEvalPlan eplan;
+    int eplan_ok = 0;
+    SbMmaPlan mplan;                  // tcgen05 statistics pass over all states
+    int mplan_ok = 0, stats_mode = 0; // 0 = shared-memory histogram, 1 = int8 tensor-core contraction
+    double *d_epartial = nullptr, *d_egeo = nullptr, *d_epost = nullptr;
+    unsigned *d_eticket = nullptr;
+    int *d_eerr = nullptr;
     std::vector<void *> allocs;
     sb_stream_t stream = 0;
     std::string err;
@@ -343,11 +354,14 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
 
     // per-chain shared state and per-CTA replica slices
     c->h_states.resize(n_chains);
+    c->stats_stride = (nG + nH + (size_t)K + 3) & ~(size_t)3;
+    TRY(mk(c, &c->d_stats, c->stats_stride * (size_t)n_chains));
     for (int i = 0; i < n_chains; i++) {
         SbShared &s = c->h_states[i];
         TRY(mk(c, &s.cluster_of, N)); TRY(mk(c, &s.W, (size_t)F * C));
         for (int b = 0; b < 2; b++) { TRY(mk(c, &s.src[b], nS)); TRY(mk(c, &s.val[b], N)); }
-        TRY(mk(c, &s.osel, N)); TRY(mk(c, &s.counts, nG)); TRY(mk(c, &s.H, nH)); TRY(mk(c, &s.sizes, K));
+        TRY(mk(c, &s.osel, N));
+        s.counts = c->d_stats + (size_t)i * c->stats_stride; s.H = s.counts + nG; s.sizes = s.H + nH;
         TRY(mk(c, &s.list_a, N)); TRY(mk(c, &s.list_b, N)); TRY(mk(c, &s.flag_a, N)); TRY(mk(c, &s.flag_b, N));
         TRY(mk(c, &s.post, 8));
     }
@@ -363,7 +377,34 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
     TRY(mk(c, &c->d_bars, c->n_teams + 1));
     TRY(mk(c, &c->d_tred, (size_t)c->n_teams * 2 * team * SB_REDW));
     TRY(mk(c, &c->d_src_tmp, nS)); TRY(mk(c, &c->d_counts_tmp, nG));
-    (void)nH;
+    // stand-alone evaluation kernels
+    {
+        size_t budget = 100 * 1024;      // two histogram CTAs per SM
+#ifdef SB_HOSTSIM
+        if (getenv("SB_HOSTSIM_EVAL_SMEM")) budget = (size_t)atol(getenv("SB_HOSTSIM_EVAL_SMEM"));
+#endif
+        c->eplan_ok = sb_eval_make_plan(P, n_chains, c->n_sm, budget, &c->eplan) == 0;
+        if (!c->eplan_ok) c->eplan_ok = sb_eval_make_plan(P, n_chains, c->n_sm, 220 * 1024, &c->eplan) == 0;
+#ifdef SB_HOSTSIM
+        if (c->eplan_ok && getenv("SB_HOSTSIM_EVAL_OBLK")) {     // tests: force several object blocks
+            int nb = atoi(getenv("SB_HOSTSIM_EVAL_OBLK"));
+            c->eplan.rows_per_blk = (N + nb - 1) / nb; c->eplan.n_oblk = (N + c->eplan.rows_per_blk - 1) / c->eplan.rows_per_blk;
+        }
+#else
+        if (c->eplan_ok) {
+            CK(cudaFuncSetAttribute((const void *)sb_eval_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->eplan.smem));
+            if (P.geo) CK(cudaFuncSetAttribute((const void *)sb_eval_geo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->smem_members * 12 + 64)));
+        }
+#endif
+        c->mplan_ok = sb_mma_make_plan(P, n_chains, c->n_sm, &c->mplan) == 0;
+#ifndef SB_HOSTSIM
+        if (c->mplan_ok) CK(cudaFuncSetAttribute((const void *)sb_counts_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->mplan.smem));
+#else
+        c->mplan_ok = 0;
+#endif
+        TRY(mk(c, &c->d_epartial, (size_t)n_chains * SB_EVAL_MAXPARTS * 4)); TRY(mk(c, &c->d_eticket, (size_t)n_chains));
+        TRY(mk(c, &c->d_egeo, (size_t)n_chains * K)); TRY(mk(c, &c->d_epost, (size_t)n_chains * 8)); TRY(mk(c, &c->d_eerr, 1));
+    }
     return dev_sync(c);
 }
 
@@ -637,6 +678,122 @@ SB_API int sb_swap(sb_ctx *c, int attempts, int only_neighbours, uint64_t seed, 
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------
+// stand-alone full evaluation of every chain (sb_eval.cuh)
+// ---------------------------------------------------------------------------------------
+static SbEvalArgs eval_args(sb_ctx *c, long long n_global) {
+    SbEvalArgs A; memset(&A, 0, sizeof A);
+    A.P = c->P; A.states = c->d_states; A.slots = c->d_slots; A.n_states = c->n_chains; A.plan = c->eplan;
+    A.partial = c->d_epartial; A.ticket = c->d_eticket; A.geo_val = c->d_egeo; A.post = c->d_epost; A.err = c->d_eerr;
+    A.n_global = n_global > 0 ? n_global : c->P.N; A.geo_cap = c->smem_members;
+    return A;
+}
+#ifndef SB_HOSTSIM
+struct EvTimer {
+    cudaEvent_t e0 = nullptr, e1 = nullptr; cudaStream_t s; float *out;
+    EvTimer(cudaStream_t st, float *o) : s(st), out(o) { if (out) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); } }
+    void stop() { if (out) { cudaEventRecord(e1, s); cudaEventSynchronize(e1); cudaEventElapsedTime(out, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1); out = nullptr; } }
+};
+#endif
+
+// statistics pass: counts, source histogram and cluster sizes of every state (zeroed first)
+SB_API int sb_eval_stats(sb_ctx *c, float *ms) {
+    TRY(check_chain(c, 0));
+    if (!c->eplan_ok && c->stats_mode == 0) return fail(c, "evaluation histogram does not fit in shared memory (too many groups x states)");
+    SbEvalArgs A = eval_args(c, 0);
+    const int grid = c->n_chains * c->eplan.n_ftiles * c->eplan.n_oblk;
+#ifdef SB_HOSTSIM
+    if (ms) *ms = 0.f;
+    TRY(dev_zero(c, c->d_stats, sizeof(int32_t) * c->stats_stride * c->n_chains));
+    hostsim::launch([&]() { sb_eval_hist_kernel(A); }, grid, 64, c->eplan.smem);
+#else
+    EvTimer t(c->stream, ms);
+    TRY(dev_zero(c, c->d_stats, sizeof(int32_t) * c->stats_stride * c->n_chains));
+    if (c->stats_mode == 1) {
+        if (!c->mplan_ok) return fail(c, "the tensor-core statistics pass does not fit this problem (more than 256 group columns)");
+        sb_counts_mma_kernel<<<c->n_chains * c->mplan.n_ftiles * c->mplan.n_oblk, SB_MMA_BLOCK, c->mplan.smem, c->stream>>>(A, c->mplan);
+    } else {
+        sb_eval_hist_kernel<<<grid, SB_EVAL_BLOCK, c->eplan.smem, c->stream>>>(A);
+    }
+    CK(cudaGetLastError());
+    t.stop();
+#endif
+    c->launches++;
+    return 0;
+}
+
+// posterior terms of every chain from the statistics currently in the ctx; `n_global` = number
+// of objects of the whole problem when this ctx holds a shard of the objects (0: not sharded)
+SB_API int sb_eval_terms(sb_ctx *c, int64_t n_global, sb_posterior_t *out, float *ms) {
+    TRY(check_chain(c, 0));
+    SbEvalArgs A = eval_args(c, (long long)n_global);
+    if (c->P.geo && n_global > 0 && n_global != c->P.N) return fail(c, "the geo prior is not supported with sharded objects");
+    TRY(dev_zero(c, c->d_eticket, sizeof(unsigned) * c->n_chains));
+    TRY(dev_zero(c, c->d_eerr, sizeof(int)));
+#ifdef SB_HOSTSIM
+    if (ms) *ms = 0.f;
+    if (c->P.geo) hostsim::launch([&]() { sb_eval_geo_kernel(A); }, c->n_chains * c->P.K, 64, (size_t)c->smem_members * 12 + 64);
+    hostsim::launch([&]() { sb_eval_terms_kernel(A); }, c->n_chains * c->eplan.n_parts, 64, 1024);
+#else
+    EvTimer t(c->stream, ms);
+    if (c->P.geo) {
+        sb_eval_geo_kernel<<<c->n_chains * c->P.K, 128, (size_t)c->smem_members * 12 + 64, c->stream>>>(A);
+        CK(cudaGetLastError());
+        c->launches++;
+    }
+    sb_eval_terms_kernel<<<c->n_chains * c->eplan.n_parts, SB_EVAL_BLOCK, 1024, c->stream>>>(A);
+    CK(cudaGetLastError());
+    t.stop();
+#endif
+    c->launches++;
+    if (out) {
+        std::vector<double> post((size_t)c->n_chains * 8);
+        TRY(d2h(c, post.data(), c->d_epost, sizeof(double) * post.size()));
+        int err = 0; TRY(d2h(c, &err, c->d_eerr, sizeof(int)));
+        if (err == 2) return fail(c, "source component out of range in state");
+        if (err == 3) return fail(c, "cluster larger than the geo-prior member list");
+        std::vector<SbSlot> slots(c->n_chains);
+        TRY(d2h(c, slots.data(), c->d_slots, sizeof(SbSlot) * c->n_chains));
+        for (int i = 0; i < c->n_chains; i++) {
+            const double *p = &post[(size_t)slots[i].state * 8];
+            out[i].ll = p[0]; out[i].size_prior = p[1]; out[i].geo_prior = p[2]; out[i].weights_prior = p[3]; out[i].source_prior = p[4];
+            out[i].prior = p[1] + p[2] + p[3] + p[4];
+        }
+    }
+    return 0;
+}
+
+// which statistics pass sb_eval_stats / sb_eval_batch run: 0 = shared-memory histogram,
+// 1 = int8 tcgen05 contraction (sb_counts.cuh)
+SB_API int sb_eval_set_mode(sb_ctx *c, int mode) {
+    if (!c) return -1;
+    if (mode != 0 && mode != 1) return fail(c, "unknown statistics mode");
+#ifdef SB_HOSTSIM
+    if (mode == 1) return fail(c, "the tensor-core statistics pass needs a GPU");
+#endif
+    if (mode == 1 && !c->mplan_ok) return fail(c, "the tensor-core statistics pass does not fit this problem (more than 256 group columns)");
+    c->stats_mode = mode;
+    return 0;
+}
+
+// uncached likelihood + prior of every chain: out[n_chains]; ms (may be NULL) receives the
+// device time of {statistics pass, terms}
+SB_API int sb_eval_batch(sb_ctx *c, sb_posterior_t *out, float *ms2) {
+    TRY(sb_eval_stats(c, ms2 ? ms2 : nullptr));
+    return sb_eval_terms(c, 0, out, ms2 ? ms2 + 1 : nullptr);
+}
+
+// device address and length (int32 elements) of the statistics block of all states, laid out
+// [state][counts G_tot*F*S | H n_pat*2*F*C | sizes K | pad]: what a sharded run all-reduces
+SB_API int sb_stats_buffer(sb_ctx *c, uint64_t *dev_ptr, int64_t *n_int32, int64_t *stride, int64_t *layout3) {
+    if (!c) return -1;
+    if (dev_ptr) *dev_ptr = (uint64_t)(uintptr_t)c->d_stats;
+    if (n_int32) *n_int32 = (int64_t)(c->stats_stride * c->n_chains);
+    if (stride) *stride = (int64_t)c->stats_stride;
+    if (layout3) { layout3[0] = (int64_t)c->P.G_tot * c->P.F * c->P.S; layout3[1] = (int64_t)c->P.n_pat * 2 * c->P.F * c->P.C; layout3[2] = c->P.K; }
+    return 0;
+}
+
 SB_API int sb_info(const sb_ctx *c, int32_t *out8) {
     if (!c) return -1;
     out8[0] = c->device; out8[1] = c->n_chains; out8[2] = c->team; out8[3] = c->grid; out8[4] = c->block;
@@ -658,15 +815,27 @@ static int counts_common(sb_ctx *c, int chain, int32_t *counts_out, float *ms, b
     TRY(dev_zero(c, c->d_counts_tmp, sizeof(int32_t) * nG));
     float t = 0.f;
 #ifdef SB_HOSTSIM
+    const int32_t *result = c->d_counts_tmp;
     if (mma) return fail(c, "the tensor-core rebuild needs a GPU");
     hostsim::launch([&]() { sb_counts_hist_kernel(P, s, c->d_counts_tmp); }, 2, 64, sb_counts_hist_smem(P));
 #else
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, c->stream));
-    int r = mma ? sb_counts_mma_launch(P, s, c->d_counts_tmp, c->n_sm, c->stream)
-                : sb_counts_hist_launch(P, s, c->d_counts_tmp, c->n_sm, c->stream);
-    if (r) return fail(c, "count rebuild launch failed");
+    const int32_t *result = c->d_counts_tmp;
+    if (mma) {
+        // single state: the tensor-core pass writes the state's own statistics block
+        SbMmaPlan mp;
+        if (sb_mma_make_plan(P, 1, c->n_sm, &mp)) return fail(c, "the tensor-core statistics pass does not fit this problem (more than 256 group columns)");
+        SbEvalArgs A = eval_args(c, 0);
+        A.states = c->d_states + slot.state; A.n_states = 1;
+        CK(cudaFuncSetAttribute((const void *)sb_counts_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mp.smem));
+        CK(cudaMemsetAsync(s.counts, 0, sizeof(int32_t) * c->stats_stride, c->stream));
+        sb_counts_mma_kernel<<<mp.n_ftiles * mp.n_oblk, SB_MMA_BLOCK, mp.smem, c->stream>>>(A, mp);
+        result = s.counts;
+    } else {
+        if (sb_counts_hist_launch(P, s, c->d_counts_tmp, c->n_sm, c->stream)) return fail(c, "count rebuild launch failed");
+    }
     CK(cudaGetLastError());
     CK(cudaEventRecord(e1, c->stream));
     CK(cudaEventSynchronize(e1));
@@ -675,7 +844,7 @@ static int counts_common(sb_ctx *c, int chain, int32_t *counts_out, float *ms, b
 #endif
     c->launches++;
     if (ms) *ms = t;
-    if (counts_out) TRY(d2h(c, counts_out, c->d_counts_tmp, sizeof(int32_t) * nG));
+    if (counts_out) TRY(d2h(c, counts_out, result, sizeof(int32_t) * nG));
     return 0;
 }
 SB_API int sb_counts_rebuild_hist(sb_ctx *c, int chain, int32_t *counts_out, float *ms) { return counts_common(c, chain, counts_out, ms, false); }

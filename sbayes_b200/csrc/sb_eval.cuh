@@ -1,0 +1,329 @@
+// sb_eval.cuh -- stand-alone full evaluation of every chain of a ctx: the uncached
+//   Model.likelihood(sample, caching=False) + Model.prior(sample, caching=False)
+// of the reference (sbayes/model/model.py:47-51) as three kernels
+//
+//   sb_eval_hist_kernel    one pass over the packed observations (2 B per observation:
+//                          state byte + source byte): the count tensors
+//                          (recalculate_feature_counts, sbayes/sampling/counts.py:10-52), the
+//                          (has-pattern, feature, component) histogram of the source array (the
+//                          sufficient statistic of SourcePrior, sbayes/model/prior.py:568-611)
+//                          and the cluster sizes.  HBM bound.
+//   sb_eval_geo_kernel     GeoPrior.__call__ (prior.py:769-805,950-962): Prim's minimum spanning
+//                          tree of every cluster over the cost matrix (cost_based configs only)
+//   sb_eval_terms_kernel   Dirichlet-categorical log-likelihood of the counts
+//                          (sbayes/model/likelihood.py:47-101, sbayes/util.py:1373-1394), source /
+//                          weights / size priors (prior.py:522-558,568-611,647-681)
+//
+// The statistics of the first kernel are plain int32 sums over objects: with the objects of a
+// very large matrix sharded over GPUs they are what gets all-reduced (sbayes_b200/shard.py).
+#pragma once
+#include "sb_platform.cuh"
+#include "sb_types.h"
+
+#define SB_EVAL_BLOCK 256
+#define SB_EVAL_MAXPARTS 64
+
+struct SbEvalPlan {
+    int ft;            // features per tile (multiple of 16 bytes of a packed row)
+    int n_ftiles;      // tiles per row
+    int n_oblk;        // object blocks per (state, tile)
+    int rows_per_blk;  // objects per block
+    int n_parts;       // CTAs per state of the terms kernel
+    unsigned smem;     // dynamic shared memory of the histogram kernel
+};
+
+struct SbEvalArgs {
+    SbProblem P;
+    const SbShared *states;      // [n_states]
+    const SbSlot *slots;         // [n_states] chain configuration (sample_from_prior)
+    int n_states;
+    SbEvalPlan plan;
+    double *partial;             // [n_states, n_parts, 4]
+    unsigned *ticket;            // [n_states] zeroed before the launch
+    double *geo_val;             // [n_states, K] per-cluster geo prior (geo only)
+    double *post;                // [n_states, 8] {ll, size, geo, weights, source, 0, 0, 0}
+    int *err;                    // [1]
+    long long n_global;          // number of objects of the whole problem (== P.N unless sharded)
+    int geo_cap;                 // capacity of the shared-memory member list (geo only)
+};
+
+struct sb_u4 { uint32_t x, y, z, w; };
+SB_DEV sb_u4 ev_load16(const uint8_t *p) {      // p is 16-byte aligned
+#ifdef SB_HOSTSIM
+    sb_u4 v; memcpy(&v, p, 16); return v;
+#else
+    const uint4 t = *(const uint4 *)p; sb_u4 v; v.x = t.x; v.y = t.y; v.z = t.z; v.w = t.w; return v;
+#endif
+}
+SB_DEV int ev_arow(const SbProblem &P, int g) { return g < P.K ? (P.dedup ? 0 : g) : g - P.arow_off; }
+
+// -----------------------------------------------------------------------------------------
+// histogram pass.  CTA = (state, feature tile, object block).  The tile's bins live in shared
+// memory: counts [G_tot, ft, S], H [n_pat*2, ft, C]; threads walk the block's rows in 16-byte
+// chunks (fully coalesced, every lane busy whatever F is) and add one to two bins per
+// observation; the non-zero bins are added to the state's int32 statistics at the end.
+// -----------------------------------------------------------------------------------------
+SB_DEV void ev_hist_chunk(const SbProblem &P, int32_t *cnt, int32_t *H, int ft, int fl0, uint32_t xw, uint32_t sw,
+                          int k, int g1, int g2, int g3, const int32_t *rows, int hbase, int &err) {
+    const int S = P.S, C = P.C;
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+    for (int j = 0; j < 4; j++) {
+        const int x = (xw >> (8 * j)) & 255;
+        if (x == SB_NA_U8) continue;
+        const int c = (sw >> (8 * j)) & 255;
+        if (c >= C) { err = 2; continue; }
+        int g = c == 0 ? k : (c == 1 ? g1 : (c == 2 ? g2 : (c == 3 ? g3 : rows[c - 1])));
+        const int fl = fl0 + j;
+        if (g >= 0) sb_atomic_add_i32(cnt + ((size_t)g * ft + fl) * S + x, 1);
+        sb_atomic_add_i32(H + (size_t)(hbase + fl) * C + c, 1);
+    }
+}
+
+SB_KERNEL sb_eval_hist_kernel(const SB_GRID_CONSTANT SbEvalArgs A) {
+    const SbProblem &P = A.P;
+    const SbEvalPlan &pl = A.plan;
+    const int F = P.F, S = P.S, C = P.C, nconf = P.n_conf;
+    int w = sb_cta();
+    const int oblk = w % pl.n_oblk; w /= pl.n_oblk;
+    const int tile = w % pl.n_ftiles; w /= pl.n_ftiles;
+    const SbShared st = A.states[w];
+    const int f0 = tile * pl.ft;                                  // first byte column of the tile
+    const int ftw = (P.ldx - f0 < pl.ft ? P.ldx - f0 : pl.ft);    // tile width in bytes (multiple of 16)
+    const int ft = pl.ft;
+    const int lo = oblk * pl.rows_per_blk, hi = lo + pl.rows_per_blk < P.N ? lo + pl.rows_per_blk : P.N;
+    int32_t *cnt = (int32_t *)sb_smem();
+    const int n_cnt = P.G_tot * ft * S, n_H = P.n_pat * 2 * ft * C;
+    int32_t *H = cnt + n_cnt;
+    int32_t *sz = H + n_H;                                        // [K] (tile 0 only)
+    const int n_bins = n_cnt + n_H + (tile == 0 ? P.K : 0);
+    for (int i = sb_tid(); i < n_bins; i += sb_nthr()) cnt[i] = 0;
+    sb_cta_sync();
+    int err = 0;
+    if (hi > lo) {
+        const int cpr = ftw >> 4;                                 // chunks per row
+        const unsigned n_chunks = (unsigned)(hi - lo) * (unsigned)cpr;
+        for (unsigned i = sb_tid(); i < n_chunks; i += sb_nthr()) {
+            const int o = lo + (int)(i / (unsigned)cpr), fc = (int)(i % (unsigned)cpr) << 4;
+            const size_t off = (size_t)o * P.ldx + f0 + fc;
+            const sb_u4 xv = ev_load16(P.x + off);
+            const sb_u4 sv = ev_load16((st.osel[o] ? st.src[1] : st.src[0]) + off);
+            const int k = st.cluster_of[o];
+            const int combo = sb_ldg(P.combo_id + o);
+            const int32_t *rows = P.combo_rows + (size_t)combo * nconf;
+            const int g1 = nconf > 0 ? sb_ldg(rows) : -1, g2 = nconf > 1 ? sb_ldg(rows + 1) : -1, g3 = nconf > 2 ? sb_ldg(rows + 2) : -1;
+            const int hbase = (sb_ldg(P.combo_pat + combo) * 2 + (k >= 0 ? 1 : 0)) * ft;
+            ev_hist_chunk(P, cnt, H, ft, fc, xv.x, sv.x, k, g1, g2, g3, rows, hbase, err);
+            ev_hist_chunk(P, cnt, H, ft, fc + 4, xv.y, sv.y, k, g1, g2, g3, rows, hbase, err);
+            ev_hist_chunk(P, cnt, H, ft, fc + 8, xv.z, sv.z, k, g1, g2, g3, rows, hbase, err);
+            ev_hist_chunk(P, cnt, H, ft, fc + 12, xv.w, sv.w, k, g1, g2, g3, rows, hbase, err);
+        }
+        if (tile == 0)
+            for (int o = lo + sb_tid(); o < hi; o += sb_nthr()) { int k = st.cluster_of[o]; if (k >= 0) sb_atomic_add_i32(sz + k, 1); }
+    }
+    if (err) *A.err = err;
+    sb_cta_sync();
+    // flush: shared bin (g, fl, s) -> counts[(g*F + f0 + fl)*S + s]; padding columns hold nothing
+    const int fv = F - f0 < ftw ? F - f0 : ftw;                    // real features in the tile
+    for (int i = sb_tid(); i < n_cnt; i += sb_nthr()) {
+        const int v = cnt[i];
+        if (v == 0) continue;
+        const int s = i % S, fl = (i / S) % ft, g = i / (S * ft);
+        if (fl < fv) sb_atomic_add_i32(st.counts + ((size_t)g * F + f0 + fl) * S + s, v);
+    }
+    for (int i = sb_tid(); i < n_H; i += sb_nthr()) {
+        const int v = H[i];
+        if (v == 0) continue;
+        const int c = i % C, fl = (i / C) % ft, pz = i / (C * ft);
+        if (fl < fv) sb_atomic_add_i32(st.H + ((size_t)pz * F + f0 + fl) * C + c, v);
+    }
+    if (tile == 0)
+        for (int k = sb_tid(); k < P.K; k += sb_nthr()) if (sz[k]) sb_atomic_add_i32(st.sizes + k, sz[k]);
+}
+
+// -----------------------------------------------------------------------------------------
+// geo prior of one cluster: CTA = (state, cluster).  Same arithmetic and tie-breaking as
+// geo_cluster of the step kernel (sb_core.cuh): members in object order, Prim from the first
+// member, the first minimum wins, zero-cost edges are skipped like scipy's sparse MST does.
+// -----------------------------------------------------------------------------------------
+SB_DEV double ev_log_expit(double z) { double m = -z > 0 ? -z : 0.0; return -(m + log(exp(0.0 - m) + exp(-z - m))); }
+SB_DEV double ev_geo_prob_fn(const SbProblem &P, double x) {
+    if (P.geo_pf == 0) return -x / P.geo_rate;
+    return ev_log_expit(-(x - P.geo_infl) / P.geo_rate) - ev_log_expit(P.geo_infl / P.geo_rate);
+}
+
+SB_KERNEL sb_eval_geo_kernel(const SB_GRID_CONSTANT SbEvalArgs A) {
+    const SbProblem &P = A.P;
+    const int k = sb_cta() % P.K, s_idx = sb_cta() / P.K;
+    const SbShared st = A.states[s_idx];
+    const int cap = A.geo_cap;
+    double *dctl = (double *)sb_smem();
+    double *best = dctl + 2;
+    int *mem = (int *)(best + cap);
+    int *ctl = mem + cap;            // [0] m, [1] argmin
+    if (sb_tid() == 0) {
+        int m = 0;
+        for (int o = 0; o < P.N; o++) if (st.cluster_of[o] == k) { if (m < cap) mem[m] = o; m++; }
+        ctl[0] = m;
+    }
+    sb_cta_sync();
+    int m = ctl[0];
+    if (m > cap) { *A.err = 3; m = cap; }
+    double sum = 0.0, mx = 0.0; int cnt = 0;
+    if (m > 1) {
+        for (int i = sb_tid(); i < m; i += sb_nthr()) best[i] = i == 0 ? -1.0 : P.cost[(size_t)mem[0] * P.N + mem[i]];
+        sb_cta_sync();
+        for (int it = 0; it < m - 1; it++) {
+            if (sb_tid() == 0) {
+                int bj = -1; double bv = 0.0;
+                for (int i = 0; i < m; i++) { double b = best[i]; if (b >= 0.0 && (bj < 0 || b < bv)) { bj = i; bv = b; } }
+                ctl[1] = bj; dctl[0] = bv;
+            }
+            sb_cta_sync();
+            const int j = ctl[1]; const double e = dctl[0];
+            sb_cta_sync();
+            if (j < 0) break;
+            if (e != 0.0 && e <= 1.7976931348623157e308) { sum += e; if (cnt == 0 || e > mx) mx = e; cnt++; }
+            for (int i = sb_tid(); i < m; i += sb_nthr()) {
+                if (i == j) best[i] = -1.0;
+                else if (best[i] >= 0.0) { double c = P.cost[(size_t)mem[j] * P.N + mem[i]]; if (c < best[i]) best[i] = c; }
+            }
+            sb_cta_sync();
+        }
+    }
+    double agg = 0.0;
+    if (cnt > 0) agg = P.geo_agg == 0 ? sum / (double)cnt : (P.geo_agg == 1 ? sum : mx);
+    if (sb_tid() == 0) A.geo_val[(size_t)s_idx * P.K + k] = ev_geo_prob_fn(P, agg);
+}
+
+// -----------------------------------------------------------------------------------------
+// posterior terms from the statistics.  CTA = (state, part); the per-part sums are combined by
+// the last CTA of the state in part order, so the result does not depend on the schedule.
+// -----------------------------------------------------------------------------------------
+SB_DEV double ev_warp_sum(double v) {
+    for (int d = 16; d > 0; d >>= 1) v += sb_shfl_f64(v, (sb_lane() + d) & 31);
+    return v;
+}
+
+SB_KERNEL sb_eval_terms_kernel(const SB_GRID_CONSTANT SbEvalArgs A) {
+    const SbProblem &P = A.P;
+    const int F = P.F, S = P.S, C = P.C;
+    const int n_parts = A.plan.n_parts;
+    const int part = sb_cta() % n_parts, s_idx = sb_cta() / n_parts;
+    const SbShared st = A.states[s_idx];
+    const long long n_ll = (long long)P.G_tot * F, n_sp = (long long)P.n_pat * 2 * F, n_wp = P.wprior_uniform ? 0 : F;
+    const long long total = n_ll + n_sp + n_wp, per = (total + n_parts - 1) / n_parts;
+    const long long lo = part * per, hi = lo + per < total ? lo + per : total;
+    double ll = 0.0, sp = 0.0, wp = 0.0;
+    for (long long it = lo + sb_tid(); it < hi; it += sb_nthr()) {
+        if (it < n_ll) {
+            // Dirichlet-categorical term of one (group, feature) row, sbayes/util.py:1373-1394
+            const int g = (int)(it / F), f = (int)(it % F);
+            const size_t ar = (size_t)ev_arow(P, g) * F + f;
+            const int32_t *cr = st.counts + (size_t)it * S;
+            const double *al = P.alpha + ar * S;
+            int n = 0; double ser = 0.0;
+            for (int s = 0; s < S; s++) {
+                const int c = cr[s]; const double a = sb_ldg(al + s);
+                n += c;
+                if (a > 0.0) ser += lgamma((double)c + a);
+            }
+            ll += sb_ldg(P.dcc + ar) - lgamma((double)n + sb_ldg(P.asum + ar)) + ser;
+        } else if (it < n_ll + n_sp) {
+            // SourcePrior: sum over the histogram of log normalised weights (prior.py:596-611,
+            // normalize_weights likelihood.py:171-190)
+            const long long i = it - n_ll;
+            const int f = (int)(i % F), pz = (int)(i / F), z = pz & 1, bits = sb_ldg(P.pat_bits + (pz >> 1));
+            const int32_t *h = st.H + (size_t)i * C;
+            double t1 = 0.0;
+            for (int c = 0; c < C; c++) {
+                const double hh = c == 0 ? (double)z : (double)((bits >> c) & 1);
+                t1 += hh * (double)st.W[f * C + c];
+            }
+            for (int c = 0; c < C; c++) {
+                const int hv = h[c];
+                if (hv == 0) continue;
+                const double hh = c == 0 ? (double)z : (double)((bits >> c) & 1);
+                const double a = t1 > 0.0 ? hh * (double)st.W[f * C + c] / t1 : 0.0;
+                sp += (double)hv * log(a);
+            }
+        } else {
+            // WeightsPrior: Dirichlet log-pdf of one weight row (prior.py:522-558, util.py:49)
+            const int f = (int)(it - n_ll - n_sp);
+            double t = 0.0;
+            for (int c = 0; c < C; c++) {
+                const double a = sb_ldg(P.alpha_w + (size_t)f * C + c);
+                if (a != 1.0) t += (a - 1.0) * log((double)st.W[f * C + c]);
+            }
+            wp += -sb_ldg(P.wlnB + f) + t;
+        }
+    }
+    // block reduction in a fixed order
+    double *red = (double *)sb_smem();                 // [3, n_warps]
+    unsigned *flag = (unsigned *)(red + 3 * 32);
+    ll = ev_warp_sum(ll); sp = ev_warp_sum(sp); wp = ev_warp_sum(wp);
+    if (sb_lane() == 0) { red[sb_warp()] = ll; red[32 + sb_warp()] = sp; red[64 + sb_warp()] = wp; }
+    sb_cta_sync();
+    if (sb_tid() == 0) {
+        double a = 0.0, b = 0.0, c = 0.0;
+        for (int i = 0; i < sb_nwarps(); i++) { a += red[i]; b += red[32 + i]; c += red[64 + i]; }
+        double *out = A.partial + ((size_t)s_idx * n_parts + part) * 4;
+        out[0] = a; out[1] = b; out[2] = c;
+        sb_threadfence();
+        const unsigned t = (unsigned)sb_atomic_add_i32((int *)A.ticket + s_idx, 1);
+        flag[0] = t == (unsigned)(n_parts - 1);
+    }
+    sb_cta_sync();
+    if (!flag[0] || sb_tid() != 0) return;
+    sb_threadfence();
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int p = 0; p < n_parts; p++) {
+        const volatile double *in = A.partial + ((size_t)s_idx * n_parts + p) * 4;
+        a += in[0]; b += in[1]; c += in[2];
+    }
+    int sfp = 0;
+    for (int i = 0; i < A.n_states; i++) if (A.slots[i].state == s_idx) sfp = A.slots[i].cfg.sample_from_prior;
+    // ClusterSizePrior (prior.py:647-681, log_multinom util.py:1125-1173)
+    double size_pr = 0.0;
+    if (P.size_prior == 1) {
+        long long tot = 0; double s = 0.0;
+        for (int k = 0; k < P.K; k++) { tot += st.sizes[k]; s += lgamma((double)st.sizes[k] + 1.0); }
+        size_pr = tot == 0 ? -0.0 : -(lgamma((double)A.n_global + 1.0) - s - lgamma((double)(A.n_global - tot) + 1.0));
+    } else if (P.size_prior == 2) {
+        double s = 0.0;
+        for (int k = 0; k < P.K; k++) { double z = (double)st.sizes[k]; s += log(z * z); }
+        size_pr = -s;
+    }
+    double geo = 0.0;
+    if (P.geo) for (int k = 0; k < P.K; k++) geo += A.geo_val[(size_t)s_idx * P.K + k];
+    double *post = A.post + (size_t)s_idx * 8;
+    post[0] = sfp ? 0.0 : a; post[1] = size_pr; post[2] = geo; post[3] = c; post[4] = b; post[5] = 0.0; post[6] = 0.0; post[7] = 0.0;
+}
+
+// launch geometry of the histogram pass: the widest feature tile whose bins fit `budget` bytes of
+// shared memory, tiles balanced, and enough object blocks to fill the machine
+static inline int sb_eval_make_plan(const SbProblem &P, int n_states, int n_sm, size_t budget, SbEvalPlan *pl) {
+    const size_t bins_per_f = (size_t)P.G_tot * P.S + (size_t)P.n_pat * 2 * P.C;
+    const size_t fixed = (size_t)P.K * 4 + 64;
+    if (budget < fixed + 16 * bins_per_f * 4) return -1;
+    int ft_max = (int)((budget - fixed) / (bins_per_f * 4)) / 16 * 16;
+    int n_ftiles = (P.ldx + ft_max - 1) / ft_max;
+    int ft = ((P.ldx + n_ftiles - 1) / n_ftiles + 15) / 16 * 16;
+    n_ftiles = (P.ldx + ft - 1) / ft;
+    long long want = 4LL * n_sm;
+    long long base = (long long)n_states * n_ftiles;
+    long long n_oblk = (want + base - 1) / base;
+    const long long chunks = (long long)P.N * (ft / 16);
+    long long max_blk = chunks / 1024; if (max_blk < 1) max_blk = 1;     // at least 4 chunks per thread
+    if (n_oblk > max_blk) n_oblk = max_blk;
+    if (n_oblk < 1) n_oblk = 1;
+    int rows = (int)((P.N + n_oblk - 1) / n_oblk);
+    n_oblk = (P.N + rows - 1) / rows;
+    pl->ft = ft; pl->n_ftiles = n_ftiles; pl->n_oblk = (int)n_oblk; pl->rows_per_blk = rows;
+    long long items = (long long)P.G_tot * P.F + (long long)P.n_pat * 2 * P.F + P.F;
+    long long parts = (items + 2047) / 2048;
+    pl->n_parts = (int)(parts < 1 ? 1 : (parts > SB_EVAL_MAXPARTS ? SB_EVAL_MAXPARTS : parts));
+    pl->smem = (unsigned)(fixed + (size_t)ft * bins_per_f * 4);
+    return 0;
+}
