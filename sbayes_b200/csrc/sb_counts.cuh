@@ -146,6 +146,14 @@ SB_DEV void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }  // namespace sbmma
 
 // args: the evaluation argument block (sb_eval.cuh) -- statistics go to st.counts / st.H / st.sizes
+//
+// Warp-specialised: 16 producer warps generate the operand stages, one extra warp issues the
+// MMAs.  full[b] (one arrival per producer warp) hands a stage to the issuer, tcgen05.commit on
+// empty[b] hands the buffer back; producers only meet each other at a named barrier between
+// zeroing and filling a stage.
+#define SB_MMA_PRODUCERS 512
+#undef SB_MMA_BLOCK
+#define SB_MMA_BLOCK (SB_MMA_PRODUCERS + 32)
 __global__ void __launch_bounds__(SB_MMA_BLOCK, 1) sb_counts_mma_kernel(const __grid_constant__ SbEvalArgs A, const __grid_constant__ SbMmaPlan mp) {
     using namespace sbmma;
     const SbProblem &P = A.P;
@@ -163,117 +171,130 @@ __global__ void __launch_bounds__(SB_MMA_BLOCK, 1) sb_counts_mma_kernel(const __
     const uint32_t LBO = 128, SBO = KC * 16;
 
     extern __shared__ __align__(1024) char sm[];
-    uint64_t *mbar = (uint64_t *)sm;                 // [2]
-    uint32_t *tmem_slot = (uint32_t *)(sm + 16);
+    uint64_t *full = (uint64_t *)sm, *empty = full + 2;
+    uint32_t *tmem_slot = (uint32_t *)(sm + 64);
     char *bufA[2] = {sm + 256, sm + 256 + mp.a_bytes};
     char *bufB[2] = {sm + 256 + 2 * mp.a_bytes, sm + 256 + 2 * mp.a_bytes + mp.b_bytes};
-    if (tid == 0) { mbar_init(smem_u32(mbar), 1); mbar_init(smem_u32(mbar + 1), 1); }
+    if (tid == 0) {
+        mbar_init(smem_u32(full), SB_MMA_PRODUCERS / 32); mbar_init(smem_u32(full + 1), SB_MMA_PRODUCERS / 32);
+        mbar_init(smem_u32(empty), 1); mbar_init(smem_u32(empty + 1), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     if (warp == 0) tmem_alloc(smem_u32(tmem_slot), (uint32_t)mp.tmem_cols);
     fence_before();
     __syncthreads();
     fence_after();
     const uint32_t tmem = *tmem_slot;
-    // instruction descriptor: D = s32, A/B = unsigned 8 bit, both MN-major, N = npad, M = 128
-    const uint32_t idesc = (2u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(mp.npad >> 3) << 17) | (8u << 24);
 
-    // this thread's 16 observations of a stage: object ol, byte columns [fc, fc + 16)
-    const int ol = tid % KC, ci = tid / KC;
-    const bool has_item = ci < cpr;
-    const int fc = ci << 4;
-    uint4 xv = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), sv = xv;
-    int k_cl = -1, combo = 0;
-    auto load_stage = [&](int stg) {
-        const int o = lo + stg * KC + ol;
-        xv = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu); sv = xv; k_cl = -1; combo = -1;
-        if (o < hi) {
-            if (has_item) {
-                const size_t off = (size_t)o * P.ldx + f0 + fc;
-                xv = *(const uint4 *)(P.x + off);
-                sv = *(const uint4 *)((st.osel[o] ? st.src[1] : st.src[0]) + off);
+    if (warp == SB_MMA_PRODUCERS / 32) {
+        // ---------------------------------------------------------------- MMA issuer
+        if (lane == 0) {
+            // instruction descriptor: D = s32, A/B = unsigned 8 bit, both MN-major, N = npad, M = 128
+            const uint32_t idesc = (2u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(mp.npad >> 3) << 17) | (8u << 24);
+            const uint64_t a_d[2] = {smem_desc(smem_u32(bufA[0]), LBO, SBO), smem_desc(smem_u32(bufA[1]), LBO, SBO)};
+            const uint64_t b_d[2] = {smem_desc(smem_u32(bufB[0]), LBO, SBO), smem_desc(smem_u32(bufB[1]), LBO, SBO)};
+            for (int stg = 0; stg < n_stages; stg++) {
+                const int b = stg & 1;
+                mbar_wait(smem_u32(full + b), (uint32_t)((stg >> 1) & 1));
+                fence_after();
+                for (int t = 0; t < mp.tiles; t++)
+#pragma unroll
+                    for (int ks = 0; ks < KC / 32; ks++)       // descriptor start address is in 16-byte units
+                        mma_i8(tmem + (uint32_t)(t * mp.npad), a_d[b] + (uint64_t)((t * 8 * SBO + ks * 4 * LBO) >> 4),
+                               b_d[b] + (uint64_t)((ks * 4 * LBO) >> 4), idesc, (stg > 0 || ks > 0) ? 1u : 0u);
+                commit(smem_u32(empty + b));
             }
-            if (ci == 0) { k_cl = st.cluster_of[o]; combo = __ldg(P.combo_id + o); }
         }
-    };
-    int err = 0;
-    if (n_stages > 0) load_stage(0);
-    for (int stg = 0; stg < n_stages; stg++) {
-        const int b = stg & 1;
-        if (stg >= 2) mbar_wait(smem_u32(mbar + b), (uint32_t)(((stg >> 1) - 1) & 1));   // MMAs of stage stg-2 have read buffer b
-        // zero the stage
-        {
-            uint4 z = make_uint4(0, 0, 0, 0);
-            uint4 *a4 = (uint4 *)bufA[b]; uint4 *b4 = (uint4 *)bufB[b];
-            for (int i = tid; i < (int)(mp.a_bytes >> 4); i += SB_MMA_BLOCK) a4[i] = z;
-            for (int i = tid; i < (int)(mp.b_bytes >> 4); i += SB_MMA_BLOCK) b4[i] = z;
-        }
-        __syncthreads();
-        // one byte per observation into A
-        if (has_item) {
-            char *base = bufA[b] + (ol & 7) * 16 + (ol >> 3) * LBO;
-            const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w}, ss[4] = {sv.x, sv.y, sv.z, sv.w};
-#pragma unroll
-            for (int q = 0; q < 4; q++)
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int x = (xs[q] >> (8 * j)) & 255, c = (ss[q] >> (8 * j)) & 255;
-                    if (x == SB_NA_U8) continue;
-                    if (c >= C) { err = 2; continue; }
-                    const int m = (fc + q * 4 + j) * mp.cs + c * S + x;
-                    base[(m >> 4) * SBO + (m & 15)] = 1;
+    } else {
+        // ---------------------------------------------------------------- producers
+        // this thread's 16 observations of a stage: object ol, byte columns [fc, fc + 16)
+        const int ol = tid % KC, ci = tid / KC;
+        const bool has_item = ci < cpr;
+        const int fc = ci << 4;
+        struct Item { uint4 xv, sv; int k_cl, combo; };
+        auto load_stage = [&](int stg) {
+            Item it;
+            it.xv = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu); it.sv = it.xv; it.k_cl = -1; it.combo = -1;
+            const int o = lo + stg * KC + ol;
+            if (stg < n_stages && o < hi) {
+                if (has_item) {
+                    const size_t off = (size_t)o * P.ldx + f0 + fc;
+                    it.xv = *(const uint4 *)(P.x + off);
+                    it.sv = *(const uint4 *)((st.osel[o] ? st.src[1] : st.src[0]) + off);
                 }
+                if (ci == 0) { it.k_cl = st.cluster_of[o]; it.combo = __ldg(P.combo_id + o); }
+            }
+            return it;
+        };
+        int err = 0;
+        Item cur = load_stage(0), nxt = load_stage(1);
+        for (int stg = 0; stg < n_stages; stg++) {
+            const int b = stg & 1;
+            if (stg >= 2) mbar_wait(smem_u32(empty + b), (uint32_t)(((stg >> 1) - 1) & 1));   // MMAs of stage stg-2 have read buffer b
+            {
+                const uint4 z = make_uint4(0, 0, 0, 0);
+                uint4 *a4 = (uint4 *)bufA[b]; uint4 *b4 = (uint4 *)bufB[b];
+                for (int i = tid; i < (int)(mp.a_bytes >> 4); i += SB_MMA_PRODUCERS) a4[i] = z;
+                for (int i = tid; i < (int)(mp.b_bytes >> 4); i += SB_MMA_PRODUCERS) b4[i] = z;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(SB_MMA_PRODUCERS) : "memory");
+            // one byte per observation into A
+            if (has_item) {
+                char *base = bufA[b] + (ol & 7) * 16 + (ol >> 3) * LBO;
+                const uint32_t xs[4] = {cur.xv.x, cur.xv.y, cur.xv.z, cur.xv.w}, ss[4] = {cur.sv.x, cur.sv.y, cur.sv.z, cur.sv.w};
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int x = (xs[q] >> (8 * j)) & 255, c = (ss[q] >> (8 * j)) & 255;
+                        if (x == SB_NA_U8) continue;
+                        if (c >= C) { err = 2; continue; }
+                        const int m = (fc + q * 4 + j) * mp.cs + c * S + x;
+                        base[(m >> 4) * SBO + (m & 15)] = 1;
+                    }
+            }
+            // membership columns of the object into B
+            if (ci == 0 && cur.combo >= 0) {
+                char *base = bufB[b] + (ol & 7) * 16 + (ol >> 3) * LBO;
+                const int k_cl = cur.k_cl;
+                if (k_cl >= 0) base[(k_cl >> 4) * SBO + (k_cl & 15)] = 1;
+                const int32_t *rows = P.combo_rows + (size_t)cur.combo * nconf;
+                for (int c = 0; c < nconf; c++) { const int g = __ldg(rows + c); if (g >= 0) base[(g >> 4) * SBO + (g & 15)] = 1; }
+                const int n = P.G_tot + __ldg(P.combo_pat + cur.combo) * 2 + (k_cl >= 0 ? 1 : 0);
+                base[(n >> 4) * SBO + (n & 15)] = 1;
+                if (tile == 0 && k_cl >= 0) atomicAdd(st.sizes + k_cl, 1);
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(full + b)) : "memory");
+            cur = nxt;
+            nxt = load_stage(stg + 2);
         }
-        // membership columns of the object into B
-        if (ci == 0 && combo >= 0) {
-            char *base = bufB[b] + (ol & 7) * 16 + (ol >> 3) * LBO;
-            if (k_cl >= 0) base[(k_cl >> 4) * SBO + (k_cl & 15)] = 1;
-            const int32_t *rows = P.combo_rows + (size_t)combo * nconf;
-            for (int c = 0; c < nconf; c++) { const int g = __ldg(rows + c); if (g >= 0) base[(g >> 4) * SBO + (g & 15)] = 1; }
-            const int n = P.G_tot + __ldg(P.combo_pat + combo) * 2 + (k_cl >= 0 ? 1 : 0);
-            base[(n >> 4) * SBO + (n & 15)] = 1;
-            if (tile == 0 && k_cl >= 0) atomicAdd(st.sizes + k_cl, 1);
-        }
-        if (stg + 1 < n_stages) load_stage(stg + 1);          // in flight while the MMAs are issued
-        fence_async_smem();
-        __syncthreads();
-        if (tid == 0) {
+        if (err) *A.err = err;
+        // wait for the last commit of each buffer, then drain TMEM
+        if (n_stages > 0) {
+            const int last = n_stages - 1;
+            mbar_wait(smem_u32(empty + (last & 1)), (uint32_t)((last >> 1) & 1));
+            if (n_stages > 1) { const int l2 = last - 1; mbar_wait(smem_u32(empty + (l2 & 1)), (uint32_t)((l2 >> 1) & 1)); }
             fence_after();
-            const uint32_t a0 = smem_u32(bufA[b]), b0 = smem_u32(bufB[b]);
-            for (int t = 0; t < mp.tiles; t++)
+            const int fv = min(F - f0, ftw);                          // real features of this CTA
+            const int quarter = warp & 3;
+            for (int t = warp >> 2; t < mp.tiles; t += SB_MMA_PRODUCERS / 128) {
+                const int m = t * 128 + quarter * 32 + lane;
+                const int fl = m / mp.cs, code = m % mp.cs, c = code / S, s = code % S;
+                const bool live = fl < fv;
+                const int g_lo = P.goff[c < C ? c : 0], g_hi = P.goff[(c < C ? c : 0) + 1];
+                for (int n0 = 0; n0 < mp.npad; n0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * mp.npad + n0), v);
+                    if (!live) continue;
 #pragma unroll
-                for (int ks = 0; ks < KC / 32; ks++) {
-                    const uint64_t ad = smem_desc(a0 + t * 8 * SBO + ks * 4 * LBO, LBO, SBO);
-                    const uint64_t bd = smem_desc(b0 + ks * 4 * LBO, LBO, SBO);
-                    mma_i8(tmem + (uint32_t)(t * mp.npad), ad, bd, idesc, (stg > 0 || ks > 0) ? 1u : 0u);
-                }
-            commit(smem_u32(mbar + b));
-        }
-    }
-    if (err) *A.err = err;
-    // wait for the last commit of each buffer, then drain TMEM
-    if (n_stages > 0) {
-        const int last = n_stages - 1;
-        mbar_wait(smem_u32(mbar + (last & 1)), (uint32_t)((last >> 1) & 1));
-        if (n_stages > 1) { const int l2 = last - 1; mbar_wait(smem_u32(mbar + (l2 & 1)), (uint32_t)((l2 >> 1) & 1)); }
-    }
-    fence_after();
-    if (n_stages > 0) {
-        const int fv = min(F - f0, ftw);                          // real features of this CTA
-        const int quarter = warp & 3;
-        for (int t = warp >> 2; t < mp.tiles; t += SB_MMA_BLOCK / 128) {
-            const int m = t * 128 + quarter * 32 + lane;
-            const int fl = m / mp.cs, code = m % mp.cs, c = code / S, s = code % S;
-            const bool live = fl < fv;
-            const int g_lo = P.goff[c < C ? c : 0], g_hi = P.goff[(c < C ? c : 0) + 1];
-            for (int n0 = 0; n0 < mp.npad; n0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * mp.npad + n0), v);
-                if (!live) continue;
-#pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const int n = n0 + i, val = (int)v[i];
-                    if (val == 0) continue;
-                    if (n < P.G_tot) { if (n >= g_lo && n < g_hi) atomicAdd(st.counts + ((size_t)n * F + f0 + fl) * S + s, val); }
-                    else if (n < P.G_tot + P.n_pat * 2) atomicAdd(st.H + ((size_t)(n - P.G_tot) * F + f0 + fl) * C + c, val);
+                    for (int i = 0; i < 16; i++) {
+                        const int n = n0 + i, val = (int)v[i];
+                        if (val == 0) continue;
+                        if (n < P.G_tot) { if (n >= g_lo && n < g_hi) atomicAdd(st.counts + ((size_t)n * F + f0 + fl) * S + s, val); }
+                        else if (n < P.G_tot + P.n_pat * 2) atomicAdd(st.H + ((size_t)(n - P.G_tot) * F + f0 + fl) * C + c, val);
+                    }
                 }
             }
         }

@@ -59,29 +59,51 @@ SB_DEV int ev_arow(const SbProblem &P, int g) { return g < P.K ? (P.dedup ? 0 : 
 
 // -----------------------------------------------------------------------------------------
 // histogram pass.  CTA = (state, feature tile, object block).  The tile's bins live in shared
-// memory: counts [G_tot, ft, S], H [n_pat*2, ft, C]; threads walk the block's rows in 16-byte
-// chunks (fully coalesced, every lane busy whatever F is) and add one to two bins per
-// observation; the non-zero bins are added to the state's int32 statistics at the end.
+// memory: counts [G_tot][ft*S (+pad)], H [n_pat*2][ft*C (+pad)] with odd row strides (rows of
+// different groups fall into different banks).  A warp takes 32 consecutive objects and walks
+// their rows in 16-byte chunks: in one instruction all lanes look at the same feature, so the
+// bins they hit differ only by group / state (or coincide, which the hardware merges); the
+// group row of an observation is selected branch-free from registers.  The non-zero bins are
+// added to the state's int32 statistics at the end.
 // -----------------------------------------------------------------------------------------
-SB_DEV void ev_hist_chunk(const SbProblem &P, int32_t *cnt, int32_t *H, int ft, int fl0, uint32_t xw, uint32_t sw,
-                          int k, int g1, int g2, int g3, const int32_t *rows, int hbase, int &err) {
-    const int S = P.S, C = P.C;
+#define SB_EV_NEG (-(1 << 28))
+SB_HD int ev_odd(int v) { return v | 1; }
+
+// predicated +1 on a shared-memory bin (straight-line: no branch around the atomic)
+#ifdef SB_HOSTSIM
+typedef int32_t *ev_bins_t;
+SB_DEV ev_bins_t ev_bins(int32_t *p) { return p; }
+SB_DEV void ev_inc(ev_bins_t b, int idx, bool pred) { if (pred) b[idx]++; }
+#else
+typedef uint32_t ev_bins_t;
+SB_DEV ev_bins_t ev_bins(int32_t *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+SB_DEV void ev_inc(ev_bins_t b, int idx, bool pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %1, 0;\n\t@p red.shared.add.u32 [%0], 1;\n\t}" ::"r"(b + ((uint32_t)idx << 2)), "r"((int)pred) : "memory");
+}
+#endif
+
+template <int UC>
+SB_DEV void ev_hist_word(ev_bins_t bins, uint32_t xw, uint32_t sw, int C, int S, int fl0, const int (&gb)[UC], int hb) {
 #ifndef SB_HOSTSIM
 #pragma unroll
 #endif
     for (int j = 0; j < 4; j++) {
-        const int x = (xw >> (8 * j)) & 255;
-        if (x == SB_NA_U8) continue;
-        const int c = (sw >> (8 * j)) & 255;
-        if (c >= C) { err = 2; continue; }
-        int g = c == 0 ? k : (c == 1 ? g1 : (c == 2 ? g2 : (c == 3 ? g3 : rows[c - 1])));
+        const int x = (xw >> (8 * j)) & 255, c = (sw >> (8 * j)) & 255;
+        int sel = gb[UC - 1];
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+        for (int u = UC - 2; u >= 0; u--) sel = c == u ? gb[u] : sel;
+        const bool ok = x != SB_NA_U8 && c < C;
         const int fl = fl0 + j;
-        if (g >= 0) sb_atomic_add_i32(cnt + ((size_t)g * ft + fl) * S + x, 1);
-        sb_atomic_add_i32(H + (size_t)(hbase + fl) * C + c, 1);
+        const int ci = sel + fl * S + x;
+        ev_inc(bins, ci, ok && ci >= 0);
+        ev_inc(bins, hb + fl * C + c, ok);
     }
 }
 
-SB_KERNEL sb_eval_hist_kernel(const SB_GRID_CONSTANT SbEvalArgs A) {
+template <int UC>
+SB_DEV void ev_hist_body(const SbEvalArgs &A) {
     const SbProblem &P = A.P;
     const SbEvalPlan &pl = A.plan;
     const int F = P.F, S = P.S, C = P.C, nconf = P.n_conf;
@@ -92,54 +114,77 @@ SB_KERNEL sb_eval_hist_kernel(const SB_GRID_CONSTANT SbEvalArgs A) {
     const int f0 = tile * pl.ft;                                  // first byte column of the tile
     const int ftw = (P.ldx - f0 < pl.ft ? P.ldx - f0 : pl.ft);    // tile width in bytes (multiple of 16)
     const int ft = pl.ft;
+    const int gs = ev_odd(ft * S), hs = ev_odd(ft * C);           // padded row strides
     const int lo = oblk * pl.rows_per_blk, hi = lo + pl.rows_per_blk < P.N ? lo + pl.rows_per_blk : P.N;
     int32_t *cnt = (int32_t *)sb_smem();
-    const int n_cnt = P.G_tot * ft * S, n_H = P.n_pat * 2 * ft * C;
+    const int n_cnt = P.G_tot * gs, n_H = P.n_pat * 2 * hs;
     int32_t *H = cnt + n_cnt;
     int32_t *sz = H + n_H;                                        // [K] (tile 0 only)
     const int n_bins = n_cnt + n_H + (tile == 0 ? P.K : 0);
     for (int i = sb_tid(); i < n_bins; i += sb_nthr()) cnt[i] = 0;
     sb_cta_sync();
-    int err = 0;
-    if (hi > lo) {
-        const int cpr = ftw >> 4;                                 // chunks per row
-        const unsigned n_chunks = (unsigned)(hi - lo) * (unsigned)cpr;
-        for (unsigned i = sb_tid(); i < n_chunks; i += sb_nthr()) {
-            const int o = lo + (int)(i / (unsigned)cpr), fc = (int)(i % (unsigned)cpr) << 4;
-            const size_t off = (size_t)o * P.ldx + f0 + fc;
-            const sb_u4 xv = ev_load16(P.x + off);
-            const sb_u4 sv = ev_load16((st.osel[o] ? st.src[1] : st.src[0]) + off);
-            const int k = st.cluster_of[o];
+    const int cpr = ftw >> 4;                                     // chunks per row
+    const ev_bins_t bins = ev_bins(cnt);
+    const uint8_t *src0 = st.src[0], *src1 = st.src[1];
+    for (int o0 = lo + sb_warp() * 32; o0 < hi; o0 += sb_nwarps() * 32) {
+        const int o = o0 + sb_lane();
+        const bool live = o < hi;
+        int gb[UC];
+        int hb = 0, k = -1;
+        const uint8_t *xr = P.x, *sr = src0;
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+        for (int u = 0; u < UC; u++) gb[u] = SB_EV_NEG;
+        if (live) {
+            k = st.cluster_of[o];
             const int combo = sb_ldg(P.combo_id + o);
             const int32_t *rows = P.combo_rows + (size_t)combo * nconf;
-            const int g1 = nconf > 0 ? sb_ldg(rows) : -1, g2 = nconf > 1 ? sb_ldg(rows + 1) : -1, g3 = nconf > 2 ? sb_ldg(rows + 2) : -1;
-            const int hbase = (sb_ldg(P.combo_pat + combo) * 2 + (k >= 0 ? 1 : 0)) * ft;
-            ev_hist_chunk(P, cnt, H, ft, fc, xv.x, sv.x, k, g1, g2, g3, rows, hbase, err);
-            ev_hist_chunk(P, cnt, H, ft, fc + 4, xv.y, sv.y, k, g1, g2, g3, rows, hbase, err);
-            ev_hist_chunk(P, cnt, H, ft, fc + 8, xv.z, sv.z, k, g1, g2, g3, rows, hbase, err);
-            ev_hist_chunk(P, cnt, H, ft, fc + 12, xv.w, sv.w, k, g1, g2, g3, rows, hbase, err);
+            gb[0] = k >= 0 ? k * gs : SB_EV_NEG;
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+            for (int u = 1; u < UC; u++)
+                if (u <= nconf) { const int g = sb_ldg(rows + u - 1); gb[u] = g >= 0 ? g * gs : SB_EV_NEG; }
+            hb = n_cnt + (sb_ldg(P.combo_pat + combo) * 2 + (k >= 0 ? 1 : 0)) * hs;     // H follows the counts
+            const size_t off = (size_t)o * P.ldx + f0;
+            xr = P.x + off; sr = (st.osel[o] ? src1 : src0) + off;
+            if (tile == 0 && k >= 0) sb_atomic_add_i32(sz + k, 1);
         }
-        if (tile == 0)
-            for (int o = lo + sb_tid(); o < hi; o += sb_nthr()) { int k = st.cluster_of[o]; if (k >= 0) sb_atomic_add_i32(sz + k, 1); }
+        sb_u4 xv, sv, xn, sn;
+        xn.x = xn.y = xn.z = xn.w = 0xFFFFFFFFu; sn = xn;
+        if (live) { xn = ev_load16(xr); sn = ev_load16(sr); }
+        for (int ch = 0; ch < cpr; ch++) {
+            xv = xn; sv = sn;
+            if (live && ch + 1 < cpr) { xn = ev_load16(xr + (ch + 1) * 16); sn = ev_load16(sr + (ch + 1) * 16); }
+            const int fl = ch << 4;
+            ev_hist_word<UC>(bins, xv.x, sv.x, C, S, fl, gb, hb);
+            ev_hist_word<UC>(bins, xv.y, sv.y, C, S, fl + 4, gb, hb);
+            ev_hist_word<UC>(bins, xv.z, sv.z, C, S, fl + 8, gb, hb);
+            ev_hist_word<UC>(bins, xv.w, sv.w, C, S, fl + 12, gb, hb);
+        }
     }
-    if (err) *A.err = err;
     sb_cta_sync();
     // flush: shared bin (g, fl, s) -> counts[(g*F + f0 + fl)*S + s]; padding columns hold nothing
     const int fv = F - f0 < ftw ? F - f0 : ftw;                    // real features in the tile
     for (int i = sb_tid(); i < n_cnt; i += sb_nthr()) {
         const int v = cnt[i];
         if (v == 0) continue;
-        const int s = i % S, fl = (i / S) % ft, g = i / (S * ft);
+        const int g = i / gs, r = i % gs, fl = r / S, s = r % S;
         if (fl < fv) sb_atomic_add_i32(st.counts + ((size_t)g * F + f0 + fl) * S + s, v);
     }
     for (int i = sb_tid(); i < n_H; i += sb_nthr()) {
         const int v = H[i];
         if (v == 0) continue;
-        const int c = i % C, fl = (i / C) % ft, pz = i / (C * ft);
+        const int pz = i / hs, r = i % hs, fl = r / C, c = r % C;
         if (fl < fv) sb_atomic_add_i32(st.H + ((size_t)pz * F + f0 + fl) * C + c, v);
     }
     if (tile == 0)
         for (int k = sb_tid(); k < P.K; k += sb_nthr()) if (sz[k]) sb_atomic_add_i32(st.sizes + k, sz[k]);
+}
+
+SB_KERNEL sb_eval_hist_kernel(const SB_GRID_CONSTANT SbEvalArgs A) {
+    if (A.P.C <= 4) ev_hist_body<4>(A); else ev_hist_body<8>(A);
 }
 
 // -----------------------------------------------------------------------------------------
@@ -305,7 +350,7 @@ SB_KERNEL sb_eval_terms_kernel(const SB_GRID_CONSTANT SbEvalArgs A) {
 // shared memory, tiles balanced, and enough object blocks to fill the machine
 static inline int sb_eval_make_plan(const SbProblem &P, int n_states, int n_sm, size_t budget, SbEvalPlan *pl) {
     const size_t bins_per_f = (size_t)P.G_tot * P.S + (size_t)P.n_pat * 2 * P.C;
-    const size_t fixed = (size_t)P.K * 4 + 64;
+    const size_t fixed = (size_t)P.K * 4 + 64 + ((size_t)P.G_tot + (size_t)P.n_pat * 2) * 4;    // + row padding
     if (budget < fixed + 16 * bins_per_f * 4) return -1;
     int ft_max = (int)((budget - fixed) / (bins_per_f * 4)) / 16 * 16;
     int n_ftiles = (P.ldx + ft_max - 1) / ft_max;
@@ -314,8 +359,7 @@ static inline int sb_eval_make_plan(const SbProblem &P, int n_states, int n_sm, 
     long long want = 4LL * n_sm;
     long long base = (long long)n_states * n_ftiles;
     long long n_oblk = (want + base - 1) / base;
-    const long long chunks = (long long)P.N * (ft / 16);
-    long long max_blk = chunks / 1024; if (max_blk < 1) max_blk = 1;     // at least 4 chunks per thread
+    long long max_blk = P.N / 128; if (max_blk < 1) max_blk = 1;         // at least 4 warps with an object group
     if (n_oblk > max_blk) n_oblk = max_blk;
     if (n_oblk < 1) n_oblk = 1;
     int rows = (int)((P.N + n_oblk - 1) / n_oblk);

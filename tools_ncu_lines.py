@@ -30,7 +30,7 @@ print("sass rows", len(body), "disasm instructions", len(ins))
 inner = collections.Counter(); outer = collections.Counter(); execd = collections.Counter()
 tot = 0
 lines = {}
-for f in ("sb_core.cuh", "sb_platform.cuh", "sb_counts.cuh"):
+for f in ("sb_core.cuh", "sb_platform.cuh", "sb_counts.cuh", "sb_eval.cuh"):
     p = os.path.join(os.path.dirname(os.path.abspath(lib)), f)
     if os.path.exists(p): lines[f] = open(p).read().splitlines()
 for r, ch in zip(body, ins):

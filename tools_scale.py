@@ -45,6 +45,16 @@ def main():
             h = min(t[1][0] for t in ts); tm = min(t[1][1] for t in ts)
             print(f"[{name}] eval_batch: stats {h*1e3:.1f} us ({fe/h/1e6:.1f} GB/s algorithmic) terms {tm*1e3:.1f} us  -> {w['chains']/((h+tm)*1e-3):.0f} evals/s  "
                   f"ll={ts[0][0][0]['ll']} prior={ts[0][0][0]['prior']}", flush=True)
+            try:
+                ctx.eval_set_mode("mma")
+                ctx.eval_batch()
+                ts = [ctx.eval_batch(timing=True) for _ in range(10)]
+                h = min(t[1][0] for t in ts); tm = min(t[1][1] for t in ts)
+                print(f"[{name}] eval_batch (tcgen05): stats {h*1e3:.1f} us ({fe/h/1e6:.1f} GB/s algorithmic) terms {tm*1e3:.1f} us  -> {w['chains']/((h+tm)*1e-3):.0f} evals/s  "
+                      f"ll={ts[0][0][0]['ll']} prior={ts[0][0][0]['prior']}", flush=True)
+            except Exception as e:
+                print(f"[{name}] mma failed: {e}", flush=True)
+            ctx.eval_set_mode("hist")
             if "--no-steps" in sys.argv: ctx.close(); continue
             ctx.run(10)
             torch.cuda.synchronize(); t = time.perf_counter()
@@ -58,4 +68,5 @@ def main():
             print(f"[{name}] failed: {e}", flush=True)
         ctx.close()
 
-main()
+if __name__ == "__main__":
+    main()
