@@ -150,6 +150,41 @@ def config_dict(n_gpus: int) -> dict:
             "l2": "flushed between timed bench steps (256 MiB write); state is L2-resident inside a step by design"}
 
 
+FULL_EVAL_SHAPES = [
+    # (label, problem, chains per GPU): BASELINE configs 4 and 5 as one GPU sees them at 8 GPUs
+    ("c4 replicates 5000x200x6, K=5, 128 chains/GPU", dict(N=5000, F=200, S=6, K=5, n_fam=20, seed=4), 128),
+    ("c5 object shard 25000x1000x8, K=16 (200000 objects over 8 GPUs)", dict(N=25000, F=1000, S=8, K=16, n_fam=64, seed=5), 1),
+]
+
+
+def full_eval_line(ctx, prob, n_chains, label, flush, peak, reps=7):
+    """Stand-alone uncached evaluation (statistics pass + terms) of every chain of `ctx`:
+    device times from CUDA events around the kernels (inside the C ABI call), L2 flushed before
+    every timed call.  Algorithmic bytes of the statistics pass: 2 B per observation (state
+    byte + source byte), SURVEY.md section 8(d) FULL_EVAL."""
+    import torch
+    out = {"workload": label, "chains": n_chains}
+    for mode in ("hist", "mma"):
+        try:
+            ctx.eval_set_mode(mode)
+            ctx.eval_batch()
+            ts = []
+            for _ in range(reps):
+                flush.fill_(1)
+                torch.cuda.synchronize()
+                ts.append(ctx.eval_batch(timing=True)[1])
+            st, tm = float(np.median([t[0] for t in ts])), float(np.median([t[1] for t in ts]))
+            algo = 2.0 * prob.N * prob.F * n_chains
+            out[mode] = {"stats_us": st * 1e3, "terms_us": tm * 1e3, "evals_per_sec": n_chains / ((st + tm) * 1e-3),
+                         "roofline": {"bound": "hbm", "kernel": "sb_eval_hist_kernel" if mode == "hist" else "sb_counts_mma_kernel",
+                                      "achieved": algo / (st * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                      "frac": algo / (st * 1e-3) / 1e9 / peak, "traffic": None}}
+        except Exception as e:       # the tensor-core pass refuses problems with > 256 group columns
+            out[mode] = {"unavailable": str(e)}
+    ctx.eval_set_mode("hist")
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -226,14 +261,31 @@ def run_ours(args):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = n_mcmc / float(e2e_s.item())
 
+    from json import load
+    peaks = {}
+    try:
+        peaks = load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    # ---- likelihood evals/s: stand-alone uncached evaluation (rank 0 reports its own GPU) ----
+    full_eval = []
+    if rank == 0 and not args.no_full_eval:
+        from sbayes_b200 import synth
+        from sbayes_b200.backend import DeviceContext
+        full_eval.append(full_eval_line(mc3.ctx, prob, w["chains_per_gpu"], config_dict(world)["workload"], flush, peak))
+        for label, shape, nch in FULL_EVAL_SHAPES:
+            p2, _ = synth.make_problem(**shape)
+            sts = [synth.initial_state(p2, seed=100 + c) for c in range(min(nch, 2))]
+            c2 = DeviceContext(p2, nch, device=local)
+            for c in range(nch):
+                c2.configure(c, ChainConfig(seed=c))
+                c2.set_state(c, sts[c % len(sts)])
+            full_eval.append(full_eval_line(c2, p2, nch, label, flush, peak))
+            c2.close()
+    barrier()
+
     if rank == 0:
-        from json import load
-        peaks = {}
-        try:
-            peaks = load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
         per_launch_bytes = step_bytes(prob) * SI * w["chains_per_gpu"]
         kern_s = total_kern_ms / 1000.0 / args.steps
         achieved = per_launch_bytes / kern_s / 1e9
@@ -241,7 +293,9 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": dict(config_dict(world), team_ctas=info["team"], grid=info["grid"]),
-            "likelihood_evals_per_sec": value,
+            "likelihood_evals_per_sec": value,     # one candidate posterior evaluation per MCMC step
+            "full_uncached_evals_per_sec": (full_eval[0]["hist"]["evals_per_sec"] * world) if full_eval else None,
+            "full_eval": full_eval,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -271,6 +325,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--team", type=int, default=0, help="CTAs per chain (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-full-eval", action="store_true", help="skip the stand-alone evaluation measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

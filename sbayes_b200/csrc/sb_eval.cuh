@@ -183,8 +183,116 @@ SB_DEV void ev_hist_body(const SbEvalArgs &A) {
         for (int k = sb_tid(); k < P.K; k += sb_nthr()) if (sz[k]) sb_atomic_add_i32(st.sizes + k, sz[k]);
 }
 
+// Fast path (at most 4 components, fewer than 255 group rows -- every BASELINE config): the group
+// rows of an object travel as four bytes of one register and are picked with a byte permute; both
+// atomics are unconditional, observations that count nowhere (missing value, component without a
+// group) are redirected to a trash word.
+#ifdef SB_HOSTSIM
+SB_DEV uint32_t ev_byte(uint32_t w, uint32_t i) { return i < 4 ? (w >> (8 * i)) & 255u : 0u; }
+SB_DEV void ev_inc1(ev_bins_t b, int idx) { b[idx]++; }
+#else
+SB_DEV uint32_t ev_byte(uint32_t w, uint32_t i) { return __byte_perm(w, 0u, 0x4440u | i); }   // i > 3 selects the zero operand
+SB_DEV void ev_inc1(ev_bins_t b, int idx) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(b + ((uint32_t)idx << 2)) : "memory"); }
+#endif
+
+SB_DEV void ev_fast_word(ev_bins_t bins, uint32_t xw, uint32_t sw, int C, int S, int gs, int fl0, uint32_t gw, int hb, int trash) {
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+    for (uint32_t j = 0; j < 4; j++) {
+        const uint32_t x = ev_byte(xw, j), c = ev_byte(sw, j);
+        const uint32_t g = ev_byte(gw, c);
+        const bool ok = x != SB_NA_U8;
+        const int fl = fl0 + (int)j;
+        const int ci = (int)g * gs + (fl * S + (int)x);
+        const int hi = hb + fl * C + (int)c;
+        ev_inc1(bins, (ok && g != 255u) ? ci : trash);
+        ev_inc1(bins, ok ? hi : trash);
+    }
+}
+
+SB_DEV void ev_hist_fast(const SbEvalArgs &A) {
+    const SbProblem &P = A.P;
+    const SbEvalPlan &pl = A.plan;
+    const int F = P.F, S = P.S, C = P.C, nconf = P.n_conf;
+    int w = sb_cta();
+    const int oblk = w % pl.n_oblk; w /= pl.n_oblk;
+    const int tile = w % pl.n_ftiles; w /= pl.n_ftiles;
+    const SbShared st = A.states[w];
+    const int f0 = tile * pl.ft;
+    const int ftw = (P.ldx - f0 < pl.ft ? P.ldx - f0 : pl.ft);
+    const int ft = pl.ft;
+    const int gs = ev_odd(ft * S), hs = ev_odd(ft * C);
+    const int lo = oblk * pl.rows_per_blk, hi = lo + pl.rows_per_blk < P.N ? lo + pl.rows_per_blk : P.N;
+    int32_t *cnt = (int32_t *)sb_smem();
+    const int n_cnt = P.G_tot * gs, n_H = P.n_pat * 2 * hs;
+    int32_t *H = cnt + n_cnt;
+    int32_t *sz = H + n_H;                                        // [K], then the trash word
+    const int trash = n_cnt + n_H + P.K;
+    for (int i = sb_tid(); i < trash + 1; i += sb_nthr()) cnt[i] = 0;
+    sb_cta_sync();
+    const int cpr = ftw >> 4;
+    const ev_bins_t bins = ev_bins(cnt);
+    const uint8_t *src0 = st.src[0], *src1 = st.src[1];
+    for (int o0 = lo + sb_warp() * 32; o0 < hi; o0 += sb_nwarps() * 32) {
+        const int o = o0 + sb_lane();
+        const bool live = o < hi;
+        uint32_t gw = 0xFFFFFFFFu;
+        int hb = 0;
+        const uint8_t *xr = P.x, *sr = src0;
+        if (live) {
+            const int k = st.cluster_of[o];
+            const int combo = sb_ldg(P.combo_id + o);
+            const int32_t *rows = P.combo_rows + (size_t)combo * nconf;
+            gw = (uint32_t)(k >= 0 ? k : 255);
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+            for (int u = 1; u < 4; u++) {
+                int g = 255;
+                if (u <= nconf) { g = sb_ldg(rows + u - 1); g = g >= 0 ? g : 255; }
+                gw |= (uint32_t)g << (8 * u);
+            }
+            hb = n_cnt + (sb_ldg(P.combo_pat + combo) * 2 + (k >= 0 ? 1 : 0)) * hs;
+            const size_t off = (size_t)o * P.ldx + f0;
+            xr = P.x + off; sr = (st.osel[o] ? src1 : src0) + off;
+            if (tile == 0 && k >= 0) sb_atomic_add_i32(sz + k, 1);
+        }
+        sb_u4 xv, sv, xn, sn;
+        xn.x = xn.y = xn.z = xn.w = 0xFFFFFFFFu; sn = xn;
+        if (live) { xn = ev_load16(xr); sn = ev_load16(sr); }
+        for (int ch = 0; ch < cpr; ch++) {
+            xv = xn; sv = sn;
+            if (live && ch + 1 < cpr) { xn = ev_load16(xr + (ch + 1) * 16); sn = ev_load16(sr + (ch + 1) * 16); }
+            const int fl = ch << 4;
+            ev_fast_word(bins, xv.x, sv.x, C, S, gs, fl, gw, hb, trash);
+            ev_fast_word(bins, xv.y, sv.y, C, S, gs, fl + 4, gw, hb, trash);
+            ev_fast_word(bins, xv.z, sv.z, C, S, gs, fl + 8, gw, hb, trash);
+            ev_fast_word(bins, xv.w, sv.w, C, S, gs, fl + 12, gw, hb, trash);
+        }
+    }
+    sb_cta_sync();
+    const int fv = F - f0 < ftw ? F - f0 : ftw;
+    for (int i = sb_tid(); i < n_cnt; i += sb_nthr()) {
+        const int v = cnt[i];
+        if (v == 0) continue;
+        const int g = i / gs, r = i % gs, fl = r / S, s = r % S;
+        if (fl < fv) sb_atomic_add_i32(st.counts + ((size_t)g * F + f0 + fl) * S + s, v);
+    }
+    for (int i = sb_tid(); i < n_H; i += sb_nthr()) {
+        const int v = H[i];
+        if (v == 0) continue;
+        const int pz = i / hs, r = i % hs, fl = r / C, c = r % C;
+        if (fl < fv) sb_atomic_add_i32(st.H + ((size_t)pz * F + f0 + fl) * C + c, v);
+    }
+    if (tile == 0)
+        for (int k = sb_tid(); k < P.K; k += sb_nthr()) if (sz[k]) sb_atomic_add_i32(st.sizes + k, sz[k]);
+}
+
 SB_KERNEL sb_eval_hist_kernel(const SB_GRID_CONSTANT SbEvalArgs A) {
-    if (A.P.C <= 4) ev_hist_body<4>(A); else ev_hist_body<8>(A);
+    if (A.P.C <= 4 && A.P.G_tot < 255) ev_hist_fast(A);
+    else if (A.P.C <= 4) ev_hist_body<4>(A);
+    else ev_hist_body<8>(A);
 }
 
 // -----------------------------------------------------------------------------------------
@@ -350,7 +458,7 @@ SB_KERNEL sb_eval_terms_kernel(const SB_GRID_CONSTANT SbEvalArgs A) {
 // shared memory, tiles balanced, and enough object blocks to fill the machine
 static inline int sb_eval_make_plan(const SbProblem &P, int n_states, int n_sm, size_t budget, SbEvalPlan *pl) {
     const size_t bins_per_f = (size_t)P.G_tot * P.S + (size_t)P.n_pat * 2 * P.C;
-    const size_t fixed = (size_t)P.K * 4 + 64 + ((size_t)P.G_tot + (size_t)P.n_pat * 2) * 4;    // + row padding
+    const size_t fixed = (size_t)P.K * 4 + 64 + ((size_t)P.G_tot + (size_t)P.n_pat * 2) * 4;    // + row padding, trash word
     if (budget < fixed + 16 * bins_per_f * 4) return -1;
     int ft_max = (int)((budget - fixed) / (bins_per_f * 4)) / 16 * 16;
     int n_ftiles = (P.ldx + ft_max - 1) / ft_max;
