@@ -157,6 +157,15 @@ FULL_EVAL_SHAPES = [
 ]
 
 
+def ncu_traffic(kernel: str, tag: str):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t[f"{kernel}|{tag}"]["bytes"]
+    except Exception:
+        return None
+
+
 def full_eval_line(ctx, prob, n_chains, label, flush, peak, reps=7):
     """Stand-alone uncached evaluation (statistics pass + terms) of every chain of `ctx`:
     device times from CUDA events around the kernels (inside the C ABI call), L2 flushed before
@@ -178,7 +187,8 @@ def full_eval_line(ctx, prob, n_chains, label, flush, peak, reps=7):
             out[mode] = {"stats_us": st * 1e3, "terms_us": tm * 1e3, "evals_per_sec": n_chains / ((st + tm) * 1e-3),
                          "roofline": {"bound": "hbm", "kernel": "sb_eval_hist_kernel" if mode == "hist" else "sb_counts_mma_kernel",
                                       "achieved": algo / (st * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                                      "frac": algo / (st * 1e-3) / 1e9 / peak, "traffic": None}}
+                                      "frac": algo / (st * 1e-3) / 1e9 / peak,
+                                      "traffic": ncu_traffic("sb_eval_hist_kernel", label[:2]) if mode == "hist" else None}}
         except Exception as e:       # the tensor-core pass refuses problems with > 256 group columns
             out[mode] = {"unavailable": str(e)}
     ctx.eval_set_mode("hist")
@@ -300,7 +310,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "sb_run_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": ncu_traffic("sb_run_kernel", "c2"),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                          "note": "persistent step kernel at 1000x100 is latency bound (state is L2/L1 resident); "
                                  "algorithmic bytes = N*F per MCMC step (SURVEY 8d)"},

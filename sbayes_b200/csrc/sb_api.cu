@@ -379,9 +379,11 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
     TRY(mk(c, &c->d_src_tmp, nS)); TRY(mk(c, &c->d_counts_tmp, nG));
     // stand-alone evaluation kernels
     {
-        size_t budget = 100 * 1024;      // two histogram CTAs per SM
+        size_t budget = 56 * 1024;       // measured best (profiles/r1k_eval_smem_sweep.txt): three CTAs per SM by registers
 #ifdef SB_HOSTSIM
         if (getenv("SB_HOSTSIM_EVAL_SMEM")) budget = (size_t)atol(getenv("SB_HOSTSIM_EVAL_SMEM"));
+#else
+        if (getenv("SB_EVAL_SMEM_KB")) budget = (size_t)atol(getenv("SB_EVAL_SMEM_KB")) * 1024;   // tuning knob
 #endif
         c->eplan_ok = sb_eval_make_plan(P, n_chains, c->n_sm, budget, &c->eplan) == 0;
         if (!c->eplan_ok) c->eplan_ok = sb_eval_make_plan(P, n_chains, c->n_sm, 220 * 1024, &c->eplan) == 0;

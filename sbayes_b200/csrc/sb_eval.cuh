@@ -272,23 +272,24 @@ SB_DEV void ev_hist_fast(const SbEvalArgs &A) {
         }
     }
     sb_cta_sync();
+    // flush: the first fv*S words of bin row g are exactly the contiguous global segment
+    // counts[g, f0 .. f0+fv, :] (same for H with C), so no index arithmetic per bin
     const int fv = F - f0 < ftw ? F - f0 : ftw;
-    for (int i = sb_tid(); i < n_cnt; i += sb_nthr()) {
-        const int v = cnt[i];
-        if (v == 0) continue;
-        const int g = i / gs, r = i % gs, fl = r / S, s = r % S;
-        if (fl < fv) sb_atomic_add_i32(st.counts + ((size_t)g * F + f0 + fl) * S + s, v);
+    for (int g = sb_warp(); g < P.G_tot; g += sb_nwarps()) {
+        const int32_t *row = cnt + g * gs;
+        int32_t *dst = st.counts + ((size_t)g * F + f0) * S;
+        for (int r = sb_lane(); r < fv * S; r += 32) { const int v = row[r]; if (v) sb_atomic_add_i32(dst + r, v); }
     }
-    for (int i = sb_tid(); i < n_H; i += sb_nthr()) {
-        const int v = H[i];
-        if (v == 0) continue;
-        const int pz = i / hs, r = i % hs, fl = r / C, c = r % C;
-        if (fl < fv) sb_atomic_add_i32(st.H + ((size_t)pz * F + f0 + fl) * C + c, v);
+    for (int pz = sb_warp(); pz < P.n_pat * 2; pz += sb_nwarps()) {
+        const int32_t *row = H + pz * hs;
+        int32_t *dst = st.H + ((size_t)pz * F + f0) * C;
+        for (int r = sb_lane(); r < fv * C; r += 32) { const int v = row[r]; if (v) sb_atomic_add_i32(dst + r, v); }
     }
     if (tile == 0)
         for (int k = sb_tid(); k < P.K; k += sb_nthr()) if (sz[k]) sb_atomic_add_i32(st.sizes + k, sz[k]);
 }
 
+// (forcing 64 registers for a fourth CTA per SM measured slower: profiles/r1l_eval_smem_sweep.txt)
 SB_KERNEL sb_eval_hist_kernel(const SB_GRID_CONSTANT SbEvalArgs A) {
     if (A.P.C <= 4 && A.P.G_tot < 255) ev_hist_fast(A);
     else if (A.P.C <= 4) ev_hist_body<4>(A);

@@ -19,6 +19,7 @@
 #define SB_HD inline
 #define SB_KERNEL static void
 #define SB_KERNEL_BIG static void
+#define SB_KERNEL_LB(threads, blocks) static void
 #define SB_GRID_CONSTANT
 #define SB_RESTRICT
 SB_DEV int sb_tid() { return hostsim::tid(); }
@@ -54,6 +55,7 @@ SB_DEV double sb_ll2d(long long u) { double v; memcpy(&v, &u, 8); return v; }
 #define SB_HD __host__ __device__ __forceinline__
 #define SB_KERNEL __global__ void
 #define SB_KERNEL_BIG __global__ void __launch_bounds__(SB_BLOCK, 1)
+#define SB_KERNEL_LB(threads, blocks) __global__ void __launch_bounds__(threads, blocks)
 #define SB_GRID_CONSTANT __grid_constant__
 #define SB_RESTRICT __restrict__
 SB_DEV int sb_tid() { return threadIdx.x; }

@@ -108,6 +108,8 @@ class ShardedEvaluator:
             keep = t[:, n_counts:n_counts + n_hist].clone()
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             t[:, n_counts:n_counts + n_hist] = keep
+        if not self._host:      # the ctx launches on its own stream: the collective must have landed
+            torch.cuda.current_stream().synchronize()
 
     def evaluate(self) -> List[dict]:
         """Uncached log-likelihood and prior terms of every chain; identical on every rank."""

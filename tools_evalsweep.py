@@ -1,0 +1,8 @@
+"""Statistics-pass time against the shared-memory budget of the histogram kernel (tuning helper)."""
+import os, subprocess, sys
+for kb in (40, 56, 75, 100, 150, 200):
+    env = dict(os.environ, SB_EVAL_SMEM_KB=str(kb))
+    out = subprocess.run([sys.executable, "tools_scale.py", sys.argv[1], "--no-steps"], env=env, capture_output=True, text=True).stdout
+    for l in out.splitlines():
+        if "eval_batch:" in l:
+            print(f"smem {kb:3d} KB  {l}", flush=True)
