@@ -187,6 +187,210 @@ class MCMCChain:
         self.ctx.close()
 
 
+class MCMC:
+    """Drop-in for `sbayes.sampling.mcmc.MCMC` (boundary B1', sbayes/sampling/mcmc.py:36-361): the
+    non-MC3 sampler and the warm-up of `MCMCSetup.sample` (sbayes/mcmc_setup.py:80-142).
+
+    The `n_chains` chains (all at temperature 1, independent Philox streams) live in ONE device
+    context and advance together in one kernel launch per logging interval; `generate_samples`
+    keeps the reference's contract: warm-up returns the sample of the chain with the highest
+    log-likelihood, sampling logs chain 0 after every step whose index is a multiple of
+    `ceil(n_steps / n_samples)` and closes the loggers at the end."""
+
+    CHECK_CACHING = __debug__
+
+    def __init__(self, model, data, operators, sample_loggers: typ.List, n_chains: int = 1, sample_from_prior: bool = False,
+                 show_screen_log: bool = False, logger: logging.Logger = None, screen_log_interval: int = 1000, *,
+                 device: typ.Optional[int] = None, seed: typ.Optional[int] = None, team: int = 0, _lib=None, **kwargs):
+        self.model, self.data = model, data
+        self.n_chains = n_chains
+        self.chain_idx = list(range(n_chains))
+        self.sample_from_prior = sample_from_prior
+        self.callable_operators = self.get_operators(operators)
+        self.sample_loggers = sample_loggers
+        self._ll = np.full(n_chains, -np.inf)
+        self._prior = np.full(n_chains, -np.inf)
+        self.show_screen_log = show_screen_log
+        self.screen_log_interval = screen_log_interval
+        self.logger = logger if logger is not None else logging.getLogger("sbayes_b200")
+        self.t_start = _time.time()
+        self.i_step_start = 0
+        for lg in self.sample_loggers:
+            if type(lg).__name__ == "OperatorStatsLogger":
+                lg.operators = list(self.callable_operators.values())
+        missing = [n for n in OP_NAMES if n not in self.callable_operators]
+        extra = [n for n in self.callable_operators if n not in OP_NAMES]
+        if missing or extra:
+            raise SbError(f"operator schedule differs from the one the device implements: missing {missing}, unknown {extra}")
+        self.prob = refbridge.problem_from_reference(data, model)
+        if device is None:
+            device = int(os.environ.get("SBAYES_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        if seed is None:
+            seed = int.from_bytes(os.urandom(8), "little") >> 1
+        self.seed = seed
+        self.ctx = DeviceContext(self.prob, n_chains, device=device, team=team, _lib=_lib)
+        w = np.array([self.callable_operators[n].weight for n in OP_NAMES], dtype=np.float64)
+        for c in self.chain_idx:
+            self.ctx.configure(c, _ExplicitWeights(sample_from_prior=bool(sample_from_prior), seed=seed + c, weights=w / w.sum(),
+                                                   p_grow=float(getattr(self.callable_operators["cluster_gibbsish_geo"], "p_grow", 0.5))))
+        self._stats0 = (np.zeros(N_OPS, np.int64), np.zeros(N_OPS, np.int64))
+
+    def get_operators(self, operators) -> dict:
+        from sbayes.sampling.operators import get_operator_schedule
+        return get_operator_schedule(operators_config=operators, model=self.model, data=self.data,
+                                     sample_from_prior=self.sample_from_prior)
+
+    # -- reference API: un-tempered posterior terms of a sample (mcmc.py:99-138) -----------------
+    def _evaluate(self, sample, chain: int) -> dict:
+        self.ctx.set_state(chain, refbridge.state_from_sample(self.prob, sample), i_step=int(sample.i_step))
+        return self.ctx.eval(chain)
+
+    def prior(self, sample, chain: int) -> float:
+        ev = self._evaluate(sample, chain)
+        sample.last_prior = ev["prior"]
+        return ev["prior"]
+
+    def likelihood(self, sample, chain: int) -> float:
+        if self.sample_from_prior:
+            sample.last_lh = 0.0
+            return 0.0
+        ev = self._evaluate(sample, chain)
+        sample.last_lh = ev["ll"]
+        return ev["ll"]
+
+    def _download(self, template, chain: int, i_step: int):
+        st = self.ctx.get_state(chain)
+        post = self.ctx.posterior(chain)
+        s = refbridge.sample_from_state(self.prob, self.model, self.data, st, type(template), i_step=i_step, chain=chain)
+        self.model.prior(sample=s)
+        if not self.sample_from_prior:
+            self.model.likelihood(sample=s, caching=True)
+        s.last_lh = 0.0 if self.sample_from_prior else post["ll"]
+        s.last_prior = post["prior"]
+        self._ll[chain], self._prior[chain] = s.last_lh, s.last_prior
+        return s
+
+    def _sync_operator_stats(self):
+        a = np.zeros(N_OPS, np.int64); r = np.zeros(N_OPS, np.int64)
+        for c in self.chain_idx:
+            ac, rc = self.ctx.op_stats(c)
+            a += ac; r += rc
+        for i, name in enumerate(OP_NAMES):
+            op = self.callable_operators[name]
+            op.accepts += int(a[i] - self._stats0[0][i])
+            op.rejects += int(r[i] - self._stats0[1][i])
+        self._stats0 = (a, r)
+
+    def _run(self, n: int):
+        try:
+            self.ctx.run(n)
+        except SbError as e:
+            if "non-finite" in str(e):
+                raise ValueError(str(e))              # mcmc.py:307-312
+            raise
+
+    def generate_samples(self, n_steps: int, n_samples: int, initial_sample=None, initializer_logger=None, initializer=None,
+                         warm_up: bool = False, warm_up_steps: typ.Optional[int] = None, log_memory_usage: bool = True):
+        """sbayes/sampling/mcmc.py:155-263."""
+        from copy import deepcopy
+        sample = []
+        for c in self.chain_idx:
+            if initial_sample is None:
+                if initializer is None:
+                    raise AttributeError("Either initial_sample or initializer needs to be defined.")
+                s = initializer.generate_sample(c)
+            else:
+                s = deepcopy(initial_sample)
+                s.chain = c
+            sample.append(s)
+            self._ll[c] = self.likelihood(s, c)       # uploads the state of chain c
+            self._prior[c] = self.prior(s, c)
+        self.t_start = _time.time()
+        if warm_up:
+            self.logger.info("Tuning parameters in warm-up...")
+            if warm_up_steps:
+                self._run(int(warm_up_steps))
+            for c in self.chain_idx:
+                p = self.ctx.posterior(c)
+                self._ll[c] = 0.0 if self.sample_from_prior else p["ll"]
+                self._prior[c] = p["prior"]
+            best = int(np.argmax(self._ll))
+            self.logger.info(f"Starting state taken from warmup chain {best} with log-likelihood {self._ll[best]} "
+                             f"(log-lokelihoods of all chains: {list(self._ll)}).")
+            self._sync_operator_stats()
+            return self._download(sample[best], best, max(int(warm_up_steps or 0) - 1, 0))
+        self.logger.info("Sampling from posterior...")
+        steps_per_sample = int(np.ceil(n_steps / n_samples))
+        self.i_step_start = start = int(sample[0].i_step)
+        i = start                                     # steps with index < i are done
+        out = sample[0]
+        while i < n_steps:
+            # run up to and including the next logged step index (a multiple of steps_per_sample)
+            nxt = i if i % steps_per_sample == 0 else (i // steps_per_sample + 1) * steps_per_sample
+            upto = min(nxt, n_steps - 1)
+            self._run(upto - i + 1)
+            crossed = (upto + 1) // self.screen_log_interval > i // self.screen_log_interval
+            i = upto + 1
+            if upto % steps_per_sample == 0 or i == n_steps:
+                out = self._download(sample[0], 0, upto)
+                if upto % steps_per_sample == 0:
+                    for lg in self.sample_loggers:
+                        lg.write_sample(out)
+            if crossed:
+                self.print_screen_log(i, sample)
+        self._sync_operator_stats()
+        for lg in self.sample_loggers:
+            lg.close()
+        self.logger.info(f"MCMC run finished after {(_time.time() - self.t_start):.1f} seconds")
+        return out
+
+    def print_screen_log(self, i_step, sample):
+        t = (_time.time() - self.t_start) / max(i_step - self.i_step_start, 1) * 1000000
+        self.logger.info(f"{i_step:<12}log-likelihood of chain 0:  {self._ll[0]:<19.2f}{t:.0f} seconds / million steps")
+
+    def close(self):
+        self.ctx.close()
+
+
+class DeviceModel:
+    """`Model.likelihood(sample, caching=True)` / `Model.prior(sample, caching=True)`
+    (sbayes/model/model.py:47-51) evaluated on the device: the calls `swap_chains`
+    (sbayes/mcmc_setup.py:389-390,418) and `SbayesInitializer.generate_sample`
+    (sbayes/sampling/initializers.py:231) make directly on the model (boundary B2).  Every
+    call is a full uncached evaluation (`sb_eval_batch`); `caching` is accepted and ignored."""
+
+    def __init__(self, model, data, *, device: int = 0, _lib=None):
+        self.model, self.data = model, data
+        self.prob = refbridge.problem_from_reference(data, model)
+        self.ctx = DeviceContext(self.prob, 1, device=device, _lib=_lib)
+        self.ctx.configure(0, ChainConfig())
+        self._last = (None, None)
+
+    def _evaluate(self, sample) -> dict:
+        key = id(sample), getattr(sample, "i_step", None)
+        if self._last[0] != key or not all(getattr(sample, p).version == v for p, v in self._last[2].items()):
+            self.ctx.set_state(0, refbridge.state_from_sample(self.prob, sample), i_step=int(sample.i_step))
+            ev = self.ctx.eval_batch()[0]
+            self._last = (key, ev, {p: getattr(sample, p).version for p in ("clusters", "weights", "source")})
+        return self._last[1]
+
+    def likelihood(self, sample, caching: bool = True) -> float:
+        ev = self._evaluate(sample)
+        sample.last_lh = ev["ll"]
+        return ev["ll"]
+
+    def prior(self, sample, caching: bool = True) -> float:
+        ev = self._evaluate(sample)
+        sample.last_prior = ev["prior"]
+        return ev["prior"]
+
+    def __call__(self, sample, caching: bool = True) -> float:
+        return self.likelihood(sample, caching) + self.prior(sample, caching)
+
+    def close(self):
+        self.ctx.close()
+
+
 class _ExplicitWeights(ChainConfig):
     """ChainConfig whose operator weights come from the reference's schedule objects."""
 
@@ -200,10 +404,14 @@ class _ExplicitWeights(ChainConfig):
 
 def install():
     """Make the reference use the device chain: `sbayes.sampling.mcmc_chain.MCMCChain` and the
-    name imported into `sbayes.mcmc_setup` (sbayes/mcmc_setup.py:25) are rebound."""
+    name imported into `sbayes.mcmc_setup` (sbayes/mcmc_setup.py:25) are rebound; so are
+    `sbayes.sampling.mcmc.MCMC` and its import in `sbayes.mcmc_setup` (warm-up and non-MC3 runs)."""
     import sbayes.model  # noqa: F401  (must be imported first: circular imports in the reference)
     import sbayes.sampling.mcmc_chain as mc
     import sbayes.mcmc_setup as ms
     mc.MCMCChain = MCMCChain
     ms.MCMCChain = MCMCChain
+    import sbayes.sampling.mcmc as mm
+    mm.MCMC = MCMC
+    ms.MCMC = MCMC
     return MCMCChain

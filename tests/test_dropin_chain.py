@@ -109,3 +109,85 @@ def test_install_rebinds_the_reference_names():
     finally:
         r.mcmc_chain.MCMCChain = orig
         r.mcmc_setup.MCMCChain = orig
+
+
+def test_dropin_mcmc_generate_samples_matches_oracle():
+    """Boundary B1': `MCMC.generate_samples` (sbayes/sampling/mcmc.py:155-263) -- warm-up picks the
+    best of several chains, sampling logs chain 0 at the reference's step indices."""
+    import logging
+    from sbayes_b200.chain import MCMC
+    r = H.ref()
+    prob0, data, model = _reference_problem()
+    opcfg = r.config.OperatorsConfig(clusters=70, weights=10, source=20)
+    st0 = synth.initial_state(prob0, seed=3, objects_per_cluster=6)
+
+    # ---- warm-up: 3 chains from the same sample, 25 steps, best log-likelihood wins ----------
+    warm = MCMC(model, data, opcfg, [], n_chains=3, logger=logging.getLogger("t"), seed=50, team=1, _lib=_lib())
+    prob = warm.prob
+    st0.counts = M.rebuild_counts(prob, st0)
+    sample0 = H.sample_from_state(prob, model, data, st0)
+    best = warm.generate_samples(n_steps=0, n_samples=0, initial_sample=sample0, warm_up=True, warm_up_steps=25)
+    ocs = [CH.OracleChain(prob, ChainConfig(seed=50 + c), st0.copy(), draws=PhiloxDraws(50 + c)) for c in range(3)]
+    for oc in ocs:
+        for _ in range(25):
+            oc.step()
+    b = int(np.argmax([oc.ll for oc in ocs]))
+    fin = H.state_from_sample(prob, best)
+    assert best.chain == b
+    assert np.array_equal(fin.cluster_of, ocs[b].state.cluster_of) and np.array_equal(fin.src, ocs[b].state.src)
+    assert np.array_equal(fin.counts, ocs[b].state.counts) and np.array_equal(fin.W, ocs[b].state.W)
+    assert abs(best.last_lh - ocs[b].ll) <= 1e-10 * abs(ocs[b].ll)
+    warm.close()
+
+    # ---- sampling: 50 steps, 5 samples -> logged after the steps with index 0, 10, 20, 30, 40 --
+    lg = CountingLogger()
+    smp = MCMC(model, data, opcfg, [lg], logger=logging.getLogger("t"), seed=77, team=2, _lib=_lib())
+    sample0.i_step = 0
+    out = smp.generate_samples(n_steps=50, n_samples=5, initial_sample=sample0)
+    assert [row[0] for row in lg.rows] == [0, 10, 20, 30, 40] and out.i_step == 49
+    oc = CH.OracleChain(prob, ChainConfig(seed=77), st0.copy(), draws=PhiloxDraws(77))
+    logged = {}
+    for i in range(50):
+        oc.step()
+        if i % 10 == 0:
+            logged[i] = (oc.ll, oc.prior, oc.state.cluster_of.copy())
+    for row in lg.rows:
+        ll, pr, co = logged[row[0]]
+        assert abs(row[1] - ll) <= 1e-10 * abs(ll) and abs(row[2] - pr) <= 1e-10 * abs(pr)
+        assert np.array_equal(np.where(row[5].any(axis=0), row[5].argmax(axis=0), -1), co)
+    fin = H.state_from_sample(prob, out)
+    assert np.array_equal(fin.src, oc.state.src) and np.array_equal(fin.counts, oc.state.counts)
+    acc = sum(op.accepts for op in smp.callable_operators.values())
+    rej = sum(op.rejects for op in smp.callable_operators.values())
+    assert acc + rej == 50 and acc == int(oc.accepts.sum())
+    smp.close()
+
+
+def test_device_model_matches_reference_model():
+    """Boundary B2 (model API): Model.likelihood / Model.prior of a reference Sample on the device"""
+    from sbayes_b200.chain import DeviceModel
+    prob0, data, model = _reference_problem()
+    dm = DeviceModel(model, data, _lib=_lib())
+    for seed in (3, 4):
+        st = synth.initial_state(dm.prob, seed=seed, objects_per_cluster=6)
+        st.counts = M.rebuild_counts(dm.prob, st)
+        s = H.sample_from_state(dm.prob, model, data, st)
+        ll_ref, pr_ref = model.likelihood(s, caching=False), model.prior(s, caching=False)
+        assert abs(dm.likelihood(s) - ll_ref) < 5e-7 * abs(ll_ref) and abs(dm.prior(s) - pr_ref) < 5e-7 * abs(pr_ref)
+        assert abs(dm.likelihood(s) - M.log_likelihood(dm.prob, st)) <= 1e-10 * abs(ll_ref)
+        assert abs(dm.prior(s) - M.log_prior(dm.prob, st)) <= 1e-10 * abs(pr_ref)
+        assert s.last_lh == dm.likelihood(s) and s.last_prior == dm.prior(s)
+    dm.close()
+
+
+def test_install_rebinds_mcmc_too():
+    from sbayes_b200 import chain as C
+    r = H.ref()
+    import sbayes.sampling.mcmc as mm
+    orig = (r.mcmc_chain.MCMCChain, mm.MCMC)
+    try:
+        C.install()
+        assert mm.MCMC is C.MCMC and r.mcmc_setup.MCMC is C.MCMC
+    finally:
+        r.mcmc_chain.MCMCChain = orig[0]; r.mcmc_setup.MCMCChain = orig[0]
+        mm.MCMC = orig[1]; r.mcmc_setup.MCMC = orig[1]
