@@ -192,6 +192,21 @@ def full_eval_line(ctx, prob, n_chains, label, flush, peak, reps=7):
         except Exception as e:       # the tensor-core pass refuses problems with > 256 group columns
             out[mode] = {"unavailable": str(e)}
     ctx.eval_set_mode("hist")
+    # observation likelihood (LikelihoodLogger's product): 2 B read + 4 B written per observation
+    try:
+        ctx.obs_loglik(False, False)
+        ts = []
+        for _ in range(reps):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            ts.append(ctx.obs_loglik(False, False)[3])
+        t = float(np.median(ts))
+        algo = 6.0 * prob.N * prob.F * n_chains
+        out["obs_lik"] = {"us": t * 1e3, "observations_per_sec": prob.N * prob.F * n_chains / (t * 1e-3),
+                          "roofline": {"bound": "hbm", "kernel": "sb_obs_lik_kernel", "achieved": algo / (t * 1e-3) / 1e9, "peak": peak,
+                                       "unit": "GB/s", "frac": algo / (t * 1e-3) / 1e9 / peak, "traffic": None}}
+    except Exception as e:
+        out["obs_lik"] = {"unavailable": str(e)}
     return out
 
 

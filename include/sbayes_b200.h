@@ -123,6 +123,11 @@ int sb_eval_batch(sb_ctx *ctx, sb_posterior_t *out, float *ms2);
 int sb_eval_stats(sb_ctx *ctx, float *ms);
 int sb_eval_set_mode(sb_ctx *ctx, int mode);   /* statistics pass: 0 shared-memory histogram, 1 int8 tcgen05 contraction */
 int sb_eval_terms(sb_ctx *ctx, int64_t n_global, sb_posterior_t *out, float *ms);
+/* Observation likelihood of every chain: lh_out [n_chains, N, F] float32 = what LikelihoodLogger
+ * appends per sample (sbayes/sampling/loggers.py:354-359, leave-one-out component likelihoods of
+ * sbayes/sampling/conditionals.py:300-367); obj_ll_out [n_chains, N] / sums_out [n_chains] = sums
+ * of log lh per object / chain.  Any output may be NULL. */
+int sb_obs_loglik(sb_ctx *ctx, float *lh_out, double *obj_ll_out, double *sums_out, float *ms);
 int sb_stats_buffer(sb_ctx *ctx, uint64_t *dev_ptr, int64_t *n_int32, int64_t *stride, int64_t *layout3);
 int sb_run(sb_ctx *ctx, int64_t n_steps, const sb_tape *tape, sb_step_record *records);
 int sb_run_async(sb_ctx *ctx, int64_t n_steps);                     /* enqueue only; sb_sync waits */

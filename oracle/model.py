@@ -293,3 +293,33 @@ def likelihood_per_component(prob: Problem, st: ChainState, objs=None) -> np.nda
     """likelihood_per_component (conditionals.py:152-223): plain tables, f64 [M,F,C]."""
     objs = np.arange(prob.N) if objs is None else np.asarray(objs)
     return gather_table(prob, st, plain_table(prob, st.counts), objs)
+
+
+# ---------------------------------------------------------------------------------------
+# observation likelihood (what LikelihoodLogger writes, sbayes/sampling/loggers.py:354-359)
+# ---------------------------------------------------------------------------------------
+
+def observation_likelihood(prob: Problem, st: ChainState) -> np.ndarray:
+    """lh[o,f] = sum_c w~[o,f,c] * l_c[o,f]  with the *leave-one-out* component likelihoods of
+    `likelihood_per_component_exact` (sbayes/sampling/conditionals.py:300-367): the table row of
+    the group of o in component c with o's own observation removed when o's source is c,
+        l_c[o,f] = (counts[g,f,x] + alpha[g,f,x] - [src == c]) / (sum_s(counts + alpha)[g,f] - [src == c]),
+    0 where o is in no group of c, 1 where the observation is missing (so lh = 1 there); the
+    weights are `update_weights` (sbayes/model/likelihood.py:153-190).  f64 [N,F]."""
+    N, F = prob.N, prob.F
+    offs = prob.group_offsets()
+    num = st.counts.astype(np.float64) + prob.alpha_stacked()          # [G_tot,F,S]
+    den = num.sum(axis=-1)                                             # [G_tot,F]
+    w = normalize_weights(st.W, has_components(prob, st))              # [N,F,C]
+    valid = prob.x != NA
+    xs = np.where(valid, prob.x, 0).astype(np.int64)
+    f_idx = np.arange(F)[None, :]
+    lh = np.zeros((N, F))
+    for c in range(prob.C):
+        gid = component_gid(prob, st, c).astype(np.int64)
+        ing = gid >= 0
+        rows = np.where(ing, gid, 0) + offs[c]
+        d = (st.src == c).astype(np.float64)
+        l = (num[rows[:, None], f_idx, xs] - d) / (den[rows[:, None], f_idx] - d)
+        lh += np.where(ing[:, None], w[:, :, c] * l, 0.0)
+    return np.where(valid, lh, 1.0)

@@ -59,7 +59,7 @@ RECORD_DTYPE = np.dtype([("op", "<i4"), ("accept", "<i4"), ("changed", "<i4"), (
 EXPORTS = ["sb_create", "sb_destroy", "sb_last_error", "sb_chain_config", "sb_set_state", "sb_get_state", "sb_eval",
            "sb_posterior", "sb_run", "sb_run_async", "sb_sync", "sb_op_stats", "sb_swap", "sb_get_slots",
            "sb_set_slots", "sb_counts_rebuild_mma", "sb_counts_rebuild_hist", "sb_info", "sb_stream",
-           "sb_eval_batch", "sb_eval_stats", "sb_eval_terms", "sb_stats_buffer", "sb_eval_set_mode"]
+           "sb_eval_batch", "sb_eval_stats", "sb_eval_terms", "sb_stats_buffer", "sb_eval_set_mode", "sb_obs_loglik"]
 
 
 def _bind(lib):
@@ -91,6 +91,7 @@ def _bind(lib):
     lib.sb_eval_terms.argtypes = [vp, i64, vp, vp]
     lib.sb_stats_buffer.argtypes = [vp, vp, vp, vp, vp]
     lib.sb_eval_set_mode.argtypes = [vp, i32]
+    lib.sb_obs_loglik.argtypes = [vp, vp, vp, vp, vp]
     return lib
 
 
@@ -239,6 +240,17 @@ class DeviceContext:
         out = (_Posterior * self.n_chains)()
         self._ck(self.lib.sb_eval_terms(self.h, int(n_global), C.cast(out, C.c_void_p), None))
         return self._posts(out)
+
+    def obs_loglik(self, want_lh: bool = True, want_objects: bool = True):
+        """Observation likelihood of every chain (LikelihoodLogger's product): returns
+        (lh float32 [n_chains,N,F] or None, per-object sums of log lh [n_chains,N] or None,
+        per-chain sums [n_chains], device ms)."""
+        p = self.prob
+        lh = np.empty((self.n_chains, p.N, p.F), np.float32) if want_lh else None
+        ob = np.empty((self.n_chains, p.N), np.float64) if want_objects else None
+        sums, ms = np.empty(self.n_chains, np.float64), np.zeros(1, np.float32)
+        self._ck(self.lib.sb_obs_loglik(self.h, _ptr(lh), _ptr(ob), _ptr(sums), _ptr(ms)))
+        return lh, ob, sums, float(ms[0])
 
     def stats_buffer(self):
         """(device address, int32 elements, per-state stride, (n_counts, n_hist, n_sizes))."""

@@ -70,6 +70,10 @@ struct sb_ctx {
     double *d_epartial = nullptr, *d_egeo = nullptr, *d_epost = nullptr;
     unsigned *d_eticket = nullptr;
     int *d_eerr = nullptr;
+    // observation likelihood (allocated by the first sb_obs_loglik)
+    SbObsPlan oplan;
+    float *d_obs_out = nullptr;
+    double *d_obs_part = nullptr, *d_obs_ll = nullptr, *d_obs_sums = nullptr;
     std::vector<void *> allocs;
     sb_stream_t stream = 0;
     std::string err;
@@ -199,6 +203,19 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
         P.n_combos = (int)combo_pat.size();
         if (combo_rows.empty()) combo_rows.push_back(-1);
         TRY(up(c, &P.combo_id, combo_id)); TRY(up(c, &P.combo_rows, combo_rows)); TRY(up(c, &P.combo_pat, combo_pat));
+        if (C <= 4 && P.G_tot < 255 && P.n_pat < 256) {
+            std::vector<uint32_t> pack(N);
+            for (int o = 0; o < N; o++) {
+                uint32_t w = (uint32_t)pat_id[o];
+                for (int u = 1; u < 4; u++) {
+                    int g = 255;
+                    if (u <= nc && gid[(size_t)(u - 1) * N + o] >= 0) g = P.goff[u] + gid[(size_t)(u - 1) * N + o];
+                    w |= (uint32_t)g << (8 * u);
+                }
+                pack[o] = w;
+            }
+            TRY(up(c, &P.obj_pack, pack));
+        }
         // per-combo pass tables: 16 B per (combo, feature, state) and CTA
         P.use_tables = (size_t)P.n_combos * F * S * 16 <= ((size_t)8 << 20);
 #ifdef SB_HOSTSIM
@@ -783,6 +800,57 @@ SB_API int sb_eval_set_mode(sb_ctx *c, int mode) {
 SB_API int sb_eval_batch(sb_ctx *c, sb_posterior_t *out, float *ms2) {
     TRY(sb_eval_stats(c, ms2 ? ms2 : nullptr));
     return sb_eval_terms(c, 0, out, ms2 ? ms2 + 1 : nullptr);
+}
+
+// Observation likelihood of every chain (LikelihoodLogger._write_sample, sbayes/sampling/
+// loggers.py:354-359; likelihood_per_component_exact, sbayes/sampling/conditionals.py:300-367).
+// Runs the statistics pass first (the tables need the committed counts), then one streaming
+// kernel.  lh_out [n_chains, N, F] float32, obj_ll_out [n_chains, N] and sums_out [n_chains]
+// (sum of log lh per object / per chain) may each be NULL; ms receives the device time of the
+// likelihood kernel + reduction.
+SB_API int sb_obs_loglik(sb_ctx *c, float *lh_out, double *obj_ll_out, double *sums_out, float *ms) {
+    TRY(check_chain(c, 0));
+    const SbProblem &P = c->P;
+    const size_t nNF = (size_t)P.N * P.F;
+    if (!c->d_obs_out) {
+        if (sb_obs_make_plan(P, c->n_chains, c->n_sm, &c->oplan)) return fail(c, "observation-likelihood tables do not fit in shared memory");
+        TRY(mk(c, &c->d_obs_out, nNF * c->n_chains));
+        TRY(mk(c, &c->d_obs_part, (size_t)c->n_chains * c->oplan.n_ftiles * P.N));
+        TRY(mk(c, &c->d_obs_ll, (size_t)c->n_chains * P.N)); TRY(mk(c, &c->d_obs_sums, (size_t)c->n_chains));
+#ifndef SB_HOSTSIM
+        CK(cudaFuncSetAttribute((const void *)sb_obs_lik_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->oplan.smem));
+#endif
+    }
+    TRY(sb_eval_stats(c, nullptr));
+    SbObsArgs A; memset(&A, 0, sizeof A);
+    A.P = P; A.states = c->d_states; A.n_states = c->n_chains; A.plan = c->oplan;
+    A.out = c->d_obs_out; A.obj_part = c->d_obs_part; A.obj_ll = c->d_obs_ll; A.sums = c->d_obs_sums;
+    const int grid = c->n_chains * c->oplan.n_ftiles * c->oplan.n_oblk;
+#ifdef SB_HOSTSIM
+    if (ms) *ms = 0.f;
+    hostsim::launch([&]() { sb_obs_lik_kernel(A); }, grid, 64, c->oplan.smem);
+    TRY(dev_zero(c, c->d_eticket, sizeof(unsigned) * c->n_chains));
+    hostsim::launch([&]() { sb_obs_reduce_kernel(A, c->d_epartial, c->d_eticket); }, c->n_chains * SB_OBS_RPARTS, 64, 1024);
+#else
+    EvTimer t(c->stream, ms);
+    sb_obs_lik_kernel<<<grid, SB_EVAL_BLOCK, c->oplan.smem, c->stream>>>(A);
+    CK(cudaGetLastError());
+    TRY(dev_zero(c, c->d_eticket, sizeof(unsigned) * c->n_chains));
+    sb_obs_reduce_kernel<<<c->n_chains * SB_OBS_RPARTS, SB_EVAL_BLOCK, 1024, c->stream>>>(A, c->d_epartial, c->d_eticket);
+    CK(cudaGetLastError());
+    t.stop();
+#endif
+    c->launches += 2;
+    std::vector<SbSlot> slots(c->n_chains);
+    TRY(d2h(c, slots.data(), c->d_slots, sizeof(SbSlot) * c->n_chains));
+    for (int i = 0; i < c->n_chains; i++) {
+        const int s = slots[i].state;
+        if (lh_out) TRY(d2h(c, lh_out + (size_t)i * nNF, c->d_obs_out + (size_t)s * nNF, sizeof(float) * nNF));
+        if (obj_ll_out) TRY(d2h(c, obj_ll_out + (size_t)i * P.N, c->d_obs_ll + (size_t)s * P.N, sizeof(double) * P.N));
+        if (sums_out) TRY(d2h(c, sums_out + i, c->d_obs_sums + s, sizeof(double)));
+    }
+    if (!lh_out && !obj_ll_out && !sums_out) TRY(dev_sync(c));
+    return 0;
 }
 
 // device address and length (int32 elements) of the statistics block of all states, laid out

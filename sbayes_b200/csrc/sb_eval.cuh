@@ -242,18 +242,9 @@ SB_DEV void ev_hist_fast(const SbEvalArgs &A) {
         const uint8_t *xr = P.x, *sr = src0;
         if (live) {
             const int k = st.cluster_of[o];
-            const int combo = sb_ldg(P.combo_id + o);
-            const int32_t *rows = P.combo_rows + (size_t)combo * nconf;
-            gw = (uint32_t)(k >= 0 ? k : 255);
-#ifndef SB_HOSTSIM
-#pragma unroll
-#endif
-            for (int u = 1; u < 4; u++) {
-                int g = 255;
-                if (u <= nconf) { g = sb_ldg(rows + u - 1); g = g >= 0 ? g : 255; }
-                gw |= (uint32_t)g << (8 * u);
-            }
-            hb = n_cnt + (sb_ldg(P.combo_pat + combo) * 2 + (k >= 0 ? 1 : 0)) * hs;
+            const uint32_t pk = sb_ldg(P.obj_pack + o);          // independent of the other loads
+            gw = (uint32_t)(k >= 0 ? k : 255) | (pk & 0xFFFFFF00u);
+            hb = n_cnt + ((int)(pk & 255u) * 2 + (k >= 0 ? 1 : 0)) * hs;
             const size_t off = (size_t)o * P.ldx + f0;
             xr = P.x + off; sr = (st.osel[o] ? src1 : src0) + off;
             if (tile == 0 && k >= 0) sb_atomic_add_i32(sz + k, 1);
@@ -291,7 +282,7 @@ SB_DEV void ev_hist_fast(const SbEvalArgs &A) {
 
 // (forcing 64 registers for a fourth CTA per SM measured slower: profiles/r1l_eval_smem_sweep.txt)
 SB_KERNEL sb_eval_hist_kernel(const SB_GRID_CONSTANT SbEvalArgs A) {
-    if (A.P.C <= 4 && A.P.G_tot < 255) ev_hist_fast(A);
+    if (A.P.obj_pack) ev_hist_fast(A);
     else if (A.P.C <= 4) ev_hist_body<4>(A);
     else ev_hist_body<8>(A);
 }
@@ -453,6 +444,210 @@ SB_KERNEL sb_eval_terms_kernel(const SB_GRID_CONSTANT SbEvalArgs A) {
     if (P.geo) for (int k = 0; k < P.K; k++) geo += A.geo_val[(size_t)s_idx * P.K + k];
     double *post = A.post + (size_t)s_idx * 8;
     post[0] = sfp ? 0.0 : a; post[1] = size_pr; post[2] = geo; post[3] = c; post[4] = b; post[5] = 0.0; post[6] = 0.0; post[7] = 0.0;
+}
+
+// -----------------------------------------------------------------------------------------
+// observation likelihood: what LikelihoodLogger writes per logged sample
+// (sbayes/sampling/loggers.py:354-359):  lh[o,f] = sum_c w~[o,f,c] * l_c[o,f]  with the
+// leave-one-out component likelihoods of likelihood_per_component_exact
+// (sbayes/sampling/conditionals.py:300-367)
+//     l_c[o,f] = (counts[g,f,x] + alpha[g,f,x] - d) / (sum_s(counts + alpha)[g,f] - d),  d = [src[o,f] == c]
+// (0 where o is in no group of c; lh = 1 where the observation is missing).
+// One streaming pass: 2 B read (state byte, source byte) + 4 B written (float32) per observation.
+// CTA = (state, feature tile, object block); the tile's tables (counts + alpha, the two
+// reciprocals of the row totals, the normalised weights per has-pattern) are built in shared
+// memory in fp64; a warp takes 32 consecutive objects, a lane one object and 16 features at a
+// time; log(lh) is accumulated through products of four.  Per-object sums over the tile go to
+// obj_part[state][tile][o]; sb_obs_reduce_kernel adds tiles and objects in a fixed order.
+// -----------------------------------------------------------------------------------------
+struct SbObsPlan { int ft, n_ftiles, n_oblk, rows_per_blk; unsigned smem; };
+
+struct SbObsArgs {
+    SbProblem P;
+    const SbShared *states;
+    int n_states;
+    SbObsPlan plan;
+    float *out;          // [n_states, N, F]
+    double *obj_part;    // [n_states, n_ftiles, N]
+    double *obj_ll;      // [n_states, N]
+    double *sums;        // [n_states]
+};
+
+static inline int sb_obs_make_plan(const SbProblem &P, int n_states, int n_sm, SbObsPlan *pl) {
+    const size_t per_f = ((size_t)P.G_tot * P.S + 2 * (size_t)P.G_tot + (size_t)P.n_pat * 2 * P.C) * 8;
+    const size_t fixed = 256 + (3 * (size_t)P.G_tot + (size_t)P.n_pat * 2) * 8;      // + odd-stride padding
+    size_t budget = 56 * 1024;
+    if (fixed + 16 * per_f > budget) budget = 110 * 1024;
+    if (fixed + 16 * per_f > budget) budget = 220 * 1024;
+    if (fixed + 16 * per_f > budget) return -1;
+    int ft_max = (int)((budget - fixed) / per_f) / 16 * 16;
+    int n_ftiles = (P.ldx + ft_max - 1) / ft_max;
+    int ft = ((P.ldx / 16 + n_ftiles - 1) / n_ftiles) * 16;
+    n_ftiles = (P.ldx + ft - 1) / ft;
+    long long want = 4LL * n_sm, base = (long long)n_states * n_ftiles;
+    long long n_oblk = (want + base - 1) / base;
+    long long max_blk = P.N / 128; if (max_blk < 1) max_blk = 1;
+    if (n_oblk > max_blk) n_oblk = max_blk;
+    int rows = (int)((P.N + n_oblk - 1) / n_oblk);
+    n_oblk = (P.N + rows - 1) / rows;
+    pl->ft = ft; pl->n_ftiles = n_ftiles; pl->n_oblk = (int)n_oblk; pl->rows_per_blk = rows;
+    pl->smem = (unsigned)(fixed + (size_t)ft * per_f);
+    return 0;
+}
+
+template <int UC>
+SB_DEV void ev_obs_body(const SbObsArgs &A) {
+    const SbProblem &P = A.P;
+    const SbObsPlan &pl = A.plan;
+    const int F = P.F, S = P.S, C = P.C, nconf = P.n_conf, N = P.N;
+    int w = sb_cta();
+    const int oblk = w % pl.n_oblk; w /= pl.n_oblk;
+    const int tile = w % pl.n_ftiles; w /= pl.n_ftiles;
+    const int s_idx = w;
+    const SbShared st = A.states[s_idx];
+    const int f0 = tile * pl.ft;
+    const int ftw = (P.ldx - f0 < pl.ft ? P.ldx - f0 : pl.ft);
+    const int ft = pl.ft;
+    const int fv = F - f0 < ftw ? F - f0 : ftw;                    // real features in the tile
+    const int gs = ev_odd(ft * S), rs = ev_odd(ft), hs = ev_odd(ft * C);
+    double *num = (double *)sb_smem();                             // [G_tot][gs]   counts + alpha
+    double *rd0 = num + (size_t)P.G_tot * gs;                      // [G_tot][rs]   1 / total
+    double *rd1 = rd0 + (size_t)P.G_tot * rs;                      // [G_tot][rs]   1 / (total - 1)
+    double *wt = rd1 + (size_t)P.G_tot * rs;                       // [n_pat*2][hs] normalised weights
+    for (int i = sb_tid(); i < P.G_tot * ft; i += sb_nthr()) {
+        const int g = i / ft, fl = i % ft;
+        double tot = 0.0;
+        if (fl < fv) {
+            const size_t ar = ((size_t)ev_arow(P, g) * F + f0 + fl) * S, cr = ((size_t)g * F + f0 + fl) * S;
+            for (int s = 0; s < S; s++) { const double v = (double)st.counts[cr + s] + sb_ldg(P.alpha + ar + s); num[(size_t)g * gs + fl * S + s] = v; tot += v; }
+        } else
+            for (int s = 0; s < S; s++) num[(size_t)g * gs + fl * S + s] = 0.0;
+        rd0[(size_t)g * rs + fl] = tot > 0.0 ? 1.0 / tot : 0.0;
+        rd1[(size_t)g * rs + fl] = tot > 1.0 ? 1.0 / (tot - 1.0) : 0.0;
+    }
+    for (int i = sb_tid(); i < P.n_pat * 2 * ft; i += sb_nthr()) {
+        const int pz = i / ft, fl = i % ft, z = pz & 1, bits = sb_ldg(P.pat_bits + (pz >> 1));
+        double t1 = 0.0;
+        if (fl < fv) for (int c = 0; c < C; c++) t1 += (c == 0 ? (double)z : (double)((bits >> c) & 1)) * (double)st.W[(f0 + fl) * C + c];
+        for (int c = 0; c < C; c++) {
+            const double hh = c == 0 ? (double)z : (double)((bits >> c) & 1);
+            wt[(size_t)pz * hs + fl * C + c] = (fl < fv && t1 > 0.0) ? hh * (double)st.W[(f0 + fl) * C + c] / t1 : 0.0;
+        }
+    }
+    sb_cta_sync();
+    const int lo = oblk * pl.rows_per_blk, hi = lo + pl.rows_per_blk < N ? lo + pl.rows_per_blk : N;
+    const int cpr = ftw >> 4;
+    const uint8_t *src0 = st.src[0], *src1 = st.src[1];
+    float *out = A.out + (size_t)s_idx * N * F;
+    double *opart = A.obj_part + ((size_t)s_idx * pl.n_ftiles + tile) * N;
+    for (int o0 = lo + sb_warp() * 32; o0 < hi; o0 += sb_nwarps() * 32) {
+        const int o = o0 + sb_lane();
+        if (o >= hi) continue;
+        int gb[UC], gr[UC];
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+        for (int u = 0; u < UC; u++) { gb[u] = -1; gr[u] = 0; }
+        const int k = st.cluster_of[o];
+        if (k >= 0) { gb[0] = k * gs; gr[0] = k * rs; }
+        int pat;
+        if (P.obj_pack) {
+            const uint32_t pk = sb_ldg(P.obj_pack + o);
+            pat = (int)(pk & 255u);
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+            for (int u = 1; u < 4; u++) { const int g = (int)((pk >> (8 * u)) & 255u); if (g != 255) { gb[u] = g * gs; gr[u] = g * rs; } }
+        } else {
+            const int combo = sb_ldg(P.combo_id + o);
+            const int32_t *rows = P.combo_rows + (size_t)combo * nconf;
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+            for (int u = 1; u < UC; u++)
+                if (u <= nconf) { const int g = sb_ldg(rows + u - 1); if (g >= 0) { gb[u] = g * gs; gr[u] = g * rs; } }
+            pat = sb_ldg(P.combo_pat + combo);
+        }
+        const double *wrow = wt + (size_t)(pat * 2 + (k >= 0 ? 1 : 0)) * hs;
+        const size_t off = (size_t)o * P.ldx + f0;
+        const uint8_t *xr = P.x + off, *sr = (st.osel[o] ? src1 : src0) + off;
+        float *orow = out + (size_t)o * F + f0;
+        double acc = 0.0, prod = 1.0;
+        for (int ch = 0; ch < cpr; ch++) {
+            const sb_u4 xv = ev_load16(xr + ch * 16), sv = ev_load16(sr + ch * 16);
+            const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w}, ss[4] = {sv.x, sv.y, sv.z, sv.w};
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+            for (int q = 0; q < 4; q++) {
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+                for (int j = 0; j < 4; j++) {
+                    const int fl = ch * 16 + q * 4 + j;
+                    if (fl >= fv) continue;
+                    const int x = (xs[q] >> (8 * j)) & 255, cs = (ss[q] >> (8 * j)) & 255;
+                    double lh = 1.0;
+                    if (x != SB_NA_U8) {
+                        lh = 0.0;
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+                        for (int u = 0; u < UC; u++) {
+                            if (u < C && gb[u] >= 0) {
+                                const bool d = cs == u;
+                                const double n = num[gb[u] + fl * S + x] - (d ? 1.0 : 0.0);
+                                const double r = d ? rd1[gr[u] + fl] : rd0[gr[u] + fl];
+                                lh += wrow[fl * C + u] * (n * r);
+                            }
+                        }
+                    }
+                    orow[fl] = (float)lh;
+                    prod *= lh;
+                }
+                acc += log(prod); prod = 1.0;
+            }
+        }
+        opart[o] = acc;
+    }
+}
+
+SB_KERNEL sb_obs_lik_kernel(const SB_GRID_CONSTANT SbObsArgs A) {
+    if (A.P.C <= 4) ev_obs_body<4>(A); else ev_obs_body<8>(A);
+}
+
+// obj_ll[state][o] = sum over tiles (tile order); sums[state] = sum over objects.  CTA =
+// (state, part of the objects); the per-part sums are combined by the last CTA of the state in
+// part order, so the chain total does not depend on the schedule.
+#define SB_OBS_RPARTS 32
+SB_KERNEL sb_obs_reduce_kernel(const SB_GRID_CONSTANT SbObsArgs A, double *partial, unsigned *ticket) {
+    const int part = sb_cta() % SB_OBS_RPARTS, s_idx = sb_cta() / SB_OBS_RPARTS, N = A.P.N, nt = A.plan.n_ftiles;
+    const int per = (N + SB_OBS_RPARTS - 1) / SB_OBS_RPARTS, lo = part * per, hi = lo + per < N ? lo + per : N;
+    double acc = 0.0;
+    for (int o = lo + sb_tid(); o < hi; o += sb_nthr()) {
+        double v = 0.0;
+        for (int t = 0; t < nt; t++) v += A.obj_part[((size_t)s_idx * nt + t) * N + o];
+        A.obj_ll[(size_t)s_idx * N + o] = v;
+        acc += v;
+    }
+    double *red = (double *)sb_smem();
+    unsigned *flag = (unsigned *)(red + 32);
+    acc = ev_warp_sum(acc);
+    if (sb_lane() == 0) red[sb_warp()] = acc;
+    sb_cta_sync();
+    if (sb_tid() == 0) {
+        double t = 0.0;
+        for (int i = 0; i < sb_nwarps(); i++) t += red[i];
+        partial[(size_t)s_idx * SB_OBS_RPARTS + part] = t;
+        sb_threadfence();
+        flag[0] = (unsigned)sb_atomic_add_i32((int *)ticket + s_idx, 1) == (unsigned)(SB_OBS_RPARTS - 1);
+        if (flag[0]) {
+            sb_threadfence();
+            double tot = 0.0;
+            for (int p = 0; p < SB_OBS_RPARTS; p++) tot += ((const volatile double *)partial)[(size_t)s_idx * SB_OBS_RPARTS + p];
+            A.sums[s_idx] = tot;
+        }
+    }
 }
 
 // launch geometry of the histogram pass: the widest feature tile whose bins fit `budget` bytes of

@@ -55,6 +55,9 @@ struct SbProblem {
     const int32_t *combo_id;     // [N]
     const int32_t *combo_rows;   // [n_combos, n_conf] stacked group row or -1
     const int32_t *combo_pat;    // [n_combos] has-pattern index
+    // one word per object for the streaming kernels (null unless C <= 4, G_tot < 255, n_pat < 256):
+    // byte 0 = has-pattern index, bytes 1..3 = stacked group row of components 1..3 (255 = none)
+    const uint32_t *obj_pack;
 };
 
 // ---------------------------------------------------------------------------------------

@@ -228,3 +228,57 @@ def test_gpu_mma_statistics_wide_groups():
     """many group columns (N tile of 96) and few features per CTA, the config-5 regime"""
     prob, _ = synth.make_problem(N=3000, F=150, S=8, K=16, n_fam=64, seed=5)
     _mma_vs_hist(prob, [synth.initial_state(prob, seed=3)])
+
+
+# ------------------------------------------------------------------ observation likelihood
+def check_obs(prob, states, lib=None):
+    ctx = DeviceContext(prob, len(states), _lib=lib)
+    try:
+        for c, st in enumerate(states):
+            ctx.configure(c, ChainConfig(seed=c))
+            ctx.set_state(c, st)
+        lh, ob, sums, _ = ctx.obs_loglik()
+        for c, st in enumerate(states):
+            ref = st.copy()
+            ref.counts = M.rebuild_counts(prob, st)
+            want = M.observation_likelihood(prob, ref)
+            assert np.array_equal(lh[c], want.astype(np.float32)) or np.max(np.abs(lh[c] - want) / want) < 1.2e-7   # float32 output
+            assert np.max(np.abs(ob[c] - np.log(want).sum(axis=1)) / np.maximum(1.0, np.abs(ob[c]))) < TOL
+            assert parity.rel(float(np.log(want).sum()), float(sums[c])) < TOL
+        return lh, sums
+    finally:
+        ctx.close()
+
+
+def test_emulated_observation_likelihood(lib, env):
+    prob, sts = small_problem()
+    check_obs(prob, sts, lib)
+    prob, sts = small_problem(F=70, N=200)
+    check_obs(prob, sts[:2], lib)
+
+
+@pytest.mark.parametrize("case", ["obs_lik_small", "obs_lik_jagged"])
+def test_emulated_observation_likelihood_golden(lib, case):
+    _obs_golden(case, lib)
+
+
+def _obs_golden(case, lib=None):
+    """vectors computed by the live reference (tests/golden/make_obs_golden.py); the reference
+    rounds tables and weights to float32, so 2e-6 relative"""
+    d = np.load(os.path.join(parity.GOLDEN, case + ".npz"), allow_pickle=False)
+    prob, st = FX.problem_from_dict(d), FX.state_from_dict(d, "st_")
+    lh, sums = check_obs(prob, [st], lib)
+    assert np.max(np.abs(lh[0] - d["ref_lh"]) / d["ref_lh"]) < 2e-6
+    assert abs(sums[0] - np.log(d["ref_lh"]).sum()) < 2e-6 * abs(sums[0])
+
+
+@pytest.mark.gpu
+def test_gpu_observation_likelihood():
+    for case in ("obs_lik_small", "obs_lik_jagged"):
+        _obs_golden(case)
+    prob, sts = small_problem(F=70, N=200)
+    check_obs(prob, sts[:2])
+    prob, _ = synth.make_problem(N=1000, F=100, S=4, K=5, n_fam=8, seed=2)
+    check_obs(prob, [synth.initial_state(prob, seed=1000 + c) for c in range(2)])
+    prob, _ = synth.make_problem(N=5000, F=200, S=6, K=5, n_fam=20, seed=4)
+    check_obs(prob, [synth.initial_state(prob, seed=100)])

@@ -1,0 +1,21 @@
+"""Short run of the observation-likelihood kernel for an ncu capture (profiling helper).
+usage: tools_obsprof.py <case> [chains]"""
+import sys
+import tools_scale as TS
+from sbayes_b200 import synth
+from sbayes_b200.backend import DeviceContext
+from sbayes_b200.packed import ChainConfig
+
+w = dict(TS.CASES[sys.argv[1]])
+if len(sys.argv) > 2:
+    w["chains"] = int(sys.argv[2])
+prob, _ = synth.make_problem(N=w["N"], F=w["F"], S=w["S"], K=w["K"], n_fam=w["n_fam"], seed=w["seed"])
+states = [synth.initial_state(prob, seed=100 + c) for c in range(min(w["chains"], 2))]
+ctx = DeviceContext(prob, w["chains"])
+for c in range(w["chains"]):
+    ctx.configure(c, ChainConfig(seed=c))
+    ctx.set_state(c, states[c % len(states)])
+for _ in range(3):
+    r = ctx.obs_loglik(False, False)
+print(sys.argv[1], r[3], r[2][0])
+ctx.close()

@@ -55,6 +55,13 @@ def main():
             except Exception as e:
                 print(f"[{name}] mma failed: {e}", flush=True)
             ctx.eval_set_mode("hist")
+            try:
+                ctx.obs_loglik(want_lh=False, want_objects=False)
+                tms = [ctx.obs_loglik(want_lh=False, want_objects=False)[3] for _ in range(8)]
+                t = min(tms)
+                print(f"[{name}] obs_loglik: {t*1e3:.1f} us  ({6*prob.N*prob.F*w['chains']/t/1e6:.1f} GB/s algorithmic at 6 B/obs, {prob.N*prob.F*w['chains']/t/1e6:.1f} G obs/s)", flush=True)
+            except Exception as e:
+                print(f"[{name}] obs_loglik failed: {e}", flush=True)
             if "--no-steps" in sys.argv: ctx.close(); continue
             ctx.run(10)
             torch.cuda.synchronize(); t = time.perf_counter()
