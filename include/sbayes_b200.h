@@ -116,8 +116,8 @@ int sb_posterior(sb_ctx *ctx, int chain, sb_posterior_t *out);     /* cached val
 /* Stand-alone full evaluation of EVERY chain of the ctx (HBM-bound statistics pass + terms):
  * sb_eval_batch = sb_eval_stats + sb_eval_terms.  out[n_chains]; ms2 (may be NULL) receives the
  * device time in ms of {statistics pass, terms}.  With the objects of a large matrix sharded over
- * GPUs, every rank runs sb_eval_stats on its shard, all-reduces the int32 block returned by
- * sb_stats_buffer, and calls sb_eval_terms(n_global = objects of the whole problem); the source
+ * GPUs, every rank runs sb_eval_stats on its shard, all-reduces the leading counts | sizes part of the int32 block
+ * returned by sb_stats_buffer (per state: counts | sizes | histogram; layout3 = {n_counts, n_hist, n_sizes}), and calls sb_eval_terms(n_global = objects of the whole problem); the source
  * prior it returns is the shard's partial sum (sbayes_b200/shard.py). */
 int sb_eval_batch(sb_ctx *ctx, sb_posterior_t *out, float *ms2);
 int sb_eval_stats(sb_ctx *ctx, float *ms);

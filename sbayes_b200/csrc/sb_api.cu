@@ -62,7 +62,7 @@ struct sb_ctx {
     int32_t *d_counts_tmp = nullptr;
     // stand-alone evaluation (sb_eval.cuh): the int32 statistics of all states are one block
     int32_t *d_stats = nullptr;
-    size_t stats_stride = 0;          // int32 per state: counts | H | sizes, padded to 16 B
+    size_t stats_stride = 0;          // int32 per state: counts | sizes | H, padded to 16 B
     SbEvalPlan eplan;
     int eplan_ok = 0;
     SbMmaPlan mplan;                  // tcgen05 statistics pass over all states
@@ -378,7 +378,7 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
         TRY(mk(c, &s.cluster_of, N)); TRY(mk(c, &s.W, (size_t)F * C));
         for (int b = 0; b < 2; b++) { TRY(mk(c, &s.src[b], nS)); TRY(mk(c, &s.val[b], N)); }
         TRY(mk(c, &s.osel, N));
-        s.counts = c->d_stats + (size_t)i * c->stats_stride; s.H = s.counts + nG; s.sizes = s.H + nH;
+        s.counts = c->d_stats + (size_t)i * c->stats_stride; s.sizes = s.counts + nG; s.H = s.sizes + K;   // counts | sizes | H
         TRY(mk(c, &s.list_a, N)); TRY(mk(c, &s.list_b, N)); TRY(mk(c, &s.flag_a, N)); TRY(mk(c, &s.flag_b, N));
         TRY(mk(c, &s.post, 8));
     }
@@ -854,7 +854,8 @@ SB_API int sb_obs_loglik(sb_ctx *c, float *lh_out, double *obj_ll_out, double *s
 }
 
 // device address and length (int32 elements) of the statistics block of all states, laid out
-// [state][counts G_tot*F*S | H n_pat*2*F*C | sizes K | pad]: what a sharded run all-reduces
+// [state][counts G_tot*F*S | sizes K | H n_pat*2*F*C | pad]; layout3 = {n_counts, n_hist, n_sizes}.
+// A sharded run all-reduces the leading counts | sizes part (the histogram is shard-local)
 SB_API int sb_stats_buffer(sb_ctx *c, uint64_t *dev_ptr, int64_t *n_int32, int64_t *stride, int64_t *layout3) {
     if (!c) return -1;
     if (dev_ptr) *dev_ptr = (uint64_t)(uintptr_t)c->d_stats;

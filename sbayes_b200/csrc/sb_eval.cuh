@@ -21,7 +21,7 @@
 #include "sb_types.h"
 
 #define SB_EVAL_BLOCK 256
-#define SB_EVAL_MAXPARTS 64
+#define SB_EVAL_MAXPARTS 512
 
 struct SbEvalPlan {
     int ft;            // features per tile (multiple of 16 bytes of a packed row)
@@ -456,8 +456,7 @@ SB_KERNEL sb_eval_terms_kernel(const SB_GRID_CONSTANT SbEvalArgs A) {
 // One streaming pass: 2 B read (state byte, source byte) + 4 B written (float32) per observation.
 // CTA = (state, feature tile, object block); the tile's tables (counts + alpha, the two
 // reciprocals of the row totals, the normalised weights per has-pattern) are built in shared
-// memory in fp64; a warp takes 32 consecutive objects, a lane one object and 16 features at a
-// time; log(lh) is accumulated through products of four.  Per-object sums over the tile go to
+// memory in fp64; log(lh) is taken of products of four.  Per-object sums over the tile go to
 // obj_part[state][tile][o]; sb_obs_reduce_kernel adds tiles and objects in a fixed order.
 // -----------------------------------------------------------------------------------------
 struct SbObsPlan { int ft, n_ftiles, n_oblk, rows_per_blk; unsigned smem; };
@@ -474,16 +473,15 @@ struct SbObsArgs {
 };
 
 static inline int sb_obs_make_plan(const SbProblem &P, int n_states, int n_sm, SbObsPlan *pl) {
-    const size_t per_f = ((size_t)P.G_tot * P.S + 2 * (size_t)P.G_tot + (size_t)P.n_pat * 2 * P.C) * 8;
-    const size_t fixed = 256 + (3 * (size_t)P.G_tot + (size_t)P.n_pat * 2) * 8;      // + odd-stride padding
+    const size_t per_f = ((size_t)P.G_tot * P.S + 2 * (size_t)P.G_tot + (size_t)P.n_pat * 2 * (P.C | 1)) * 8;
+    const size_t fixed = 256 + 2 * (size_t)P.G_tot * 8;                                  // + odd-stride padding
     size_t budget = 56 * 1024;
     if (fixed + 16 * per_f > budget) budget = 110 * 1024;
     if (fixed + 16 * per_f > budget) budget = 220 * 1024;
     if (fixed + 16 * per_f > budget) return -1;
-    int ft_max = (int)((budget - fixed) / per_f) / 16 * 16;
-    int n_ftiles = (P.ldx + ft_max - 1) / ft_max;
-    int ft = ((P.ldx / 16 + n_ftiles - 1) / n_ftiles) * 16;
-    n_ftiles = (P.ldx + ft - 1) / ft;
+    int ft = 16;                                                                           // power of two: 4, 8, 16 or 32 lanes per row
+    while (ft < 128 && fixed + 2 * ft * per_f <= budget && ft < P.ldx) ft *= 2;
+    int n_ftiles = (P.ldx + ft - 1) / ft;
     long long want = 4LL * n_sm, base = (long long)n_states * n_ftiles;
     long long n_oblk = (want + base - 1) / base;
     long long max_blk = P.N / 128; if (max_blk < 1) max_blk = 1;
@@ -495,6 +493,10 @@ static inline int sb_obs_make_plan(const SbProblem &P, int n_states, int n_sm, S
     return 0;
 }
 
+// Work mapping: a row of the tile (one object, ft features) is shared by ft/4 lanes, lane j of
+// the row takes features j, j + ft/4, j + 2 ft/4, j + 3 ft/4 -- every load, table gather and
+// store of one instruction then touches consecutive features (coalesced bytes in, coalesced
+// floats out, table rows with odd strides); 32 / (ft/4) rows per warp iteration.
 template <int UC>
 SB_DEV void ev_obs_body(const SbObsArgs &A) {
     const SbProblem &P = A.P;
@@ -505,23 +507,24 @@ SB_DEV void ev_obs_body(const SbObsArgs &A) {
     const int tile = w % pl.n_ftiles; w /= pl.n_ftiles;
     const int s_idx = w;
     const SbShared st = A.states[s_idx];
-    const int f0 = tile * pl.ft;
-    const int ftw = (P.ldx - f0 < pl.ft ? P.ldx - f0 : pl.ft);
-    const int ft = pl.ft;
-    const int fv = F - f0 < ftw ? F - f0 : ftw;                    // real features in the tile
-    const int gs = ev_odd(ft * S), rs = ev_odd(ft), hs = ev_odd(ft * C);
-    double *num = (double *)sb_smem();                             // [G_tot][gs]   counts + alpha
-    double *rd0 = num + (size_t)P.G_tot * gs;                      // [G_tot][rs]   1 / total
-    double *rd1 = rd0 + (size_t)P.G_tot * rs;                      // [G_tot][rs]   1 / (total - 1)
-    double *wt = rd1 + (size_t)P.G_tot * rs;                       // [n_pat*2][hs] normalised weights
+    const int ft = pl.ft;                                          // 16, 32, 64 or 128
+    const int f0 = tile * ft;
+    const int fv = F - f0 < ft ? F - f0 : ft;                      // real features in the tile
+    // state rows are dense (S doubles); the state index is rotated by the feature, (x + fl) mod S,
+    // so lanes on consecutive features with equal states fall into different banks
+    const int Cp = ev_odd(C);
+    const int gs = ft * S, rs = ev_odd(ft), hs = ft * Cp;
+    double *num = (double *)sb_smem();                             // [G_tot][ft][S]    counts + alpha (rotated)
+    double *rd0 = num + (size_t)P.G_tot * gs;                      // [G_tot][rs]       1 / total
+    double *rd1 = rd0 + (size_t)P.G_tot * rs;                      // [G_tot][rs]       1 / (total - 1)
+    double *wt = rd1 + (size_t)P.G_tot * rs;                       // [n_pat*2][ft][Cp] normalised weights
     for (int i = sb_tid(); i < P.G_tot * ft; i += sb_nthr()) {
         const int g = i / ft, fl = i % ft;
         double tot = 0.0;
         if (fl < fv) {
             const size_t ar = ((size_t)ev_arow(P, g) * F + f0 + fl) * S, cr = ((size_t)g * F + f0 + fl) * S;
-            for (int s = 0; s < S; s++) { const double v = (double)st.counts[cr + s] + sb_ldg(P.alpha + ar + s); num[(size_t)g * gs + fl * S + s] = v; tot += v; }
-        } else
-            for (int s = 0; s < S; s++) num[(size_t)g * gs + fl * S + s] = 0.0;
+            for (int s = 0; s < S; s++) { const double v = (double)st.counts[cr + s] + sb_ldg(P.alpha + ar + s); num[(size_t)g * gs + fl * S + (s + fl) % S] = v; tot += v; }
+        }
         rd0[(size_t)g * rs + fl] = tot > 0.0 ? 1.0 / tot : 0.0;
         rd1[(size_t)g * rs + fl] = tot > 1.0 ? 1.0 / (tot - 1.0) : 0.0;
     }
@@ -531,84 +534,92 @@ SB_DEV void ev_obs_body(const SbObsArgs &A) {
         if (fl < fv) for (int c = 0; c < C; c++) t1 += (c == 0 ? (double)z : (double)((bits >> c) & 1)) * (double)st.W[(f0 + fl) * C + c];
         for (int c = 0; c < C; c++) {
             const double hh = c == 0 ? (double)z : (double)((bits >> c) & 1);
-            wt[(size_t)pz * hs + fl * C + c] = (fl < fv && t1 > 0.0) ? hh * (double)st.W[(f0 + fl) * C + c] / t1 : 0.0;
+            wt[(size_t)pz * hs + fl * Cp + c] = (fl < fv && t1 > 0.0) ? hh * (double)st.W[(f0 + fl) * C + c] / t1 : 0.0;
         }
     }
     sb_cta_sync();
     const int lo = oblk * pl.rows_per_blk, hi = lo + pl.rows_per_blk < N ? lo + pl.rows_per_blk : N;
-    const int cpr = ftw >> 4;
+    const int lpr = ft >> 2, rpw = 32 / lpr;                       // lanes per row, rows per warp iteration
+    const int fg = sb_lane() % lpr, rw = sb_lane() / lpr;
+    int rot[4];
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+    for (int j = 0; j < 4; j++) rot[j] = (fg + j * lpr) % S;
     const uint8_t *src0 = st.src[0], *src1 = st.src[1];
     float *out = A.out + (size_t)s_idx * N * F;
     double *opart = A.obj_part + ((size_t)s_idx * pl.n_ftiles + tile) * N;
-    for (int o0 = lo + sb_warp() * 32; o0 < hi; o0 += sb_nwarps() * 32) {
-        const int o = o0 + sb_lane();
-        if (o >= hi) continue;
+    for (int o0 = lo + sb_warp() * rpw; o0 < hi; o0 += sb_nwarps() * rpw) {
+        const int o = o0 + rw;
+        const bool live = o < hi;
         int gb[UC], gr[UC];
 #ifndef SB_HOSTSIM
 #pragma unroll
 #endif
         for (int u = 0; u < UC; u++) { gb[u] = -1; gr[u] = 0; }
-        const int k = st.cluster_of[o];
-        if (k >= 0) { gb[0] = k * gs; gr[0] = k * rs; }
-        int pat;
-        if (P.obj_pack) {
-            const uint32_t pk = sb_ldg(P.obj_pack + o);
-            pat = (int)(pk & 255u);
+        double acc = 0.0;
+        if (live) {
+            const int k = st.cluster_of[o];
+            if (k >= 0) { gb[0] = k * gs; gr[0] = k * rs; }
+            int pat;
+            if (P.obj_pack) {
+                const uint32_t pk = sb_ldg(P.obj_pack + o);
+                pat = (int)(pk & 255u);
 #ifndef SB_HOSTSIM
 #pragma unroll
 #endif
-            for (int u = 1; u < 4; u++) { const int g = (int)((pk >> (8 * u)) & 255u); if (g != 255) { gb[u] = g * gs; gr[u] = g * rs; } }
-        } else {
-            const int combo = sb_ldg(P.combo_id + o);
-            const int32_t *rows = P.combo_rows + (size_t)combo * nconf;
+                for (int u = 1; u < 4; u++) { const int g = (int)((pk >> (8 * u)) & 255u); if (g != 255) { gb[u] = g * gs; gr[u] = g * rs; } }
+            } else {
+                const int combo = sb_ldg(P.combo_id + o);
+                const int32_t *rows = P.combo_rows + (size_t)combo * nconf;
 #ifndef SB_HOSTSIM
 #pragma unroll
 #endif
-            for (int u = 1; u < UC; u++)
-                if (u <= nconf) { const int g = sb_ldg(rows + u - 1); if (g >= 0) { gb[u] = g * gs; gr[u] = g * rs; } }
-            pat = sb_ldg(P.combo_pat + combo);
-        }
-        const double *wrow = wt + (size_t)(pat * 2 + (k >= 0 ? 1 : 0)) * hs;
-        const size_t off = (size_t)o * P.ldx + f0;
-        const uint8_t *xr = P.x + off, *sr = (st.osel[o] ? src1 : src0) + off;
-        float *orow = out + (size_t)o * F + f0;
-        double acc = 0.0, prod = 1.0;
-        for (int ch = 0; ch < cpr; ch++) {
-            const sb_u4 xv = ev_load16(xr + ch * 16), sv = ev_load16(sr + ch * 16);
-            const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w}, ss[4] = {sv.x, sv.y, sv.z, sv.w};
+                for (int u = 1; u < UC; u++)
+                    if (u <= nconf) { const int g = sb_ldg(rows + u - 1); if (g >= 0) { gb[u] = g * gs; gr[u] = g * rs; } }
+                pat = sb_ldg(P.combo_pat + combo);
+            }
+            const double *wrow = wt + (size_t)(pat * 2 + (k >= 0 ? 1 : 0)) * hs;
+            const size_t off = (size_t)o * P.ldx + f0;
+            const uint8_t *xr = P.x + off, *sr = (st.osel[o] ? src1 : src0) + off;
+            float *orow = out + (size_t)o * F + f0;
+            int xs[4], cs[4];
 #ifndef SB_HOSTSIM
 #pragma unroll
 #endif
-            for (int q = 0; q < 4; q++) {
+            for (int j = 0; j < 4; j++) { const int fl = fg + j * lpr; xs[j] = fl < fv ? (int)sb_ldg(xr + fl) : SB_NA_U8; cs[j] = fl < fv ? (int)sr[fl] : SB_NA_U8; }
+            double prod = 1.0;
 #ifndef SB_HOSTSIM
 #pragma unroll
 #endif
-                for (int j = 0; j < 4; j++) {
-                    const int fl = ch * 16 + q * 4 + j;
-                    if (fl >= fv) continue;
-                    const int x = (xs[q] >> (8 * j)) & 255, cs = (ss[q] >> (8 * j)) & 255;
-                    double lh = 1.0;
-                    if (x != SB_NA_U8) {
-                        lh = 0.0;
+            for (int j = 0; j < 4; j++) {
+                const int fl = fg + j * lpr;
+                if (fl >= fv) continue;
+                const int x = xs[j];
+                double lh = 1.0;
+                if (x != SB_NA_U8) {
+                    lh = 0.0;
+                    int xr_ = x + rot[j]; xr_ = xr_ >= S ? xr_ - S : xr_;       // (x + fl) mod S
 #ifndef SB_HOSTSIM
 #pragma unroll
 #endif
-                        for (int u = 0; u < UC; u++) {
-                            if (u < C && gb[u] >= 0) {
-                                const bool d = cs == u;
-                                const double n = num[gb[u] + fl * S + x] - (d ? 1.0 : 0.0);
-                                const double r = d ? rd1[gr[u] + fl] : rd0[gr[u] + fl];
-                                lh += wrow[fl * C + u] * (n * r);
-                            }
+                    for (int u = 0; u < UC; u++) {
+                        if (u < C && gb[u] >= 0) {
+                            const bool d = cs[j] == u;
+                            const double n = num[gb[u] + fl * S + xr_] - (d ? 1.0 : 0.0);
+                            const double r = d ? rd1[gr[u] + fl] : rd0[gr[u] + fl];
+                            lh += wrow[fl * Cp + u] * (n * r);
                         }
                     }
-                    orow[fl] = (float)lh;
-                    prod *= lh;
                 }
-                acc += log(prod); prod = 1.0;
+                orow[fl] = (float)lh;
+                prod *= lh;
             }
+            acc = log(prod);
         }
-        opart[o] = acc;
+        // sum over the lanes of the row (segments of lpr lanes, lpr a power of two)
+        for (int d = lpr >> 1; d > 0; d >>= 1) acc += sb_shfl_f64(acc, sb_lane() ^ d);
+        if (live && fg == 0) opart[o] = acc;
     }
 }
 
@@ -670,7 +681,7 @@ static inline int sb_eval_make_plan(const SbProblem &P, int n_states, int n_sm, 
     n_oblk = (P.N + rows - 1) / rows;
     pl->ft = ft; pl->n_ftiles = n_ftiles; pl->n_oblk = (int)n_oblk; pl->rows_per_blk = rows;
     long long items = (long long)P.G_tot * P.F + (long long)P.n_pat * 2 * P.F + P.F;
-    long long parts = (items + 2047) / 2048;
+    long long parts = (items + 511) / 512;               // two rows per thread: the terms are lgamma-latency bound
     pl->n_parts = (int)(parts < 1 ? 1 : (parts > SB_EVAL_MAXPARTS ? SB_EVAL_MAXPARTS : parts));
     pl->smem = (unsigned)(fixed + (size_t)ft * bins_per_f * 4);
     return 0;

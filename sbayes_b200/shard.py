@@ -7,7 +7,7 @@ sum over objects: the count tensors (`recalculate_feature_counts`, sbayes/sampli
 568-611).  Each rank holds a contiguous block of objects in its own `DeviceContext` and runs the
 statistics pass (`sb_eval_stats`) on it; then
 
-  1. ONE all-reduce (sum, int32) of the statistics block of all chains: counts | histogram | sizes
+  1. ONE all-reduce (sum, int32) of the leading `counts | sizes` part of every chain's statistics block
   2. the terms kernel on every rank (`sb_eval_terms`, identical counts -> identical log-likelihood
      and size prior on every rank; the source prior it returns is the shard's partial sum)
   3. ONE all-reduce (sum, fp64) of the per-chain partial source priors.
@@ -81,6 +81,34 @@ class ShardedEvaluator:
             self._stats = torch.as_tensor(_DeviceArray(ptr, n), device=torch.device("cuda", device))
             self._stats_np = None
 
+    @classmethod
+    def from_shard(cls, local_prob: Problem, n_global: int, n_chains: int, rank: int, world: int, device: int = 0, _lib=None,
+                   stats_mode: str = "hist") -> "ShardedEvaluator":
+        """Build from a rank's own block of objects (e.g. loaded or generated per rank: the whole
+        matrix never has to exist in one process); states are then set with `set_local_state`."""
+        self = cls.__new__(cls)
+        self.N, self.rank, self.world, self.n_chains = int(n_global), rank, world, n_chains
+        self.lo, self.hi = 0, local_prob.N
+        self.local = local_prob
+        self.ctx = DeviceContext(local_prob, n_chains, device=device, _lib=_lib)
+        self._host = _lib is not None
+        if stats_mode != "hist":
+            self.ctx.eval_set_mode(stats_mode)
+        ptr, n, stride, lay = self.ctx.stats_buffer()
+        self._stride, self._lay = stride, lay
+        if self._host:
+            self._stats_np = np.frombuffer((ctypes.c_int32 * n).from_address(ptr), dtype=np.int32)
+            self._stats = None
+        else:
+            import torch
+            self._stats = torch.as_tensor(_DeviceArray(ptr, n), device=torch.device("cuda", device))
+            self._stats_np = None
+        return self
+
+    def set_local_state(self, chain: int, st: ChainState):
+        """`st` covers only this rank's block of objects."""
+        self.ctx.set_state(chain, st)
+
     def configure(self, chain: int, cfg: ChainConfig):
         self.ctx.configure(chain, cfg)
 
@@ -98,16 +126,15 @@ class ShardedEvaluator:
             t = torch.from_numpy(self._stats_np).view(self.n_chains, self._stride)
         else:
             t = self._stats.view(self.n_chains, self._stride)
-        # counts and sizes are reduced; the histogram columns stay local (shard-specific pattern order)
-        if n_hist * 8 < n_counts:
-            packed = torch.cat([t[:, :n_counts], t[:, n_counts + n_hist:n_counts + n_hist + n_sizes]], dim=1).contiguous()
-            dist.all_reduce(packed, op=dist.ReduceOp.SUM)
-            t[:, :n_counts] = packed[:, :n_counts]
-            t[:, n_counts + n_hist:n_counts + n_hist + n_sizes] = packed[:, n_counts:]
+        # counts | sizes lead every state's block and are reduced in place; the histogram that
+        # follows stays local (shard-specific pattern order)
+        n_red = n_counts + n_sizes
+        if self.n_chains == 1:
+            dist.all_reduce(t[0, :n_red], op=dist.ReduceOp.SUM)
         else:
-            keep = t[:, n_counts:n_counts + n_hist].clone()
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            t[:, n_counts:n_counts + n_hist] = keep
+            packed = t[:, :n_red].contiguous()
+            dist.all_reduce(packed, op=dist.ReduceOp.SUM)
+            t[:, :n_red] = packed
         if not self._host:      # the ctx launches on its own stream: the collective must have landed
             torch.cuda.current_stream().synchronize()
 
