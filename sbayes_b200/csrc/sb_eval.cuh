@@ -19,6 +19,7 @@
 #pragma once
 #include "sb_platform.cuh"
 #include "sb_types.h"
+#include <stdlib.h>
 
 #define SB_EVAL_BLOCK 256
 #define SB_EVAL_MAXPARTS 512
@@ -479,8 +480,12 @@ static inline int sb_obs_make_plan(const SbProblem &P, int n_states, int n_sm, S
     if (fixed + 16 * per_f > budget) budget = 110 * 1024;
     if (fixed + 16 * per_f > budget) budget = 220 * 1024;
     if (fixed + 16 * per_f > budget) return -1;
-    int ft = 16;                                                                           // power of two: 4, 8, 16 or 32 lanes per row
-    while (ft < 128 && fixed + 2 * ft * per_f <= budget && ft < P.ldx) ft *= 2;
+    // 16, 32, 64 or 128 features per tile (4 .. 32 lanes per row).  Narrow tiles measured fastest on
+    // every BASELINE shape (profiles/r1s_obs_tile_sweep.txt): more CTAs and more rows per warp iteration
+    int ft = 16;
+#ifndef SB_HOSTSIM
+    if (getenv("SB_OBS_FT")) { int v = atoi(getenv("SB_OBS_FT")); if ((v == 16 || v == 32 || v == 64 || v == 128) && fixed + (size_t)v * per_f <= 220 * 1024) ft = v; }   // tuning knob
+#endif
     int n_ftiles = (P.ldx + ft - 1) / ft;
     long long want = 4LL * n_sm, base = (long long)n_states * n_ftiles;
     long long n_oblk = (want + base - 1) / base;

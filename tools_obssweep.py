@@ -1,0 +1,8 @@
+"""Observation-likelihood kernel time against the feature-tile width (tuning helper)."""
+import os, subprocess, sys
+for ft in (16, 32, 64, 128):
+    env = dict(os.environ, SB_OBS_FT=str(ft))
+    out = subprocess.run([sys.executable, "tools_scale.py", sys.argv[1], "--no-steps"], env=env, capture_output=True, text=True).stdout
+    for l in out.splitlines():
+        if "obs_loglik" in l:
+            print(f"ft {ft:3d}  {l}", flush=True)
