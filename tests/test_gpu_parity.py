@@ -129,3 +129,37 @@ def test_philox_lockstep_six_components():
     cfgs = [ChainConfig(seed=7), ChainConfig(temperature=1.15, prior_temperature=1.05, seed=8)]
     st0 = [synth.initial_state(prob, seed=40 + i, objects_per_cluster=4) for i in range(2)]
     parity.philox_lockstep(prob, st0, cfgs, 200, team=2)
+
+
+@pytest.mark.parametrize("team", [1, 0])
+def test_philox_lockstep_c4_shape(team):
+    """BASELINE config 4 shape (5000 x 200 x 6, K=5, 20 families): the replicas do not fit in
+    shared memory (private HBM slices) and, at team 1, one CTA walks a whole chain -- the
+    placement the 128-chains-per-GPU replicate runs use.  Lockstep with the fp64 oracle."""
+    prob, _ = synth.make_problem(N=5000, F=200, S=6, K=5, n_fam=20, seed=4)
+    cfgs = [ChainConfig(seed=300), ChainConfig(temperature=1.1, prior_temperature=1.05, seed=301)]
+    st0 = [synth.initial_state(prob, seed=100 + c) for c in range(2)]
+    parity.philox_lockstep(prob, st0, cfgs, 40, team=team)
+
+
+def test_replicate_chains_are_independent_of_batching():
+    """independent replicates (config 4): a chain's trajectory depends on its seed only, not on
+    how many other chains share the launch or on the team size"""
+    prob, _ = synth.make_problem(N=300, F=40, S=5, K=4, n_fam=6, seed=8)
+    sts = [synth.initial_state(prob, seed=c) for c in range(6)]
+
+    def run(chains, team):
+        ctx = DeviceContext(prob, len(chains), team=team)
+        try:
+            for i, c in enumerate(chains):
+                ctx.configure(i, ChainConfig(seed=1000 + c))
+                ctx.set_state(i, sts[c])
+            ctx.run(300)
+            return {c: (ctx.get_state(i), ctx.posterior(i)) for i, c in enumerate(chains)}
+        finally:
+            ctx.close()
+    a, b = run([0, 1, 2, 3, 4, 5], 1), run([4, 2], 4)
+    for c in (4, 2):
+        assert np.array_equal(a[c][0].cluster_of, b[c][0].cluster_of) and np.array_equal(a[c][0].src, b[c][0].src)
+        assert np.array_equal(a[c][0].counts, b[c][0].counts) and np.array_equal(a[c][0].W, b[c][0].W)
+        assert parity.rel(a[c][1]["ll"], b[c][1]["ll"]) < 1e-12 and parity.rel(a[c][1]["prior"], b[c][1]["prior"]) < 1e-12

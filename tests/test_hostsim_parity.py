@@ -57,3 +57,25 @@ def test_emulated_lockstep_six_components(lib):
     cfgs = [ChainConfig(seed=7), ChainConfig(temperature=1.15, prior_temperature=1.05, seed=8)]
     st0 = [synth.initial_state(prob, seed=40 + i, objects_per_cluster=4) for i in range(2)]
     parity.philox_lockstep(prob, st0, cfgs, 100, lib=lib, team=2)
+
+
+@pytest.fixture
+def env():
+    saved = dict(os.environ)
+    yield os.environ
+    os.environ.clear()
+    os.environ.update(saved)
+
+
+@pytest.mark.parametrize("smem,no_tables", [(24 * 1024, False), (24 * 1024, True), (200 * 1024, True)])
+def test_emulated_lockstep_replicas_in_hbm_slice(lib, env, smem, no_tables):
+    """the placement the large shapes (BASELINE config 4 / 5) run with: the group-indexed replica
+    does not fit in shared memory and lives in the CTA's private HBM slice; with and without the
+    per-combo pass tables"""
+    env["SB_HOSTSIM_SMEM"] = str(smem)
+    if no_tables:
+        env["SB_NO_TABLES"] = "1"
+    prob, _ = synth.make_problem(N=60, F=14, S=4, K=3, n_fam=4, seed=17, jagged_states=True, max_size=25)
+    cfgs = [ChainConfig(seed=200), ChainConfig(temperature=1.25, prior_temperature=1.1, seed=201)]
+    st0 = [synth.initial_state(prob, seed=15 + i, objects_per_cluster=6) for i in range(2)]
+    parity.philox_lockstep(prob, st0, cfgs, 150, lib=lib, team=2)
