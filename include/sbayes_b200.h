@@ -72,11 +72,17 @@ typedef struct sb_problem_desc {
     const int32_t *adj_indices;
 } sb_problem_desc;
 
+/* sb_chain_cfg.flags.  SB_CFG_PROPOSE_ONLY: the operator API of the reference
+ * (Operator.function(sample) -> (sample', log_q, log_q_back), sbayes/sampling/operators.py:269-276):
+ * every proposal the operator does not reject itself is committed without the Metropolis-Hastings
+ * test, so one step with a one-hot op_weights vector and a step record is one operator call. */
+#define SB_CFG_PROPOSE_ONLY 1
+
 /* Per-chain run parameters. */
 typedef struct sb_chain_cfg {
     double temperature, prior_temperature;
     int32_t sample_from_prior;
-    int32_t reserved;
+    int32_t flags;                /* SB_CFG_* */
     double op_weights[SB_N_OPS];  /* normalised operator probabilities               */
     double p_grow;
     uint64_t seed;                /* Philox key of the chain                         */

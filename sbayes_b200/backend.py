@@ -38,7 +38,7 @@ class _ProblemDesc(C.Structure):
 class _ChainCfg(C.Structure):
     _fields_ = [
         ("temperature", C.c_double), ("prior_temperature", C.c_double), ("sample_from_prior", C.c_int32),
-        ("reserved", C.c_int32), ("op_weights", C.c_double * N_OPS), ("p_grow", C.c_double), ("seed", C.c_uint64),
+        ("flags", C.c_int32), ("op_weights", C.c_double * N_OPS), ("p_grow", C.c_double), ("seed", C.c_uint64),
     ]
 
 
@@ -184,6 +184,7 @@ class DeviceContext:
         c = _ChainCfg()
         c.temperature, c.prior_temperature = cfg.temperature, cfg.prior_temperature
         c.sample_from_prior = int(cfg.sample_from_prior)
+        c.flags = 1 if getattr(cfg, "propose_only", False) else 0
         w = cfg.op_weight_vector(self.prob.K)
         for i in range(N_OPS):
             c.op_weights[i] = float(w[i])

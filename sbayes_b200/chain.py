@@ -391,6 +391,67 @@ class DeviceModel:
         self.ctx.close()
 
 
+class _OperatorEngine:
+    """One device context that executes single operator calls (boundary B2, operator API)."""
+
+    def __init__(self, model, data, temperature, prior_temperature, sample_from_prior, p_grow, device, seed, _lib):
+        self.model, self.data = model, data
+        self.prob = refbridge.problem_from_reference(data, model)
+        self.ctx = DeviceContext(self.prob, 1, device=device, _lib=_lib)
+        self.base = dict(temperature=float(temperature), prior_temperature=float(prior_temperature),
+                         sample_from_prior=bool(sample_from_prior), seed=int(seed), p_grow=float(p_grow))
+        self.calls = 0
+        self.last_record = None
+
+    def propose(self, op_index: int, sample):
+        """Operator.function(sample) (sbayes/sampling/operators.py:269-276): one step of operator
+        `op_index` with the Metropolis-Hastings test switched off (SB_CFG_PROPOSE_ONLY)."""
+        w = np.zeros(N_OPS)
+        w[op_index] = 1.0
+        cfg = _ExplicitWeights(weights=w, **self.base)
+        cfg.propose_only = True
+        self.ctx.configure(0, cfg)
+        self.ctx.set_state(0, refbridge.state_from_sample(self.prob, sample), i_step=self.calls)   # draws of step calls + 1
+        self.calls += 1
+        rec = self.ctx.run(1, records=True)[0, 0]
+        self.last_record = rec
+        lq, lqb = float(rec["log_q"]), float(rec["log_q_back"])
+        if not rec["changed"] or not rec["accept"]:
+            return sample, 0, -np.inf                 # Q_REJECT, Q_BACK_REJECT (operators.py:245-247)
+        st = self.ctx.get_state(0)
+        new = refbridge.sample_from_state(self.prob, self.model, self.data, st, type(sample), i_step=int(sample.i_step),
+                                          chain=getattr(sample, "chain", 0))
+        return new, lq, lqb
+
+
+def device_operator_schedule(operators, model, data, temperature: float = 1.0, prior_temperature: float = 1.0,
+                             sample_from_prior: bool = False, *, device: int = 0, seed: typ.Optional[int] = None, _lib=None) -> dict:
+    """`get_operator_schedule` (sbayes/sampling/operators.py:28-209) with every operator's proposal
+    executed on the device.  The returned objects ARE the reference's operator objects (same
+    classes, weights, statistics API, parameter strings); only `_propose` is rebound, so
+    `op.function(sample) -> (sample', log_q, log_q_back)` keeps the reference's contract including
+    the sentinels (Q_GIBBS / Q_BACK_GIBBS for the Gibbs operators, Q_REJECT / Q_BACK_REJECT when
+    the operator rejects by itself)."""
+    from sbayes.sampling.operators import get_operator_schedule
+    ops = get_operator_schedule(operators_config=operators, model=model, data=data, temperature=temperature,
+                                prior_temperature=prior_temperature, sample_from_prior=sample_from_prior)
+    missing = [n for n in OP_NAMES if n not in ops]
+    extra = [n for n in ops if n not in OP_NAMES]
+    if missing or extra:
+        raise SbError(f"operator schedule differs from the one the device implements: missing {missing}, unknown {extra}")
+    if seed is None:
+        seed = int.from_bytes(os.urandom(8), "little") >> 1
+    engine = _OperatorEngine(model, data, temperature, prior_temperature, sample_from_prior,
+                             getattr(ops["cluster_gibbsish_geo"], "p_grow", 0.5), device, seed, _lib)
+    for i, name in enumerate(OP_NAMES):
+        op = ops[name]
+
+        def _propose(self, sample, _i=i, **kwargs):
+            return engine.propose(_i, sample)
+        op.__class__ = type(type(op).__name__, (type(op),), {"_propose": _propose, "device_engine": engine})
+    return ops
+
+
 class _ExplicitWeights(ChainConfig):
     """ChainConfig whose operator weights come from the reference's schedule objects."""
 

@@ -244,6 +244,7 @@ struct Run {
     Draws D;
     double T, Tp, invT, invTp, p_grow;
     int sfp;
+    int propose_only;            // operator API: commit every proposal the operator does not reject itself (no MH test)
     int tsize, rank, par, vpar, spar, use_cluster, hcur;
     unsigned long long epoch;
     int nd;            // number of dirty rows of the open proposal
@@ -1814,6 +1815,7 @@ SB_DEV void mcmc_step(Run &R, sb_step_record *rec) {
     bool accept; double ratio = NAN, log_u = NAN;
     if (!touched || lqb == -SB_INF) accept = false;
     else if (lq == -SB_INF) accept = true;
+    else if (R.propose_only) accept = true;
     else {
         double prior_old = R.pr_size + R.pr_geo + R.pr_w + R.pr_src;
         ratio = (ll_new / R.T + prior_new / R.Tp) - (R.ll / R.T + prior_old / R.Tp) - (lq - lqb);
@@ -1950,7 +1952,7 @@ SB_KERNEL_BIG sb_run_kernel(const SB_GRID_CONSTANT SbLaunch L) {
         sb_cta_sync();
         const sb_chain_cfg &cfg = slot->cfg;
         R.T = cfg.temperature; R.Tp = cfg.prior_temperature; R.invT = 1.0 / R.T; R.invTp = 1.0 / R.Tp;
-        R.p_grow = cfg.p_grow; R.sfp = cfg.sample_from_prior;
+        R.p_grow = cfg.p_grow; R.sfp = cfg.sample_from_prior; R.propose_only = cfg.flags & SB_CFG_PROPOSE_ONLY;
         R.D.k0 = (uint32_t)(cfg.seed & 0xFFFFFFFFull); R.D.k1 = (uint32_t)(cfg.seed >> 32);
         R.D.tv = L.tape.vals; R.D.toff = nullptr; R.D.tlen = nullptr; R.D.wide_n = 0; R.D.step = 0;
         R.err = 0;

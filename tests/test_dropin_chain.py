@@ -191,3 +191,50 @@ def test_install_rebinds_mcmc_too():
     finally:
         r.mcmc_chain.MCMCChain = orig[0]; r.mcmc_setup.MCMCChain = orig[0]
         mm.MCMC = orig[1]; r.mcmc_setup.MCMC = orig[1]
+
+
+def test_device_operator_api_matches_oracle_proposals():
+    """Boundary B2 (operator API): `op.function(sample) -> (sample', log_q, log_q_back)` of every
+    scheduled operator, executed on the device, against the oracle's proposal on the same draws."""
+    from oracle import operators as O
+    from sbayes_b200.chain import device_operator_schedule
+    from sbayes_b200.packed import OP_NAMES
+    r = H.ref()
+    prob0, data, model = _reference_problem()
+    opcfg = r.config.OperatorsConfig(clusters=70, weights=10, source=20)
+    ops = device_operator_schedule(opcfg, model, data, seed=4242, _lib=_lib())
+    ref_ops = r.operators.get_operator_schedule(operators_config=opcfg, model=model, data=data)
+    engine = next(iter(ops.values())).device_engine
+    prob = engine.prob
+    st = synth.initial_state(prob, seed=3, objects_per_cluster=6)
+    st.counts = M.rebuild_counts(prob, st)
+    sample = H.sample_from_state(prob, model, data, st)
+    n_changed = 0
+    for rnd in range(3):
+        for i, name in enumerate(OP_NAMES):
+            op = ops[name]
+            assert type(op).__name__ == type(ref_ops[name]).__name__ and op.weight == ref_ops[name].weight
+            assert op.get_parameters_string() == ref_ops[name].get_parameters_string()
+            step = engine.calls + 1
+            new, lq, lqb = op.function(sample)
+            draws = PhiloxDraws(4242)
+            draws.begin_step(step)
+            cur = H.state_from_sample(prob, sample)
+            prop = O.propose(prob, cur, ChainConfig(seed=4242), draws, i)
+            if not prop.changed or prop.log_q_back == O.NEG_INF:
+                assert new is sample and lq == op.Q_REJECT and lqb == op.Q_BACK_REJECT
+                continue
+            n_changed += 1
+            got = H.state_from_sample(prob, new)
+            assert np.array_equal(got.cluster_of, prop.state.cluster_of) and np.array_equal(got.src, prop.state.src)
+            assert np.array_equal(got.W, prop.state.W) and np.array_equal(got.counts, prop.state.counts)
+            if prop.log_q == O.NEG_INF:
+                assert lq == op.Q_GIBBS and lqb == op.Q_BACK_GIBBS
+            else:
+                assert abs(lq - prop.log_q) <= 1e-10 * max(1, abs(prop.log_q))
+                assert abs(lqb - prop.log_q_back) <= 1e-10 * max(1, abs(prop.log_q_back))
+            # the proposal is a valid reference Sample
+            assert abs(model.likelihood(new, caching=False) - M.log_likelihood(prob, prop.state)) < 5e-7 * abs(M.log_likelihood(prob, prop.state))
+            sample = new
+    assert n_changed >= 15
+    engine.ctx.close()

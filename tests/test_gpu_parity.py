@@ -163,3 +163,49 @@ def test_replicate_chains_are_independent_of_batching():
         assert np.array_equal(a[c][0].cluster_of, b[c][0].cluster_of) and np.array_equal(a[c][0].src, b[c][0].src)
         assert np.array_equal(a[c][0].counts, b[c][0].counts) and np.array_equal(a[c][0].W, b[c][0].W)
         assert parity.rel(a[c][1]["ll"], b[c][1]["ll"]) < 1e-12 and parity.rel(a[c][1]["prior"], b[c][1]["prior"]) < 1e-12
+
+
+def test_propose_only_operator_calls():
+    """SB_CFG_PROPOSE_ONLY (operator API of the reference, operators.py:269-276): one step of a
+    forced operator commits its proposal without the MH test; state, log_q and log_q_back equal
+    the oracle's proposal on the same draws."""
+    from dataclasses import replace
+    from oracle import operators as O
+    from oracle.draws import PhiloxDraws
+    from sbayes_b200.packed import N_OPS
+
+    class OneHot(ChainConfig):
+        def op_weight_vector(self, n_clusters):
+            return self._w
+    prob, _ = synth.make_problem(N=120, F=24, S=4, K=3, n_fam=4, seed=7, max_size=40)
+    st = synth.initial_state(prob, seed=5, objects_per_cluster=8)
+    st.counts = M.rebuild_counts(prob, st)
+    ctx = DeviceContext(prob, 1, team=2)
+    try:
+        step, changed = 0, 0
+        for rnd in range(3):
+            for op in range(N_OPS):
+                cfg = OneHot(seed=99)
+                cfg._w = np.eye(N_OPS)[op]
+                cfg.propose_only = True
+                ctx.configure(0, cfg)
+                ctx.set_state(0, st, i_step=step)
+                rec = ctx.run(1, records=True)[0, 0]
+                step += 1
+                draws = PhiloxDraws(99)
+                draws.begin_step(step)
+                prop = O.propose(prob, st, ChainConfig(seed=99), draws, op)
+                assert rec["op"] == op
+                if not prop.changed or prop.log_q_back == O.NEG_INF:
+                    assert not rec["accept"]
+                    continue
+                assert rec["accept"], "propose-only must commit every proposal the operator does not reject"
+                assert parity.rel(prop.log_q, rec["log_q"]) < 1e-10 and parity.rel(prop.log_q_back, rec["log_q_back"]) < 1e-10
+                got = ctx.get_state(0)
+                assert np.array_equal(got.cluster_of, prop.state.cluster_of) and np.array_equal(got.src, prop.state.src)
+                assert np.array_equal(got.counts, prop.state.counts) and np.array_equal(got.W, prop.state.W)
+                st = got
+                changed += 1
+        assert changed >= 15
+    finally:
+        ctx.close()
