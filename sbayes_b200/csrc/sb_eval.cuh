@@ -487,14 +487,23 @@ static inline int sb_obs_make_plan(const SbProblem &P, int n_states, int n_sm, S
     if (getenv("SB_OBS_FT")) { int v = atoi(getenv("SB_OBS_FT")); if ((v == 16 || v == 32 || v == 64 || v == 128) && fixed + (size_t)v * per_f <= 220 * 1024) ft = v; }   // tuning knob
 #endif
     int n_ftiles = (P.ldx + ft - 1) / ft;
-    long long want = 4LL * n_sm, base = (long long)n_states * n_ftiles;
-    long long n_oblk = (want + base - 1) / base;
+    // object blocks per (state, tile): every CTA builds the tile's tables first (about ten
+    // operations per table entry), so minimise  waves * (observations per CTA + table cost)
+    const size_t smem = fixed + (size_t)ft * per_f;
+    long long per_sm = (long long)((227 * 1024) / (smem + 1024)); if (per_sm > 3) per_sm = 3; if (per_sm < 1) per_sm = 1;
+    const long long slots = per_sm * n_sm, base = (long long)n_states * n_ftiles;
     long long max_blk = P.N / 128; if (max_blk < 1) max_blk = 1;
-    if (n_oblk > max_blk) n_oblk = max_blk;
+    if (max_blk > 4096) max_blk = 4096;
+    long long n_oblk = 1; double best = -1.0;
+    for (long long n = 1; n <= max_blk; n++) {
+        const long long waves = (base * n + slots - 1) / slots;
+        const double cost = (double)waves * ((double)((P.N + n - 1) / n) * ft + 10.0 * (double)ft * P.G_tot * P.S);
+        if (best < 0.0 || cost < best) { best = cost; n_oblk = n; }
+    }
     int rows = (int)((P.N + n_oblk - 1) / n_oblk);
     n_oblk = (P.N + rows - 1) / rows;
     pl->ft = ft; pl->n_ftiles = n_ftiles; pl->n_oblk = (int)n_oblk; pl->rows_per_blk = rows;
-    pl->smem = (unsigned)(fixed + (size_t)ft * per_f);
+    pl->smem = (unsigned)smem;
     return 0;
 }
 
@@ -676,18 +685,26 @@ static inline int sb_eval_make_plan(const SbProblem &P, int n_states, int n_sm, 
     int n_ftiles = (P.ldx + ft_max - 1) / ft_max;
     int ft = ((P.ldx + n_ftiles - 1) / n_ftiles + 15) / 16 * 16;
     n_ftiles = (P.ldx + ft - 1) / ft;
-    long long want = 4LL * n_sm;
-    long long base = (long long)n_states * n_ftiles;
-    long long n_oblk = (want + base - 1) / base;
+    // object blocks per (state, tile): every CTA pays for zeroing and flushing its bins, so the
+    // split that minimises  waves * (observations per CTA + 4 * bins per CTA)  is taken
+    // (waves = CTAs over the resident slots: at most 3 CTAs per SM by registers)
+    const size_t smem = fixed + (size_t)ft * bins_per_f * 4;
+    long long per_sm = (long long)((227 * 1024) / (smem + 1024)); if (per_sm > 3) per_sm = 3; if (per_sm < 1) per_sm = 1;
+    const long long slots = per_sm * n_sm, base = (long long)n_states * n_ftiles;
     long long max_blk = P.N / 128; if (max_blk < 1) max_blk = 1;         // at least 4 warps with an object group
-    if (n_oblk > max_blk) n_oblk = max_blk;
-    if (n_oblk < 1) n_oblk = 1;
+    if (max_blk > 4096) max_blk = 4096;
+    long long n_oblk = 1; double best = -1.0;
+    for (long long n = 1; n <= max_blk; n++) {
+        const long long waves = (base * n + slots - 1) / slots;
+        const double cost = (double)waves * ((double)((P.N + n - 1) / n) * ft + 4.0 * (double)ft * bins_per_f);
+        if (best < 0.0 || cost < best) { best = cost; n_oblk = n; }
+    }
     int rows = (int)((P.N + n_oblk - 1) / n_oblk);
     n_oblk = (P.N + rows - 1) / rows;
     pl->ft = ft; pl->n_ftiles = n_ftiles; pl->n_oblk = (int)n_oblk; pl->rows_per_blk = rows;
     long long items = (long long)P.G_tot * P.F + (long long)P.n_pat * 2 * P.F + P.F;
     long long parts = (items + 511) / 512;               // two rows per thread: the terms are lgamma-latency bound
     pl->n_parts = (int)(parts < 1 ? 1 : (parts > SB_EVAL_MAXPARTS ? SB_EVAL_MAXPARTS : parts));
-    pl->smem = (unsigned)(fixed + (size_t)ft * bins_per_f * 4);
+    pl->smem = (unsigned)smem;
     return 0;
 }
