@@ -1544,7 +1544,10 @@ SB_DEV Prop op_gibbs_source(Run &R, bool groups_mode) {
             if (sb_tid() < M) R.c->slist[sb_tid()] = popl[sb_tid()];
         } else {
             M = kmax;
-            // uniform k-subset: Floyd's algorithm over ranks, then sort (oracle/draws.py:subset_of)
+            // uniform k-subset: Floyd's algorithm over ranks, then sort (oracle/draws.py:subset_of);
+            // the M Philox draws are taken by M threads, thread 0 only runs the sequential part
+            if (!R.D.tv && sb_tid() < M) R.c->sint[sb_tid()] = draw_index(R.D, SITE_SUBSET, (uint32_t)(pop - M + sb_tid()), pop - M + sb_tid() + 1);
+            sb_cta_sync();
             if (sb_tid() == 0) {
                 int *ch = R.c->slist;
                 if (R.D.tv) {
@@ -1552,7 +1555,7 @@ SB_DEV Prop op_gibbs_source(Run &R, bool groups_mode) {
                 } else {
                     int n = 0;
                     for (int j = pop - M; j < pop; j++) {
-                        int t = draw_index(R.D, SITE_SUBSET, (uint32_t)j, j + 1);
+                        int t = R.c->sint[j - (pop - M)];
                         bool in = false;
                         for (int q = 0; q < n; q++) in |= ch[q] == t;
                         ch[n++] = in ? j : t;
@@ -1571,9 +1574,12 @@ SB_DEV Prop op_gibbs_source(Run &R, bool groups_mode) {
     PH(R, 14);
     int32_t *Hc = proposal_open(R, M, S);
     PH(R, 6);
-    // --- G1: forward conditional from the committed tables, draw
+    // --- G1: forward conditional from the committed tables, draw.  The (object, feature) items are
+    // split over the team (the draws are addressed by item, the candidate sources go to the shared
+    // state in HBM); the team sum below is also the barrier that publishes them to every CTA
+    int ilo, ihi; team_range(R, (int)items, ilo, ihi);
     double acc[2] = {0.0, 0.0};
-    for (long long it = sb_tid(); it < items; it += sb_nthr()) {
+    for (long long it = ilo + sb_tid(); it < ihi; it += sb_nthr()) {
         int m = (int)(it / F), f = (int)(it % F), o = S[m];
         int x = sb_ldg(P.x + (size_t)o * P.ldx + f);
         uint8_t *sn = R.c->st.src[m_osel(R, o) ^ 1] + (size_t)o * P.ldx;
@@ -1588,9 +1594,9 @@ SB_DEV Prop op_gibbs_source(Run &R, bool groups_mode) {
         if (nw != c_old) acc[1] += lw[nw] - lw[c_old];
         sn[f] = (uint8_t)nw;
     }
-    sb_cta_sync();
+    team_sum<2>(R, acc);
     PH(R, 15);
-    // --- counts delta (after every forward read of the tables)
+    // --- counts delta on the CTA's own replica (after every forward read of the tables)
     for (long long it = sb_tid(); it < items; it += sb_nthr()) {
         int m = (int)(it / F), f = (int)(it % F), o = S[m];
         int x = sb_ldg(P.x + (size_t)o * P.ldx + f);
@@ -1604,7 +1610,7 @@ SB_DEV Prop op_gibbs_source(Run &R, bool groups_mode) {
         sb_atomic_add_i32(Hc + ((size_t)(pat * 2 + z) * F + f) * C + c_old, -1);
         sb_atomic_add_i32(Hc + ((size_t)(pat * 2 + z) * F + f) * C + nw, 1);
     }
-    block_sum<2>(R, acc);
+    sb_cta_sync();
     pr.lq = acc[0];
     pr.sp_new = R.pr_src + acc[1];
     pr.src_changed = 1;
@@ -1614,7 +1620,7 @@ SB_DEV Prop op_gibbs_source(Run &R, bool groups_mode) {
     pr.geo_new = candidate_geo(R, false);
     // --- G2: backward conditional from the new tables, evaluated at the old sources
     double bq[1] = {0.0};
-    for (long long it = sb_tid(); it < items; it += sb_nthr()) {
+    for (long long it = ilo + sb_tid(); it < ihi; it += sb_nthr()) {
         int m = (int)(it / F), f = (int)(it % F), o = S[m];
         int x = sb_ldg(P.x + (size_t)o * P.ldx + f);
         if (x == SB_NA_U8) continue;
@@ -1623,7 +1629,7 @@ SB_DEV Prop op_gibbs_source(Run &R, bool groups_mode) {
         source_posterior(R, o, f, x, k_o, pat, z, q);
         bq[0] += log(pick_c(q, C, R.c->st.src[m_osel(R, o)][(size_t)o * P.ldx + f]));
     }
-    block_sum<1>(R, bq);
+    team_sum<1>(R, bq);
     PH(R, 17);
     pr.lqb = bq[0];
     pr.need_sync = 1;
