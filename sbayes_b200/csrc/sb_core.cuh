@@ -1100,10 +1100,16 @@ SB_DEV void resample_sources(Run &R, Prop &pr, int M, const int *S, int k_new, i
     }
     sb_cta_sync();
     PH(R, 7);
-    // R2: conditional source distribution given the unchanged observations, draw
+    // R2: conditional source distribution given the unchanged observations, draw.  With many
+    // flipped objects (the wide operator) the items are split over the team: the draws are
+    // addressed by item, the candidate sources go to the shared state in HBM, and the team sum is
+    // the barrier that publishes them; a single flipped object is done by every CTA on its own
     const bool unitT = R.T == 1.0;
+    const bool split = R.tsize > 1 && items >= 4LL * sb_nthr();
+    int rlo = 0, rhi = (int)items;
+    if (split) team_range(R, (int)items, rlo, rhi);
     double acc[3] = {0.0, 0.0, 0.0};
-    for (long long it = sb_tid(); it < items; it += sb_nthr()) {
+    for (long long it = rlo + sb_tid(); it < rhi; it += sb_nthr()) {
         int m = (int)(it / F), f = (int)(it % F), o = S[m];
         int x = sb_ldg(P.x + (size_t)o * P.ldx + f);
         uint8_t *sn = R.c->st.src[m_osel(R, o) ^ 1] + (size_t)o * P.ldx;
@@ -1134,7 +1140,7 @@ SB_DEV void resample_sources(Run &R, Prop &pr, int M, const int *S, int k_new, i
         if (R.i_step == 1 && R.rank == 0) printf("R2 m=%d f=%d o=%d x=%d c_old=%d nw=%d q=%.6f %.6f %.6f qb=%.6f %.6f %.6f z=%d%d nn=%d %d\n", m, f, o, x, c_old, nw, q[0], q[1], q[2], qb[0], qb[1], qb[2], z_old, z_new, R.c->rp.nn[(size_t)k_new * F + f], R.c->rp.nn[(size_t)conf_group(R, 1, o) * F + f]);
 #endif
     }
-    sb_cta_sync();
+    if (split) team_sum<3>(R, acc); else sb_cta_sync();
     PH(R, 8);
     // R3: add the new observations; H += new
     for (long long it = sb_tid(); it < items; it += sb_nthr()) {
@@ -1147,7 +1153,7 @@ SB_DEV void resample_sources(Run &R, Prop &pr, int M, const int *S, int k_new, i
         if (g >= 0) count_add(R, g, f, x, 1);
         sb_atomic_add_i32(Hc + ((size_t)(pat * 2 + z_new) * F + f) * C + nw, 1);
     }
-    block_sum<3>(R, acc);
+    if (!split) block_sum<3>(R, acc);
     lq = acc[0]; lqb = acc[1];
     pr.sp_new = R.pr_src + acc[2];
     pr.src_changed = 1;

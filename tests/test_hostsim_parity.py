@@ -79,3 +79,23 @@ def test_emulated_lockstep_replicas_in_hbm_slice(lib, env, smem, no_tables):
     cfgs = [ChainConfig(seed=200), ChainConfig(temperature=1.25, prior_temperature=1.1, seed=201)]
     st0 = [synth.initial_state(prob, seed=15 + i, objects_per_cluster=6) for i in range(2)]
     parity.philox_lockstep(prob, st0, cfgs, 150, lib=lib, team=2)
+
+
+class _WideHeavy(ChainConfig):
+    """operator mix dominated by the wide cluster operator and the source operators (the paths
+    whose per-item work is split over the team)"""
+
+    def op_weight_vector(self, n_clusters):
+        import numpy as np
+        w = np.array([0.02, 0.02, 0.02, 0.02, 0.12, 0.4, 0.1, 0.12, 0.12, 0.06])
+        return w / w.sum()
+
+
+def test_emulated_lockstep_team_split_items(lib, env):
+    """many flipped objects x features: the source resampling of the wide operator and the source
+    Gibbs passes split their items over the team (threshold: 4 items per thread)"""
+    env["SB_HOSTSIM_BLOCK"] = "32"
+    prob, _ = synth.make_problem(N=70, F=40, S=4, K=3, n_fam=4, seed=23, max_size=30)
+    cfgs = [_WideHeavy(seed=400), _WideHeavy(temperature=1.2, prior_temperature=1.1, seed=401)]
+    st0 = [synth.initial_state(prob, seed=25 + i, objects_per_cluster=6) for i in range(2)]
+    parity.philox_lockstep(prob, st0, cfgs, 120, lib=lib, team=3)
