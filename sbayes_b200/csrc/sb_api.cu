@@ -281,7 +281,8 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
         memset(&pl, 0, sizeof(pl));
         const size_t nGF = (size_t)P.G_tot * F, nT = P.use_tables ? (size_t)P.n_combos * F * S : 1;
         size_t bytes[A_N];
-        bytes[A_TAB0] = nT * 8; bytes[A_TAB1] = nT * 8; bytes[A_WQ] = nH * 8; bytes[A_COUNTS] = nG * 4; bytes[A_NN] = nGF * 4;
+        bytes[A_TAB0] = nT * 16; bytes[A_TAB1] = 0;      // both pass tables interleaved in A_TAB0
+        bytes[A_WQ] = nH * 8; bytes[A_COUNTS] = nG * 4; bytes[A_NN] = nGF * 4;
         bytes[A_RT] = nGF * 8; bytes[A_RP] = nGF * 8; bytes[A_WP] = alias_w ? 0 : nH * 8; bytes[A_W1] = alias_w ? 0 : nH * 8; bytes[A_LW] = nH * 8;
         bytes[A_H0] = nH * 4; bytes[A_H1] = nH * 4; bytes[A_DCNT] = nG * 4; bytes[A_LLGF] = nGF * 8; bytes[A_BST] = nGF * 8;
         bytes[A_BK_LLGF] = nGF * 8; bytes[A_BK_RP] = nGF * 8; bytes[A_BK_RT] = nGF * 8;

@@ -197,7 +197,7 @@ struct Rep {
     double *bk_llgf, *bk_rP, *bk_rT;                  // backups of the dirty rows (undo)
     int32_t *H[2];                                    // [n_pat*2, F, C]; H[hcur] committed, the other one candidate
     double *w1, *wp, *wq, *lw;                        // [n_pat*2, F, C] weight tables
-    double *tab0, *tab1;                              // [n_combos, F, S] pass tables (build_tables)
+    SbD2 *tab;                                        // [n_combos, F, S] pass tables, the two of them interleaved (build_tables)
     const uint8_t *xblk;                              // the CTA's own block of observation rows, or null
     int xlo, xhi;
     double *lh, *bk_lh;                               // [G_tot] per-group log-likelihood
@@ -772,7 +772,7 @@ SB_DEV double geo_delta(Run &R, int o, int k, int view, int m_size) {
 // -----------------------------------------------------------------------------------------
 struct Marg { Prod p0, p1; double geo; int on; };
 
-// tables over combos: tab0[j,f,x] = sum_{c>=1} l_c w0_c,  tab1[j,f,x] = l_0 w1_0 + sum_{c>=1} l_c w1_c.  CTA-local.
+// tables over combos: tab[j,f,x].a = sum_{c>=1} l_c w0_c,  tab[j,f,x].b = l_0 w1_0 + sum_{c>=1} l_c w1_c.  CTA-local.
 SB_DEV void build_tables(Run &R, int k, bool wide) {
     const SbProblem &P = *R.P;
     const int F = P.F, S = P.S, C = P.C;
@@ -788,7 +788,7 @@ SB_DEV void build_tables(Run &R, int k, bool wide) {
             rC[c] = gC[c] >= 0 ? R.c->rp.rP[(size_t)gC[c] * F + f] : 0.0;
         }
         const double rk = R.c->rp.rT[(size_t)k * F + f], w10 = w1[0];
-        double *t0 = R.c->rp.tab0 + ((size_t)j * F + f) * S, *t1 = R.c->rp.tab1 + ((size_t)j * F + f) * S;
+        SbD2 *t = R.c->rp.tab + ((size_t)j * F + f) * S;
         for (int x = 0; x < S; x++) {
             double l0 = num_T(R, k, f, x) * rk;
             if (powT) l0 = pow_inv(l0, R.invT, false);
@@ -799,13 +799,13 @@ SB_DEV void build_tables(Run &R, int k, bool wide) {
                     a0 += l * w0[c]; a1 += l * w1[c];
                 }
             }
-            t0[x] = a0; t1[x] = a1;
+            SbD2 v; v.a = a0; v.b = a1; t[x] = v;
         }
     }
     sb_cta_sync();
 }
 
-// whole warp -> every lane.  TABLE: gather from tab0 / tab1 (must be built for this k / wide).
+// whole warp -> every lane.  TABLE: gather from tab (must be built for this k / wide).
 template <bool TABLE>
 SB_DEV void obj_marginals(const Run &R, int o, int k, bool wide, Prod &p0, Prod &p1) {
     const SbProblem &P = *R.P;
@@ -815,15 +815,15 @@ SB_DEV void obj_marginals(const Run &R, int o, int k, bool wide, Prod &p0, Prod 
     p0 = prod_one(); p1 = prod_one();
     if (TABLE) {
         const int j = m_combo(R, o);
-        const double *t0 = R.c->rp.tab0 + (size_t)j * F * S, *t1 = R.c->rp.tab1 + (size_t)j * F * S;
+        const SbD2 *t = R.c->rp.tab + (size_t)j * F * S;
         for (int w = sb_lane(); w < nwords; w += 32) {
             uint32_t word = xw[w];
 #pragma unroll
             for (int b = 0; b < 4; b++) {
                 int x = (word >> (8 * b)) & 0xFF;
                 if (x == SB_NA_U8) continue;
-                int e = (4 * w + b) * S + x;
-                p0.m *= t0[e]; p1.m *= t1[e];
+                const SbD2 v = t[(4 * w + b) * S + x];
+                p0.m *= v.a; p1.m *= v.b;
             }
             prod_renorm(p0); prod_renorm(p1);
         }
@@ -856,6 +856,39 @@ SB_DEV void obj_marginals(const Run &R, int o, int k, bool wide, Prod &p0, Prod 
         }
     }
     p0 = warp_prod_reduce(p0); p1 = warp_prod_reduce(p1);
+}
+
+// one lane -> one object: the same marginals from the per-combo tables without any shuffle.  Used
+// by passes with many objects per warp (large N, few CTAs per chain): 32 independent gather streams
+// per warp hide the latency of tables that live in the CTA's HBM slice.
+SB_DEV void obj_marginals_lane(const Run &R, int o, Prod &p0, Prod &p1) {
+    const SbProblem &P = *R.P;
+    const int F = P.F, S = P.S;
+    const int j = m_combo(R, o);
+    const SbD2 *t = R.c->rp.tab + (size_t)j * F * S;
+    const uint32_t *xw = (const uint32_t *)x_row(R, o);
+    const int nwords = P.ldx >> 2;             // a multiple of 4 (rows are padded to 16 bytes)
+    p0 = prod_one(); p1 = prod_one();
+    for (int w = 0; w < nwords; w += 2) {
+        // eight features per iteration, branch-free: all sixteen gathers are issued before the
+        // first multiply (a missing value reads entry 0 and contributes a factor one)
+        const uint32_t wd[2] = {xw[w], xw[w + 1]};
+        double a[8], b[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int x = (wd[i >> 2] >> (8 * (i & 3))) & 0xFF;
+            const bool na = x == SB_NA_U8;
+            const int e = na ? 0 : (4 * w + i) * S + x;
+            const SbD2 v = t[e];                  // one 16-byte gather: both tables are interleaved
+            a[i] = na ? 1.0 : v.a; b[i] = na ? 1.0 : v.b;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            p0.m *= (a[4 * h] * a[4 * h + 1]) * (a[4 * h + 2] * a[4 * h + 3]);
+            p1.m *= (b[4 * h] * b[4 * h + 1]) * (b[4 * h + 2] * b[4 * h + 3]);
+            prod_renorm(p0); prod_renorm(p1);
+        }
+    }
 }
 
 // whether a pass over about n_obj objects (split over the team) should gather from tables
@@ -1222,6 +1255,17 @@ SB_DEV void posterior_pass(Run &R, int k, int view, bool flat, bool use_geo, int
     const bool tables = !flat && pass_uses_tables(R, n_obj);
     if (tables) build_tables(R, k, false);
     PH(R, 20);
+    if (tables && !geo && hi - lo >= 32 * sb_nwarps()) {
+        // many objects per warp: a lane per object (no shuffles, 32 gather streams in flight per warp)
+        for (int o = lo + sb_tid(); o < hi; o += sb_nthr()) {
+            Marg a; a.on = sel(o) ? 1 : 0; a.geo = 0.0; a.p0 = prod_one(); a.p1 = prod_one();
+            if (a.on) obj_marginals_lane(R, o, a.p0, a.p1);
+            lane_out(o, a.on != 0, a.on ? posterior_tail(R, a, flat, geo) : 0.0);
+        }
+        sb_cta_sync();
+        PH(R, 21);
+        return;
+    }
     batch_items<Marg>(lo, hi,
         [&](int o) {
             Marg a; a.on = sel(o) ? 1 : 0; a.geo = 0.0; a.p0 = prod_one(); a.p1 = prod_one();
@@ -1330,6 +1374,23 @@ SB_DEV void wide_probs(Run &R, double *p, int k, int n_av, int view, bool use_ge
     const bool geo = use_geo && P.geo && !R.sfp;
     const bool tables = !R.sfp && pass_uses_tables(R, n_av);
     if (tables) build_tables(R, k, true);
+    auto tail = [&](int i, const Marg &a) {
+        double raw = 0.5;
+        if (!R.sfp) {
+            double m0 = exp(prod_log(a.p0) * R.invT), m1 = exp(prod_log(a.p1) * R.invT);
+            if (geo) m1 = m1 * exp(a.geo * R.invTp / SB_GEO_SCALER);
+            raw = m1 / (m0 + m1 + SB_EPS32);
+        }
+        p[i] = raw + SB_EPS32;
+    };
+    if (tables && !geo && hi - lo >= 32 * sb_nwarps()) {
+        // many objects per warp: a lane per object (see posterior_pass)
+        for (int i = lo + sb_tid(); i < hi; i += sb_nthr()) {
+            Marg a; a.on = 1; a.geo = 0.0;
+            obj_marginals_lane(R, R.c->st.list_b[i], a.p0, a.p1);
+            tail(i, a);
+        }
+    } else
     batch_items<Marg>(lo, hi,
         [&](int i) {
             Marg a; a.on = 1; a.geo = 0.0; a.p0 = prod_one(); a.p1 = prod_one();
@@ -1341,15 +1402,7 @@ SB_DEV void wide_probs(Run &R, double *p, int k, int n_av, int view, bool use_ge
             }
             return a;
         },
-        [&](int i, const Marg &a) {
-            double raw = 0.5;
-            if (!R.sfp) {
-                double m0 = exp(prod_log(a.p0) * R.invT), m1 = exp(prod_log(a.p1) * R.invT);
-                if (geo) m1 = m1 * exp(a.geo * R.invTp / SB_GEO_SCALER);
-                raw = m1 / (m0 + m1 + SB_EPS32);
-            }
-            p[i] = raw + SB_EPS32;
-        });
+        tail);
     sb_cta_sync();
     double s[1];
     s[0] = 0.0; for (int i = lo + sb_tid(); i < hi; i += sb_nthr()) s[0] += p[i];
@@ -1886,7 +1939,7 @@ SB_DEV void setup_replica(Run &R, const SbLaunch &L, char *smem, char *glob) {
     if (sb_tid() == 0) {
         auto at = [&](int a) -> char * { return pl.in_smem[a] ? smem + pl.smem_off[a] : glob + pl.glob_off[a]; };
         Rep &rp = c->rp;
-        rp.tab0 = (double *)at(A_TAB0); rp.tab1 = (double *)at(A_TAB1);
+        rp.tab = (SbD2 *)at(A_TAB0);
         rp.wq = (double *)at(A_WQ); rp.lw = (double *)at(A_LW);
         rp.wp = pl.alias_w ? rp.wq : (double *)at(A_WP); rp.w1 = pl.alias_w ? rp.wq : (double *)at(A_W1);
         c->alpha = pl.in_smem[A_ALPHA] ? (const double *)(smem + pl.smem_off[A_ALPHA]) : P.alpha;

@@ -99,3 +99,15 @@ def test_emulated_lockstep_team_split_items(lib, env):
     cfgs = [_WideHeavy(seed=400), _WideHeavy(temperature=1.2, prior_temperature=1.1, seed=401)]
     st0 = [synth.initial_state(prob, seed=25 + i, objects_per_cluster=6) for i in range(2)]
     parity.philox_lockstep(prob, st0, cfgs, 120, lib=lib, team=3)
+
+
+def test_emulated_lockstep_lane_per_object_pass(lib, env):
+    """a CTA with at least 32 objects per warp walks the posterior pass with one lane per object
+    (the large-N placement: config 4 with one CTA per chain)"""
+    env["SB_HOSTSIM_BLOCK"] = "32"
+    prob, _ = synth.make_problem(N=90, F=18, S=4, K=3, n_fam=4, seed=29, max_size=35, jagged_states=True)
+    cfgs = [ChainConfig(seed=500), _WideHeavy(temperature=1.3, prior_temperature=1.15, seed=501)]
+    st0 = [synth.initial_state(prob, seed=35 + i, objects_per_cluster=7) for i in range(2)]
+    parity.philox_lockstep(prob, st0, cfgs, 150, lib=lib, team=2)
+    env["SB_HOSTSIM_SMEM"] = str(24 * 1024)          # and with the tables in the HBM slice
+    parity.philox_lockstep(prob, st0, cfgs, 80, lib=lib, team=1)

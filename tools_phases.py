@@ -1,5 +1,5 @@
 """Per-phase cycle breakdown of the step kernel (needs a library built with SB_CFLAGS=-DSB_PHASE_PROF).
-usage: tools_phases.py <team> <steps>"""
+usage: tools_phases.py <team> <steps> [c2|c4] [chains]"""
 import ctypes as C, sys
 import numpy as np
 import bench
@@ -12,11 +12,19 @@ NAMES = {1: "op choice", 2: "grow_candidates", 20: "build_tables", 21: "pass (ba
          14: "subset", 15: "G1", 16: "G delta+sum", 17: "G2", 18: "jump fwd", 19: "jump bwd+sum", 22: "weights loop",
          23: "weight_tables", 24: "sp+wp", 29: "op tail", 30: "posterior+MH", 31: "commit/close"}
 team, nsteps = int(sys.argv[1]), int(sys.argv[2])
-prob, states = bench.make_workload(0)
-ctx = DeviceContext(prob, 4, team=team)
-for c in range(4):
-    ctx.configure(c, ChainConfig(temperature=1 + 0.05 * c, seed=c))
-    ctx.set_state(c, states[c])
+shape = sys.argv[3] if len(sys.argv) > 3 else "c2"
+if shape == "c4":      # config 4: 5000 x 200 x 6, many chains per GPU
+    from sbayes_b200 import synth
+    nch = int(sys.argv[4]) if len(sys.argv) > 4 else 128
+    prob, _ = synth.make_problem(N=5000, F=200, S=6, K=5, n_fam=20, seed=4)
+    states = [synth.initial_state(prob, seed=100 + c) for c in range(4)]
+else:
+    nch = 4
+    prob, states = bench.make_workload(0)
+ctx = DeviceContext(prob, nch, team=team)
+for c in range(nch):
+    ctx.configure(c, ChainConfig(temperature=1 + 0.05 * (c % 4) if shape == "c2" else 1.0, seed=c))
+    ctx.set_state(c, states[c % len(states)])
 ctx.run(100)
 ph, n = np.zeros((10, NPH), np.int64), np.zeros(10, np.int64)
 ctx.lib.sb_debug_phases.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
