@@ -301,6 +301,7 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
         int max_optin = 0;
         CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
         budget = (size_t)max_optin;
+        if (getenv("SB_SMEM_CAP_KB")) budget = std::min(budget, (size_t)atol(getenv("SB_SMEM_CAP_KB")) * 1024);   // tuning knob: leave room for L1
 #endif
         FixedSmem fx0 = sb_fixed_smem(P.G_tot, K, F, C, c->smem_members, 0);
         if (fx0.end + 1024 > budget) return fail(c, "problem too large for the fixed shared-memory part of the step kernel");

@@ -869,24 +869,31 @@ SB_DEV void obj_marginals_lane(const Run &R, int o, Prod &p0, Prod &p1) {
     const uint32_t *xw = (const uint32_t *)x_row(R, o);
     const int nwords = P.ldx >> 2;             // a multiple of 4 (rows are padded to 16 bytes)
     p0 = prod_one(); p1 = prod_one();
-    for (int w = 0; w < nwords; w += 2) {
-        // eight features per iteration, branch-free: all sixteen gathers are issued before the
-        // first multiply (a missing value reads entry 0 and contributes a factor one)
-        const uint32_t wd[2] = {xw[w], xw[w + 1]};
-        double a[8], b[8];
+    // sixteen features per iteration; the next 16 bytes of the row are requested before the
+    // gathers of the current ones, so one memory round trip (not two) bounds an iteration
+    uint32_t nx[4] = {xw[0], xw[1], xw[2], xw[3]};
+    for (int w = 0; w < nwords; w += 4) {
+        const uint32_t wd[4] = {nx[0], nx[1], nx[2], nx[3]};
+        if (w + 4 < nwords) { nx[0] = xw[w + 4]; nx[1] = xw[w + 5]; nx[2] = xw[w + 6]; nx[3] = xw[w + 7]; }
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int x = (wd[i >> 2] >> (8 * (i & 3))) & 0xFF;
-            const bool na = x == SB_NA_U8;
-            const int e = na ? 0 : (4 * w + i) * S + x;
-            const SbD2 v = t[e];                  // one 16-byte gather: both tables are interleaved
-            a[i] = na ? 1.0 : v.a; b[i] = na ? 1.0 : v.b;
-        }
+        for (int half = 0; half < 2; half++) {
+            // eight features, branch-free: all gathers are issued before the first multiply (a
+            // missing value reads entry 0 and contributes a factor one)
+            double a[8], b[8];
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            p0.m *= (a[4 * h] * a[4 * h + 1]) * (a[4 * h + 2] * a[4 * h + 3]);
-            p1.m *= (b[4 * h] * b[4 * h + 1]) * (b[4 * h + 2] * b[4 * h + 3]);
-            prod_renorm(p0); prod_renorm(p1);
+            for (int i = 0; i < 8; i++) {
+                const int x = (wd[2 * half + (i >> 2)] >> (8 * (i & 3))) & 0xFF;
+                const bool na = x == SB_NA_U8;
+                const int e = na ? 0 : (4 * w + 8 * half + i) * S + x;
+                const SbD2 v = t[e];                  // one 16-byte gather: both tables are interleaved
+                a[i] = na ? 1.0 : v.a; b[i] = na ? 1.0 : v.b;
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                p0.m *= (a[4 * h] * a[4 * h + 1]) * (a[4 * h + 2] * a[4 * h + 3]);
+                p1.m *= (b[4 * h] * b[4 * h + 1]) * (b[4 * h + 2] * b[4 * h + 3]);
+                prod_renorm(p0); prod_renorm(p1);
+            }
         }
     }
 }

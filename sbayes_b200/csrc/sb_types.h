@@ -90,7 +90,8 @@ struct SbShared {
 };
 
 // replica arrays that may live in shared memory (placement priority = enum order)
-enum { A_TAB0 = 0, A_TAB1, A_COUNTS, A_NN, A_RT, A_RP, A_WQ, A_ALPHA, A_MCL, A_MCOMBO, A_MOSEL, A_COMBOT, A_APPLM, A_XBLK,
+// (the small per-object lookups first: every item of every pass reads them)
+enum { A_MCL = 0, A_MCOMBO, A_MOSEL, A_COMBOT, A_APPLM, A_TAB0, A_TAB1, A_COUNTS, A_NN, A_RT, A_RP, A_WQ, A_ALPHA, A_XBLK,
        A_WP, A_W1, A_LW, A_H0, A_H1, A_DCNT, A_LLGF, A_ASUM, A_BST, A_BK_LLGF, A_BK_RP, A_BK_RT, A_N };
 
 // a pair of doubles read with one 16-byte access (the two pass tables, interleaved)
