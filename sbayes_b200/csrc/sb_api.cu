@@ -301,7 +301,12 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
         int max_optin = 0;
         CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
         budget = (size_t)max_optin;
-        if (getenv("SB_SMEM_CAP_KB")) budget = std::min(budget, (size_t)atol(getenv("SB_SMEM_CAP_KB")) * 1024);   // tuning knob: leave room for L1
+        // when the pass tables cannot live in shared memory anyway (large N x F), the passes gather
+        // them through L1: leave most of the SM's 256 KB to the cache (measured at config 4:
+        // +10 % steps/s, profiles/r2e_c4_smem_cap.txt)
+        FixedSmem fx_probe = sb_fixed_smem(P.G_tot, K, F, C, c->smem_members, 0);
+        if (P.use_tables && nT * 16 + 4096 > budget) budget = std::min(budget, std::max((size_t)64 * 1024, (size_t)fx_probe.end + 32 * 1024));
+        if (getenv("SB_SMEM_CAP_KB")) budget = std::min((size_t)max_optin, (size_t)atol(getenv("SB_SMEM_CAP_KB")) * 1024);   // tuning knob
 #endif
         FixedSmem fx0 = sb_fixed_smem(P.G_tot, K, F, C, c->smem_members, 0);
         if (fx0.end + 1024 > budget) return fail(c, "problem too large for the fixed shared-memory part of the step kernel");
