@@ -306,7 +306,25 @@ def run_ours(args):
             for c in range(nch):
                 c2.configure(c, ChainConfig(seed=c))
                 c2.set_state(c, sts[c % len(sts)])
-            full_eval.append(full_eval_line(c2, p2, nch, label, flush, peak))
+            line2 = full_eval_line(c2, p2, nch, label, flush, peak)
+            if nch > 1:
+                # MCMC steps/s of the replicate-chain configuration itself (one CTA per chain)
+                n_st = 200
+                c2.run(20)
+                st2 = torch.cuda.ExternalStream(c2.stream(), device=torch.device("cuda", local))
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                flush.fill_(1)
+                torch.cuda.synchronize()
+                ev0.record(st2)
+                c2.run_async(n_st)
+                ev1.record(st2)
+                c2.sync()
+                ms = ev0.elapsed_time(ev1)
+                algo = float(p2.N) * p2.F * nch * n_st
+                line2["steps"] = {"mcmc_steps_per_sec": nch * n_st / (ms * 1e-3), "us_per_step_and_chain": ms * 1e3 / n_st, "team_ctas": c2.info()["team"],
+                                  "roofline": {"bound": "hbm", "kernel": "sb_run_kernel", "achieved": algo / (ms * 1e-3) / 1e9, "peak": peak,
+                                               "unit": "GB/s", "frac": algo / (ms * 1e-3) / 1e9 / peak, "traffic": None}}
+            full_eval.append(line2)
             c2.close()
     barrier()
 
