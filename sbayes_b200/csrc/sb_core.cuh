@@ -1626,9 +1626,18 @@ SB_DEV Prop op_gibbs_source(Run &R, bool groups_mode) {
                         for (int q = 0; q < n; q++) in |= ch[q] == t;
                         ch[n++] = in ? j : t;
                     }
-                    if (!identity) for (int j = 0; j < M; j++) ch[j] = popl[ch[j]];
                 }
-                for (int a = 1; a < M; a++) { int v = ch[a], b = a - 1; while (b >= 0 && ch[b] > v) { ch[b + 1] = ch[b]; b--; } ch[b + 1] = v; }
+            }
+            sb_cta_sync();
+            // ranks -> object ids and the sort, by M threads: the look-ups are independent loads and
+            // the values are distinct, so every thread places its own value at its rank
+            int v = 0;
+            if (sb_tid() < M) { v = R.c->slist[sb_tid()]; if (!identity && !R.D.tv) v = popl[v]; R.c->sint[32 + sb_tid()] = v; }
+            sb_cta_sync();
+            if (sb_tid() < M) {
+                int rank = 0;
+                for (int q = 0; q < M; q++) rank += R.c->sint[32 + q] < v ? 1 : 0;
+                R.c->slist[rank] = v;
             }
         }
         sb_cta_sync();
