@@ -1262,11 +1262,12 @@ SB_DEV void posterior_pass(Run &R, int k, int view, bool flat, bool use_geo, int
     const bool tables = !flat && pass_uses_tables(R, n_obj);
     if (tables) build_tables(R, k, false);
     PH(R, 20);
-    if (tables && !geo && hi - lo >= 32 * sb_nwarps()) {
-        // many objects per warp: a lane per object (no shuffles, 32 gather streams in flight per warp)
+    if ((tables || flat) && !geo && hi - lo >= 32 * sb_nwarps()) {
+        // many objects per warp: a lane per object (no shuffles, 32 gather streams in flight per
+        // warp; for the flat proposals of the naive operators just the candidate predicate)
         for (int o = lo + sb_tid(); o < hi; o += sb_nthr()) {
             Marg a; a.on = sel(o) ? 1 : 0; a.geo = 0.0; a.p0 = prod_one(); a.p1 = prod_one();
-            if (a.on) obj_marginals_lane(R, o, a.p0, a.p1);
+            if (a.on && !flat) obj_marginals_lane(R, o, a.p0, a.p1);
             lane_out(o, a.on != 0, a.on ? posterior_tail(R, a, flat, geo) : 0.0);
         }
         sb_cta_sync();
