@@ -282,3 +282,24 @@ def test_gpu_observation_likelihood():
     check_obs(prob, [synth.initial_state(prob, seed=1000 + c) for c in range(2)])
     prob, _ = synth.make_problem(N=5000, F=200, S=6, K=5, n_fam=20, seed=4)
     check_obs(prob, [synth.initial_state(prob, seed=100)])
+
+
+def test_emulated_eval_and_obs_six_components(lib):
+    """more than four mixture components: the generic (non-packed) paths of the statistics pass
+    and of the observation-likelihood kernel"""
+    from test_hostsim_parity import _many_confounders
+    prob = _many_confounders(3)
+    assert prob.C == 6
+    sts = [synth.initial_state(prob, seed=40 + i, objects_per_cluster=4) for i in range(2)]
+    check_batch(prob, sts, lib)
+    check_obs(prob, sts, lib)
+
+
+@pytest.mark.gpu
+def test_gpu_eval_and_obs_six_components():
+    from test_hostsim_parity import _many_confounders
+    prob = _many_confounders(3)
+    sts = [synth.initial_state(prob, seed=40 + i, objects_per_cluster=4) for i in range(2)]
+    check_batch(prob, sts)
+    check_obs(prob, sts)
+    _mma_vs_hist(prob, sts)
