@@ -251,6 +251,13 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
         wlnB[f] = sl - lgamma(sa);
     }
     TRY(up(c, &P.alpha_w, aw)); TRY(up(c, &P.wlnB, wlnB));
+    {
+        const int n_tab = (int)std::min<long long>((long long)N + S + 64, 1LL << 22);
+        std::vector<double> lf(n_tab);
+        for (int i = 0; i < n_tab; i++) lf[i] = lgamma((double)i + 1.0);
+        TRY(up(c, &P.lfact, lf));
+        P.lfact_n = n_tab;
+    }
     if (P.geo) { std::vector<double> cost(d->geo_cost, d->geo_cost + (size_t)N * N); TRY(up(c, &P.cost, cost)); }
     if (d->adj_indptr) {
         std::vector<int32_t> ip(d->adj_indptr, d->adj_indptr + N + 1);

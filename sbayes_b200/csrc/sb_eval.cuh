@@ -369,13 +369,19 @@ SB_KERNEL sb_eval_terms_kernel(const SB_GRID_CONSTANT SbEvalArgs A) {
             const size_t ar = (size_t)ev_arow(P, g) * F + f;
             const int32_t *cr = st.counts + (size_t)it * S;
             const double *al = P.alpha + ar * S;
+            // lgamma(c + 1) and lgamma(n + integer) come from the log-factorial table (unit
+            // concentrations = the uniform prior, the common case); anything else is evaluated
             int n = 0; double ser = 0.0;
             for (int s = 0; s < S; s++) {
                 const int c = cr[s]; const double a = sb_ldg(al + s);
                 n += c;
-                if (a > 0.0) ser += lgamma((double)c + a);
+                if (a == 1.0 && c < P.lfact_n) ser += sb_ldg(P.lfact + c);
+                else if (a > 0.0) ser += lgamma((double)c + a);
             }
-            ll += sb_ldg(P.dcc + ar) - lgamma((double)n + sb_ldg(P.asum + ar)) + ser;
+            const double as = sb_ldg(P.asum + ar);
+            const int ai = (int)as;
+            const double lgn = ((double)ai == as && ai >= 1 && n + ai - 1 < P.lfact_n) ? sb_ldg(P.lfact + n + ai - 1) : lgamma((double)n + as);
+            ll += sb_ldg(P.dcc + ar) - lgn + ser;
         } else if (it < n_ll + n_sp) {
             // SourcePrior: sum over the histogram of log normalised weights (prior.py:596-611,
             // normalize_weights likelihood.py:171-190)

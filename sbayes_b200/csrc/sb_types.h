@@ -58,6 +58,10 @@ struct SbProblem {
     // one word per object for the streaming kernels (null unless C <= 4, G_tot < 255, n_pat < 256):
     // byte 0 = has-pattern index, bytes 1..3 = stacked group row of components 1..3 (255 = none)
     const uint32_t *obj_pack;
+    // lfact[i] = lgamma(i + 1) for i < lfact_n: with unit concentrations (uniform priors, the default)
+    // the Dirichlet-categorical terms of the evaluation are table look-ups instead of lgamma calls
+    const double *lfact;
+    int lfact_n;
 };
 
 // ---------------------------------------------------------------------------------------
