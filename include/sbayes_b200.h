@@ -30,7 +30,10 @@
  *   sb_posterior         MCMCChain._ll / _prior and Sample.last_lh / last_prior
  *                        (sbayes/sampling/mcmc_chain.py:87,108)
  *   sb_op_stats          Operator.accepts / rejects / step_times (sbayes/sampling/operators.py:278-293)
- *   sb_swap              swap_chains (sbayes/mcmc_setup.py:365-418)
+ *   sb_swap              swap_chains (sbayes/mcmc_setup.py:365-418) over the chains of one ctx
+ *   sb_swap_scalars      the same decision procedure on host scalars (no ctx): used when the
+ *                        temperature ladder spans several GPUs / processes, and to replay the
+ *                        reference's recorded pairs and uniforms (tests/golden/mc3_swap.npz)
  *   sb_counts_rebuild_mma  recalculate_feature_counts as an int8 tensor-core contraction
  *                        (sbayes/sampling/counts.py:10-52)
  */
@@ -141,12 +144,19 @@ int sb_sync(sb_ctx *ctx);
 int sb_op_stats(sb_ctx *ctx, int chain, int64_t *accepts, int64_t *rejects, int64_t *cycles /* may be NULL */);
 int sb_swap(sb_ctx *ctx, int attempts, int only_neighbours, uint64_t seed, int64_t round,
             int32_t *state_of_slot, int32_t *n_accepted);
+/* ll / prior [n]: un-tempered posterior terms of state s; temps / prior_temps [n]: the ladder (slot i);
+ * state_at_slot [n] in/out; tape_pairs [attempts,2] + tape_u [attempts] replay recorded draws (NULL: Philox
+ * stream (seed, round)); accepted_pairs [attempts,2] (may be NULL) receives the accepted (from, to) slots. */
+int sb_swap_scalars(int32_t n, const double *ll, const double *prior, const double *temps, const double *prior_temps,
+                    int32_t attempts, int32_t only_neighbours, uint64_t seed, int64_t round, const int32_t *tape_pairs,
+                    const double *tape_u, int32_t *state_at_slot, int32_t *accepted_pairs, int32_t *n_accepted);
 int sb_get_slots(sb_ctx *ctx, int32_t *state_of_slot);
 int sb_set_slots(sb_ctx *ctx, const int32_t *state_of_slot);
 int sb_counts_rebuild_mma(sb_ctx *ctx, int chain, int32_t *counts_out, float *ms);
 int sb_counts_rebuild_hist(sb_ctx *ctx, int chain, int32_t *counts_out, float *ms);
 int sb_info(const sb_ctx *ctx, int32_t *out8);     /* {device, n_chains, team, grid, block, smem, n_sm, launches} */
 uint64_t sb_stream(const sb_ctx *ctx);              /* cudaStream_t of the ctx (for event timing) */
+int64_t sb_clock_khz(const sb_ctx *ctx);            /* SM clock rate (kHz) behind the cycle counters of sb_op_stats */
 
 #ifdef __cplusplus
 }

@@ -1,8 +1,8 @@
 """Import the live sBayes reference (from /root/reference) and convert between its objects
 and the packed containers of `oracle/problem.py`.
 
-TEST INFRASTRUCTURE (see oracle/__init__.py).  Only usable where /root/reference exists
-(the build container).  Used by `tests/golden/make_golden.py` to generate the committed
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Usable where /root/reference exists (the build
+container) or where oracle/make_ref.py placed its copy (oracle/_ref, shipped to the GPU box).  Used by `tests/golden/make_golden.py` to generate the committed
 fixtures and by the optional `-m ref` tests.  Recipe: SURVEY.md Appendix B.
 """
 from __future__ import annotations
@@ -16,13 +16,31 @@ import numpy as np
 
 from . import problem as P
 
-REFERENCE_ROOT = os.environ.get("SBAYES_REFERENCE", "/root/reference")
-_STUBS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "refstubs")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_STUBS = os.path.join(_HERE, "refstubs")
 _ref = None
+
+
+def _find_reference() -> str:
+    """/root/reference in the build container; the unmodified copy made by oracle/make_ref.py
+    (git-ignored oracle/_ref, travels to the GPU box) otherwise."""
+    cands = [os.environ.get("SBAYES_REFERENCE"), "/root/reference", os.path.join(_HERE, "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "sbayes")):
+            return c
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference()
 
 
 def reference_available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "sbayes"))
+
+
+def reference_paths() -> list:
+    """sys.path entries that make `import sbayes` resolve to the reference (stubs first)."""
+    return [_STUBS, REFERENCE_ROOT]
 
 
 def ref():
@@ -59,6 +77,26 @@ def ref():
             setattr(ns, k, v)
     _ref = ns
     return ns
+
+
+def patch_network_for_stubs():
+    """With the `pyproj` stub (CRS -> None) `ComputeNetwork` uses Euclidean distances and leaves
+    `lat_lon = None` (sbayes/preprocessing.py:136-155), which the cost_based geo prior
+    dereferences (sbayes/model/prior.py:812).  Give the network an identity projection
+    (`lat_lon = locations`) so that configs with `geo: cost_based` (test/test_files/config.yaml)
+    run through `sbayes.cli.main` in this environment.  Harness-side only; idempotent."""
+    r = ref()
+    CN = r.preprocessing.ComputeNetwork
+    if getattr(CN, "_sb_patched", False):
+        return
+    orig = CN.__init__
+
+    def init(self, *a, **kw):
+        orig(self, *a, **kw)
+        if getattr(self, "lat_lon", None) is None:
+            self.lat_lon = self.locations
+    CN.__init__ = init
+    CN._sb_patched = True
 
 
 def seed_reference(seed: int):

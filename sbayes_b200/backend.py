@@ -59,7 +59,8 @@ RECORD_DTYPE = np.dtype([("op", "<i4"), ("accept", "<i4"), ("changed", "<i4"), (
 EXPORTS = ["sb_create", "sb_destroy", "sb_last_error", "sb_chain_config", "sb_set_state", "sb_get_state", "sb_eval",
            "sb_posterior", "sb_run", "sb_run_async", "sb_sync", "sb_op_stats", "sb_swap", "sb_get_slots",
            "sb_set_slots", "sb_counts_rebuild_mma", "sb_counts_rebuild_hist", "sb_info", "sb_stream",
-           "sb_eval_batch", "sb_eval_stats", "sb_eval_terms", "sb_stats_buffer", "sb_eval_set_mode", "sb_obs_loglik"]
+           "sb_eval_batch", "sb_eval_stats", "sb_eval_terms", "sb_stats_buffer", "sb_eval_set_mode", "sb_obs_loglik",
+           "sb_swap_scalars", "sb_clock_khz"]
 
 
 def _bind(lib):
@@ -79,6 +80,7 @@ def _bind(lib):
     lib.sb_sync.argtypes = [vp]
     lib.sb_op_stats.argtypes = [vp, i32, vp, vp, vp]
     lib.sb_swap.argtypes = [vp, i32, i32, u64, i64, vp, vp]
+    lib.sb_swap_scalars.argtypes = [i32, vp, vp, vp, vp, i32, i32, u64, i64, vp, vp, vp, vp, vp]
     lib.sb_get_slots.argtypes = [vp, vp]
     lib.sb_set_slots.argtypes = [vp, vp]
     lib.sb_counts_rebuild_mma.argtypes = [vp, i32, vp, vp]
@@ -86,6 +88,8 @@ def _bind(lib):
     lib.sb_info.argtypes = [vp, vp]
     lib.sb_stream.argtypes = [vp]
     lib.sb_stream.restype = u64
+    lib.sb_clock_khz.argtypes = [vp]
+    lib.sb_clock_khz.restype = i64
     lib.sb_eval_batch.argtypes = [vp, vp, vp]
     lib.sb_eval_stats.argtypes = [vp, vp]
     lib.sb_eval_terms.argtypes = [vp, i64, vp, vp]
@@ -111,6 +115,32 @@ def load():
 
 def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def swap_scalars(ll, prior, temps, prior_temps, state_at_slot, seed: int, round_: int, attempts: int = 100,
+                 only_neighbours: bool = False, tape_pairs=None, tape_u=None, _lib=None):
+    """swap_chains (sbayes/mcmc_setup.py:365-418) on host scalars through the C ABI
+    (`sb_swap_scalars`).  `state_at_slot` (list or int32 array) is updated in place; returns
+    the accepted (from, to) slot pairs."""
+    lib = _lib if _lib is not None else load()
+    n = len(state_at_slot)
+    a = lambda v: np.ascontiguousarray(v, np.float64)
+    ll, prior, temps, prior_temps = a(ll), a(prior), a(temps), a(prior_temps)
+    sas = np.ascontiguousarray(state_at_slot, np.int32).copy()
+    n_pairs = n - 1 if only_neighbours else n * (n - 1) // 2
+    attempts = min(int(attempts), n_pairs)
+    tp = None if tape_pairs is None else np.ascontiguousarray(tape_pairs, np.int32)
+    tu = None if tape_u is None else np.ascontiguousarray(tape_u, np.float64)
+    if tp is not None and (tp.shape != (attempts, 2) or tu is None or tu.shape != (attempts,)):
+        raise SbError("swap tape must hold `attempts` pairs and uniforms")
+    acc, n_acc = np.zeros((max(attempts, 1), 2), np.int32), np.zeros(1, np.int32)
+    rc = lib.sb_swap_scalars(n, _ptr(ll), _ptr(prior), _ptr(temps), _ptr(prior_temps), attempts, int(only_neighbours), int(seed),
+                             int(round_), _ptr(tp), _ptr(tu), _ptr(sas), _ptr(acc), _ptr(n_acc))
+    if rc != 0:
+        raise SbError(f"sb_swap_scalars failed ({rc})")
+    for i in range(n):
+        state_at_slot[i] = int(sas[i])
+    return [tuple(int(v) for v in p) for p in acc[:int(n_acc[0])]]
 
 
 class DeviceContext:
@@ -179,6 +209,12 @@ class DeviceContext:
 
     def stream(self) -> int:
         return int(self.lib.sb_stream(self.h))
+
+    def clock_hz(self) -> float:
+        """SM clock the per-operator cycle counters are converted with (cudaDevAttrClockRate)."""
+        if getattr(self, "_clock_hz", None) is None:
+            self._clock_hz = float(self.lib.sb_clock_khz(self.h)) * 1e3
+        return self._clock_hz
 
     def configure(self, chain: int, cfg: ChainConfig):
         c = _ChainCfg()

@@ -76,6 +76,14 @@ class MCMCChain:
         self.ctx.configure(0, self._cfg)
         self._stats0 = (np.zeros(N_OPS, np.int64), np.zeros(N_OPS, np.int64))
         self._uploaded = None          # the Sample object whose state currently sits on the device
+        # The device addresses every draw by (Philox key, step index).  The reference restarts the
+        # step index on the SAME chain object (every warm-up attempt of MCMCChainProcess.initialize_sample
+        # starts at i_step 0, and the best sample is reset to 0 before sampling, mcmc_setup.py:503-523),
+        # so the key must change whenever the step index does not continue where the last run ended:
+        # `_epoch` counts those restarts and is mixed into the key (epoch 0 = the seed itself).
+        self._epoch = 0
+        self._next_i_step = None
+        self._restart = False
 
     # ---- reference API ---------------------------------------------------------------------
     def get_operators(self, operators) -> dict:
@@ -114,6 +122,7 @@ class MCMCChain:
         loggers see the state after every step whose index is a multiple of `logging_interval`."""
         sample = initial_sample
         self._uploaded = None
+        self._rekey(int(sample.i_step))
         self._ll = self.likelihood(sample)
         self._prior = self.prior(sample)
         self.t_start = _time.time()
@@ -136,7 +145,19 @@ class MCMCChain:
                         lg.write_sample(sample)
             if crossed_screen:
                 self.print_screen_log(i + 1, sample)
+        self._next_i_step = end
         return sample
+
+    def _rekey(self, i_step: int):
+        """new Philox key when the step index restarts (see __init__)"""
+        if self._restart or (self._next_i_step is not None and i_step != self._next_i_step):
+            self._epoch += 1
+            z = (self.seed + 0x9E3779B97F4A7C15 * self._epoch) & 0xFFFFFFFFFFFFFFFF      # splitmix64
+            z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+            z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+            self._cfg.seed = (z ^ (z >> 31)) >> 1
+            self.ctx.configure(0, self._cfg)
+        self._restart = False
 
     def _download(self, template, i_step: int):
         st = self.ctx.get_state(0)
@@ -165,7 +186,7 @@ class MCMCChain:
             op.rejects += dr
             n = da + dr
             if n:   # mean device time per step of this operator since the last sync
-                op.step_times.extend([float(cyc[i]) / 1.965e9 / max(int(a[i] + r[i]), 1)] * n)
+                op.step_times.extend([float(cyc[i]) / self.ctx.clock_hz() / max(int(a[i] + r[i]), 1)] * n)
         self._stats0 = (a, r)
 
     def close_loggers(self):
@@ -182,6 +203,7 @@ class MCMCChain:
         self._ll = -np.inf
         self._prior = -np.inf
         self._uploaded = None
+        self._restart = True
 
     def close(self):
         self.ctx.close()
@@ -271,14 +293,17 @@ class MCMC:
         return s
 
     def _sync_operator_stats(self):
-        a = np.zeros(N_OPS, np.int64); r = np.zeros(N_OPS, np.int64)
+        a = np.zeros(N_OPS, np.int64); r = np.zeros(N_OPS, np.int64); cyc = np.zeros(N_OPS, np.int64)
         for c in self.chain_idx:
             ac, rc = self.ctx.op_stats(c)
-            a += ac; r += rc
+            a += ac; r += rc; cyc += self.ctx.op_cycles(c)
         for i, name in enumerate(OP_NAMES):
             op = self.callable_operators[name]
-            op.accepts += int(a[i] - self._stats0[0][i])
-            op.rejects += int(r[i] - self._stats0[1][i])
+            da, dr = int(a[i] - self._stats0[0][i]), int(r[i] - self._stats0[1][i])
+            op.accepts += da
+            op.rejects += dr
+            if da + dr:   # mean device time per step of this operator (Operator.step_times, operators.py:232-293)
+                op.step_times.extend([float(cyc[i]) / self.ctx.clock_hz() / max(int(a[i] + r[i]), 1)] * (da + dr))
         self._stats0 = (a, r)
 
     def _run(self, n: int):
@@ -333,6 +358,7 @@ class MCMC:
             i = upto + 1
             if upto % steps_per_sample == 0 or i == n_steps:
                 out = self._download(sample[0], 0, upto)
+                self._sync_operator_stats()            # OperatorStatsLogger rewrites its file at every sample
                 if upto % steps_per_sample == 0:
                     for lg in self.sample_loggers:
                         lg.write_sample(out)
@@ -463,16 +489,49 @@ class _ExplicitWeights(ChainConfig):
         return self._w
 
 
-def install():
+def install(*, seed: typ.Optional[int] = None, device: typ.Optional[int] = None, _lib=None):
     """Make the reference use the device chain: `sbayes.sampling.mcmc_chain.MCMCChain` and the
     name imported into `sbayes.mcmc_setup` (sbayes/mcmc_setup.py:25) are rebound; so are
-    `sbayes.sampling.mcmc.MCMC` and its import in `sbayes.mcmc_setup` (warm-up and non-MC3 runs)."""
+    `sbayes.sampling.mcmc.MCMC` and its import in `sbayes.mcmc_setup` (warm-up and non-MC3 runs).
+    After this call `sbayes.cli.main(config.yaml)` (sbayes/cli.py:17-44) runs unchanged with the
+    MCMC steps on the B200: `MCMCSetup.sample` builds the device `MCMC`, `MCMCSetup.sample_mc3`
+    forks one `MCMCChainProcess` per chain and each child builds a device `MCMCChain` (its own
+    context on the GPU; the parent never touches CUDA, so the fork is safe).
+
+    `seed` fixes the Philox keys (reproducible runs; the reference itself is unseeded), `device`
+    the GPU; `_lib` is for the tests of the GPU-less build container (fibre-emulator build of the
+    same device code) -- the product default is the CUDA library and nothing else."""
     import sbayes.model  # noqa: F401  (must be imported first: circular imports in the reference)
     import sbayes.sampling.mcmc_chain as mc
     import sbayes.mcmc_setup as ms
-    mc.MCMCChain = MCMCChain
-    ms.MCMCChain = MCMCChain
     import sbayes.sampling.mcmc as mm
-    mm.MCMC = MCMC
-    ms.MCMC = MCMC
-    return MCMCChain
+    defaults = dict(seed=seed, device=device, _lib=_lib)
+
+    class InstalledMCMCChain(MCMCChain):
+        def __init__(self, *a, **kw):
+            for k, v in defaults.items():
+                if v is not None:
+                    kw.setdefault(k, v)
+            if kw.get("seed") is not None:     # one stream per temperature of the ladder
+                kw["seed"] = int(kw["seed"]) + 7919 * int(round(1e6 * float(kw.get("temperature", 1.0))))
+            super().__init__(*a, **kw)
+
+    class InstalledMCMC(MCMC):
+        _instances = 0
+
+        def __init__(self, *a, **kw):
+            for k, v in defaults.items():
+                if v is not None:
+                    kw.setdefault(k, v)
+            if kw.get("seed") is not None:     # the warm-up sampler and the sampler proper must not share streams
+                kw["seed"] = int(kw["seed"]) + 1000003 * InstalledMCMC._instances
+            InstalledMCMC._instances += 1
+            super().__init__(*a, **kw)
+
+    InstalledMCMCChain.__name__ = InstalledMCMCChain.__qualname__ = "MCMCChain"
+    InstalledMCMC.__name__ = InstalledMCMC.__qualname__ = "MCMC"
+    mc.MCMCChain = InstalledMCMCChain
+    ms.MCMCChain = InstalledMCMCChain
+    mm.MCMC = InstalledMCMC
+    ms.MCMC = InstalledMCMC
+    return InstalledMCMCChain

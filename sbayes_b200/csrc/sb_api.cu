@@ -41,7 +41,7 @@ typedef cudaStream_t sb_stream_t;
 static std::string g_create_error;
 
 struct sb_ctx {
-    int device = 0, n_chains = 0, team = 1, n_teams = 1, grid = 1, block = 256, n_sm = 1, smem_members = 0;
+    int device = 0, n_chains = 0, team = 1, n_teams = 1, grid = 1, block = 256, n_sm = 1, smem_members = 0, clock_khz = 1000000;
     size_t smem = 0;
     long long launches = 0;
     SbProblem P;
@@ -150,6 +150,7 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
     CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail(c, "sbayes_b200 needs an sm_100a (B200) device");
     c->n_sm = prop.multiProcessorCount;
+    { int khz = 0; if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device) == cudaSuccess && khz > 0) c->clock_khz = khz; }
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 #else
     c->n_sm = 4;
@@ -359,6 +360,20 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
         if (want > 8 && want <= 32 && cap_per_chain >= 16) team = 16;   // a full 16-CTA cluster measured fastest (profiles/r1e_team_sweep)
     }
     if (team > capacity) team = capacity;
+#ifndef SB_HOSTSIM
+    // the capacity above came from the placement without the per-CTA block of observation rows
+    // (A_XBLK depends on the team size): re-place with the chosen team and re-query the occupancy
+    // until it is consistent, so the cooperative launch never asks for more CTAs than can be resident
+    for (int iter = 0; iter < 4; iter++) {
+        TRY(c->place_fn(team, 0));
+        CK(cudaFuncSetAttribute(c->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, c->kernel, c->block, c->smem));
+        if (per_sm < 1) return fail(c, "step kernel does not fit on an SM");
+        capacity = per_sm * c->n_sm;
+        if (team <= capacity) break;
+        team = capacity;
+    }
+#endif
     c->team = team;
     c->use_cluster = 0;
 #ifndef SB_HOSTSIM
@@ -562,8 +577,20 @@ SB_API int sb_run_async(sb_ctx *c, int64_t n_steps) {
 SB_API int sb_run(sb_ctx *c, int64_t n_steps, const sb_tape *tape, sb_step_record *records) {
     TRY(check_chain(c, 0));
     sb_tape td; memset(&td, 0, sizeof td);
-    std::vector<void *> tmp_from = c->allocs;   // tape / record buffers are released after the run
-    size_t n_keep = c->allocs.size();
+    // tape / record buffers live for this call only: released on every path out of it
+    struct TmpGuard {
+        sb_ctx *c; size_t n_keep;
+        ~TmpGuard() {
+            while (c->allocs.size() > n_keep) {
+#ifdef SB_HOSTSIM
+                free(c->allocs.back());
+#else
+                cudaFree(c->allocs.back());
+#endif
+                c->allocs.pop_back();
+            }
+        }
+    } guard{c, c->allocs.size()};
     if (tape && tape->vals) {
         double *v; int32_t *o, *l, *w;
         TRY(mk(c, &v, (size_t)std::max<int64_t>(tape->n_vals, 1))); TRY(h2d(c, v, tape->vals, sizeof(double) * tape->n_vals));
@@ -578,14 +605,6 @@ SB_API int sb_run(sb_ctx *c, int64_t n_steps, const sb_tape *tape, sb_step_recor
     int r = launch(c, n_steps, (tape && tape->vals) ? &td : nullptr, rd);
     if (!r) r = dev_sync(c);
     if (!r && rd) r = d2h(c, records, rd, sizeof(sb_step_record) * n_rec);
-    while (c->allocs.size() > n_keep) {
-#ifdef SB_HOSTSIM
-        free(c->allocs.back());
-#else
-        cudaFree(c->allocs.back());
-#endif
-        c->allocs.pop_back();
-    }
     if (r) return r;
     return check_errors(c);
 }
@@ -659,10 +678,64 @@ SB_API int sb_set_slots(sb_ctx *c, const int32_t *state_of_slot) {
     return 0;
 }
 
-// swap_chains (sbayes/mcmc_setup.py:365-418).  The states stay where they are in HBM; a
-// swap exchanges which state a temperature slot points at.  The decisions are taken on
-// the host from the per-chain scalars (48 bytes per chain), with the same Philox
-// addressing as oracle/draws.py: swap_pairs / swap_uniform (step = round).
+// swap_chains (sbayes/mcmc_setup.py:365-418) on scalars: THE swap implementation of the
+// library (sb_swap and the multi-rank ladder of sbayes_b200/mc3.py both end here).
+//   ll / prior [n]        un-tempered posterior terms of the state with index s
+//   temps / ptemps [n]    ladder: temperature and prior temperature of slot i
+//   state_at_slot [n]     in/out: which state sits at slot i; an accepted swap exchanges two entries
+// Draws: Philox stream (seed, step = round, SITE_SWAP; sub 0 = partial Fisher-Yates over the
+// candidate pairs, sub 1 = uniforms), same addressing as oracle/draws.py: swap_pairs /
+// swap_uniform; or, replaying a recording of the reference, tape_pairs [attempts, 2] (slot
+// indices in the order the reference drew them) and tape_u [attempts].
+static int swap_decide(int n, const double *ll, const double *pr, const double *temps, const double *ptemps, int attempts,
+                       int only_neighbours, uint64_t seed, int64_t round, const int32_t *tape_pairs, const double *tape_u,
+                       int32_t *state_at_slot, int32_t *accepted_pairs, int32_t *n_accepted) {
+    std::vector<std::pair<int, int>> pairs;
+    if (only_neighbours) for (int i = 0; i + 1 < n; i++) pairs.push_back({i, i + 1});
+    else for (int i = 0; i + 1 < n; i++) for (int j = i + 1; j < n; j++) pairs.push_back({i, j});
+    attempts = std::min<int>(attempts, (int)pairs.size());
+    const uint32_t k0 = (uint32_t)(seed & 0xFFFFFFFFull), k1 = (uint32_t)(seed >> 32);
+    auto uni = [&](uint32_t idx, int sub) {
+        uint32_t c1 = (uint32_t)SITE_SWAP | ((uint32_t)sub << 8);
+        Philox4 p = philox4x32_10(idx, c1, (uint32_t)((uint64_t)round & 0xFFFFFFFFull), (uint32_t)((uint64_t)round >> 32), k0, k1);
+        return u01_double(p.w[0], p.w[1]);
+    };
+    std::vector<int> idx(pairs.size());
+    for (size_t i = 0; i < idx.size(); i++) idx[i] = (int)i;
+    int acc = 0;
+    for (int a = 0; a < attempts; a++) {
+        int i0, j0;
+        if (tape_pairs) { i0 = tape_pairs[2 * a]; j0 = tape_pairs[2 * a + 1]; if (i0 < 0 || j0 < 0 || i0 >= n || j0 >= n) return -1; }
+        else {
+            int rem = (int)idx.size() - a;
+            int j = a + std::min((int)(uni((uint32_t)a, 0) * rem), rem - 1);
+            std::swap(idx[a], idx[j]);
+            i0 = pairs[idx[a]].first; j0 = pairs[idx[a]].second;
+        }
+        const int si = state_at_slot[i0], sj = state_at_slot[j0];
+        const double r = -((pr[si] - pr[sj]) * (1.0 / ptemps[i0] - 1.0 / ptemps[j0]) + (ll[si] - ll[sj]) * (1.0 / temps[i0] - 1.0 / temps[j0]));
+        const double u = tape_u ? tape_u[a] : uni((uint32_t)a, 1);
+        const double lu = u > 0 ? log(u) : -INFINITY;
+        if (lu < r) {
+            state_at_slot[i0] = sj; state_at_slot[j0] = si;
+            if (accepted_pairs) { accepted_pairs[2 * acc] = i0; accepted_pairs[2 * acc + 1] = j0; }
+            acc++;
+        }
+    }
+    if (n_accepted) *n_accepted = acc;
+    return 0;
+}
+
+SB_API int sb_swap_scalars(int32_t n, const double *ll, const double *prior, const double *temps, const double *prior_temps,
+                           int32_t attempts, int32_t only_neighbours, uint64_t seed, int64_t round, const int32_t *tape_pairs,
+                           const double *tape_u, int32_t *state_at_slot, int32_t *accepted_pairs, int32_t *n_accepted) {
+    if (n <= 0 || !ll || !prior || !temps || !prior_temps || !state_at_slot) return -1;
+    return swap_decide(n, ll, prior, temps, prior_temps, attempts, only_neighbours, seed, round, tape_pairs, tape_u,
+                       state_at_slot, accepted_pairs, n_accepted);
+}
+
+// swap of the chains of ONE ctx: the states stay where they are in HBM; a swap exchanges which
+// state a temperature slot points at.  Decisions on the host from the per-chain scalars.
 SB_API int sb_swap(sb_ctx *c, int attempts, int only_neighbours, uint64_t seed, int64_t round,
                    int32_t *state_of_slot, int32_t *n_accepted) {
     TRY(check_chain(c, 0));
@@ -670,42 +743,20 @@ SB_API int sb_swap(sb_ctx *c, int attempts, int only_neighbours, uint64_t seed, 
     const int n = c->n_chains;
     std::vector<SbSlot> slots(n);
     TRY(d2h(c, slots.data(), c->d_slots, sizeof(SbSlot) * n));
-    std::vector<double> ll(n), pr(n);
+    std::vector<double> ll(n), pr(n), T(n), Tp(n);
+    std::vector<int32_t> sas(n);
     for (int s = 0; s < n; s++) {
         double post[8];
         TRY(d2h(c, post, c->h_states[s].post, sizeof(post)));
         ll[s] = post[0]; pr[s] = post[1] + post[2] + post[3] + post[4];
+        T[s] = slots[s].cfg.temperature; Tp[s] = slots[s].cfg.prior_temperature; sas[s] = slots[s].state;
     }
-    std::vector<std::pair<int, int>> pairs;
-    if (only_neighbours) for (int i = 0; i + 1 < n; i++) pairs.push_back({i, i + 1});
-    else for (int i = 0; i + 1 < n; i++) for (int j = i + 1; j < n; j++) pairs.push_back({i, j});
-    attempts = std::min<int>(attempts, (int)pairs.size());
-    Draws D; memset(&D, 0, sizeof D);
-    D.k0 = (uint32_t)(seed & 0xFFFFFFFFull); D.k1 = (uint32_t)(seed >> 32); D.step = (unsigned long long)round;
-    auto uni = [&](uint32_t idx, int sub) {
-        uint32_t c1 = (uint32_t)SITE_SWAP | ((uint32_t)sub << 8);
-        Philox4 p = philox4x32_10(idx, c1, (uint32_t)(D.step & 0xFFFFFFFFull), (uint32_t)(D.step >> 32), D.k0, D.k1);
-        return u01_double(p.w[0], p.w[1]);
-    };
-    std::vector<int> idx(pairs.size());
-    for (size_t i = 0; i < idx.size(); i++) idx[i] = (int)i;
     int acc = 0;
-    for (int a = 0; a < attempts; a++) {
-        int rem = (int)idx.size() - a;
-        int j = a + std::min((int)(uni((uint32_t)a, 0) * rem), rem - 1);
-        std::swap(idx[a], idx[j]);
-        int i0 = pairs[idx[a]].first, j0 = pairs[idx[a]].second;
-        int si = slots[i0].state, sj = slots[j0].state;
-        double Ti = slots[i0].cfg.temperature, Tj = slots[j0].cfg.temperature;
-        double Pi = slots[i0].cfg.prior_temperature, Pj = slots[j0].cfg.prior_temperature;
-        double r = -((pr[si] - pr[sj]) * (1.0 / Pi - 1.0 / Pj) + (ll[si] - ll[sj]) * (1.0 / Ti - 1.0 / Tj));
-        double u = uni((uint32_t)a, 1);
-        double lu = u > 0 ? log(u) : -INFINITY;
-        if (lu < r) { slots[i0].state = sj; slots[j0].state = si; acc++; }
-    }
+    if (swap_decide(n, ll.data(), pr.data(), T.data(), Tp.data(), attempts, only_neighbours, seed, round, nullptr, nullptr,
+                    sas.data(), nullptr, &acc)) return fail(c, "swap failed");
     for (int i = 0; i < n; i++) {
-        TRY(h2d(c, &c->d_slots[i].state, &slots[i].state, sizeof(int)));
-        if (state_of_slot) state_of_slot[i] = slots[i].state;
+        if (sas[i] != slots[i].state) TRY(h2d(c, &c->d_slots[i].state, &sas[i], sizeof(int)));
+        if (state_of_slot) state_of_slot[i] = sas[i];
     }
     if (n_accepted) *n_accepted = acc;
     return 0;
@@ -759,6 +810,7 @@ SB_API int sb_eval_stats(sb_ctx *c, float *ms) {
 // of objects of the whole problem when this ctx holds a shard of the objects (0: not sharded)
 SB_API int sb_eval_terms(sb_ctx *c, int64_t n_global, sb_posterior_t *out, float *ms) {
     TRY(check_chain(c, 0));
+    if (!c->eplan_ok) return fail(c, "evaluation plan unavailable (the histogram bins of one 16-feature tile do not fit in shared memory)");
     SbEvalArgs A = eval_args(c, (long long)n_global);
     if (c->P.geo && n_global > 0 && n_global != c->P.N) return fail(c, "the geo prior is not supported with sharded objects");
     TRY(dev_zero(c, c->d_eticket, sizeof(unsigned) * c->n_chains));
@@ -887,6 +939,7 @@ SB_API int sb_info(const sb_ctx *c, int32_t *out8) {
 }
 
 SB_API uint64_t sb_stream(const sb_ctx *c) { return c ? (uint64_t)(uintptr_t)c->stream : 0; }
+SB_API int64_t sb_clock_khz(const sb_ctx *c) { return c ? (int64_t)c->clock_khz : 0; }
 
 // bulk count rebuild as stand-alone kernels (sb_counts.cuh): shared-memory histogram and the
 // int8 tensor-core contraction.  Both read the committed state of `chain` and return the

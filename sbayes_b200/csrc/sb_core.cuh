@@ -1176,9 +1176,6 @@ SB_DEV void resample_sources(Run &R, Prop &pr, int M, const int *S, int k_new, i
         acc[0] += log(pick_c(q, C, nw)); acc[1] += log(pick_c(qb, C, c_old));
         acc[2] += R.c->rp.lw[((size_t)(pat * 2 + z_new) * F + f) * C + nw] - R.c->rp.lw[((size_t)(pat * 2 + z_old) * F + f) * C + c_old];
         sn[f] = (uint8_t)nw;
-#ifdef SB_DEBUG_PRINT
-        if (R.i_step == 1 && R.rank == 0) printf("R2 m=%d f=%d o=%d x=%d c_old=%d nw=%d q=%.6f %.6f %.6f qb=%.6f %.6f %.6f z=%d%d nn=%d %d\n", m, f, o, x, c_old, nw, q[0], q[1], q[2], qb[0], qb[1], qb[2], z_old, z_new, R.c->rp.nn[(size_t)k_new * F + f], R.c->rp.nn[(size_t)conf_group(R, 1, o) * F + f]);
-#endif
     }
     if (split) team_sum<3>(R, acc); else sb_cta_sync();
     PH(R, 8);
@@ -1308,9 +1305,6 @@ SB_DEV Prop op_alter_cluster(Run &R, bool gibbsish, bool use_geo, int nb) {
         double ex[2] = {0.0, 0.0};
         posterior_pass(R, k, 0, flat, use_geo, size, free_now, [&](int o) { return nb == NB_EVERYWHERE ? m_cl(R, o) < 0 : R.c->st.flag_b[o] != 0; },
                        [&](int o, bool on, double post) { val[o] = on ? heat(R, post) : 0.0; if (on) ex[0] += 1.0;
-#ifdef SB_DEBUG_PRINT
-                           if (R.i_step == 1 && R.c->slot->cfg.seed == 100) printf("FWD o=%d on=%d cl=%d flag=%d warp=%d lane=%d\n", o, (int)on, m_cl(R, o), (int)R.c->st.flag_b[o], sb_warp(), sb_lane());
-#endif
                        });
         double total;
         int o = team_pick(R, val, P.N, draw_uniform(R.D, SITE_OBJECT), total, ex);
@@ -1335,9 +1329,6 @@ SB_DEV Prop op_alter_cluster(Run &R, bool gibbsish, bool use_geo, int nb) {
         double lqb_obj = log(s[1] / s[0]);
         pr.lq = lq_obj + lqs + log(R.p_grow);
         pr.lqb = lqb_obj + lqbs + log(1.0 - R.p_grow) + extra;
-#ifdef SB_DEBUG_PRINT
-        if (sb_tid() == 0 && R.rank == 0) printf("grow k=%d o=%d ncand=%g total=%g lq_obj=%g lqs=%g lqbs=%g lqb_obj=%g\n", k, o, ex[0], total, lq_obj, lqs, lqbs, lqb_obj);
-#endif
     } else {
         if (size == P.min_size) return pr;
         posterior_pass(R, k, 0, flat, use_geo, size, size, [&](int o) { return m_cl(R, o) == k; },
@@ -2056,9 +2047,10 @@ SB_KERNEL_BIG sb_run_kernel(const SB_GRID_CONSTANT SbLaunch L) {
             if (sb_tid() == 0) {
                 R.c->st.post[0] = R.ll; R.c->st.post[1] = R.pr_size; R.c->st.post[2] = R.pr_geo; R.c->st.post[3] = R.pr_w;
                 R.c->st.post[4] = R.pr_src; R.c->st.post[5] = (double)R.i_step;
-                if (R.err) slot->err = R.err;
             }
         }
+        // an error seen by ANY CTA of the team (e.g. a bad source byte in its block of objects) is reported
+        if (R.err && sb_tid() == 0) slot->err = R.err;
         team_sync(R);
     }
 }

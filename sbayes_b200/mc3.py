@@ -11,16 +11,13 @@ chains' *temperatures*, so no state ever crosses NVLink.
 """
 from __future__ import annotations
 
-import math
 from dataclasses import replace
 from typing import List, Optional
 
 import numpy as np
 
-from .backend import DeviceContext
+from .backend import DeviceContext, swap_scalars
 from .packed import Problem, ChainState, ChainConfig
-
-SITE_SWAP = 13
 
 
 def temperature_ladder(n_chains: int, dT: float, dTp: float, exponential: bool):
@@ -29,50 +26,6 @@ def temperature_ladder(n_chains: int, dT: float, dTp: float, exponential: bool):
     if exponential:
         return (1.0 + dT) ** idx, (1.0 + dTp) ** idx
     return 1.0 + dT * idx, 1.0 + dTp * idx
-
-
-# --- Philox4x32-10, the swap stream (same addressing as the device code, sb_core.cuh) -------
-def _philox(c0, c1, c2, c3, k0, k1):
-    M0, M1, MASK = 0xD2511F53, 0xCD9E8D57, 0xFFFFFFFF
-    for _ in range(10):
-        p0, p1 = M0 * c0, M1 * c2
-        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & MASK, p1 & MASK, ((p0 >> 32) ^ c3 ^ k1) & MASK, p0 & MASK
-        k0, k1 = (k0 + 0x9E3779B9) & MASK, (k1 + 0xBB67AE85) & MASK
-    return c0, c1, c2, c3
-
-
-def _swap_uniform(seed: int, round_: int, idx: int, sub: int) -> float:
-    w = _philox(idx, SITE_SWAP | (sub << 8), round_ & 0xFFFFFFFF, (round_ >> 32) & 0xFFFFFFFF,
-                seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    return ((w[0] >> 5) * 67108864.0 + (w[1] >> 6)) / 9007199254740992.0
-
-
-def swap_decisions(ll, prior, temps, prior_temps, chain_at_slot: List[int], seed: int, round_: int,
-                   attempts: int = 100, only_neighbours: bool = False):
-    """swap_chains (sbayes/mcmc_setup.py:365-418) on scalars.  `chain_at_slot[s]` is the chain
-    currently running at temperature slot s; accepted swaps are applied to it in place.
-    Deterministic in (seed, round_): every rank computes the same result."""
-    n = len(chain_at_slot)
-    if only_neighbours:
-        pairs = [(i, i + 1) for i in range(n - 1)]
-    else:
-        pairs = [(i, j) for i in range(n - 1) for j in range(i + 1, n)]
-    attempts = min(attempts, len(pairs))
-    idx = list(range(len(pairs)))
-    accepted = []
-    for a in range(attempts):
-        rem = len(idx) - a
-        j = a + min(int(_swap_uniform(seed, round_, a, 0) * rem), rem - 1)
-        idx[a], idx[j] = idx[j], idx[a]
-        i0, j0 = pairs[idx[a]]
-        ci, cj = chain_at_slot[i0], chain_at_slot[j0]
-        r = -((prior[ci] - prior[cj]) * (1.0 / prior_temps[i0] - 1.0 / prior_temps[j0])
-              + (ll[ci] - ll[cj]) * (1.0 / temps[i0] - 1.0 / temps[j0]))
-        u = _swap_uniform(seed, round_, a, 1)
-        if (math.log(u) if u > 0 else -math.inf) < r:
-            chain_at_slot[i0], chain_at_slot[j0] = cj, ci
-            accepted.append((i0, j0))
-    return accepted
 
 
 class DeviceMC3:
@@ -138,8 +91,10 @@ class DeviceMC3:
     def swap(self):
         allv = self.gather_scalars(self.local_scalars())
         self.round += 1
-        acc = swap_decisions(allv[:, 0], allv[:, 1], self.temps, self.prior_temps, self.chain_at_slot,
-                             self.swap_seed, self.round, self.attempts, self.only_neighbours)
+        # the decision procedure lives once, in the library (sb_swap_scalars); every rank calls it
+        # on the same gathered scalars and the same Philox stream -> the same decisions everywhere
+        acc = swap_scalars(allv[:, 0], allv[:, 1], self.temps, self.prior_temps, self.chain_at_slot,
+                           self.swap_seed, self.round, self.attempts, self.only_neighbours, _lib=self.ctx.lib)
         for i, j in acc:
             self.swap_matrix[i, j] += 1
         if acc:

@@ -26,4 +26,4 @@ def pytest_collection_modifyitems(config, items):
 
 
 def golden_cases():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith("obs_lik_"))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith(("obs_lik_", "mc3_swap")))

@@ -67,41 +67,66 @@ def replay_golden(case: str, lib=None, team: int = 1, n_steps=None):
     return n
 
 
-def philox_lockstep(prob, st0, cfgs, n_steps, lib=None, team: int = 1, tol=TOL_ORACLE):
+def oracle_trajectory(args):
+    """One oracle chain on its Philox stream: per-step records and the final state.  A plain
+    function of picklable arguments, so long runs can be spread over host processes."""
+    prob, cfg, st0, n_steps = args
+    s = st0.copy()
+    s.counts = None
+    oc = CH.OracleChain(prob, cfg, s, draws=PhiloxDraws(cfg.seed))
+    recs = []
+    for _ in range(n_steps):
+        o = oc.step()
+        recs.append((o.op, bool(o.accept), o.log_q, o.log_q_back, o.ll_new, o.prior_new, o.mh_ratio, o.log_u))
+    return dict(recs=recs, state=oc.state, ll=oc.ll, prior=oc.prior, accepts=oc.accepts, rejects=oc.rejects)
+
+
+def oracle_trajectories(jobs, procs: int = 1):
+    """`jobs` = [(prob, cfg, st0, n_steps)]; with procs > 1 the chains run in forked workers
+    (numpy only: the children never touch CUDA)."""
+    if procs <= 1 or len(jobs) <= 1:
+        return [oracle_trajectory(j) for j in jobs]
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(min(procs, len(jobs))) as pool:
+        return pool.map(oracle_trajectory, jobs, chunksize=1)
+
+
+def compare_with_trajectories(ctx, rec, trajs, tol=TOL_ORACLE):
+    """device records / final states of every chain of `ctx` against oracle trajectories"""
+    near_ties = 0
+    for c, tr in enumerate(trajs):
+        for i, (op, acc, lq, lqb, ll_new, pr_new, ratio, log_u) in enumerate(tr["recs"]):
+            r = rec[c, i]
+            assert r["op"] == op, f"chain {c} step {i}: operator {r['op']} vs {op}"
+            if np.isfinite(ratio) and abs(log_u - ratio) < 1e-9:
+                near_ties += 1
+            assert bool(r["accept"]) == acc, f"chain {c} step {i} op {op}: accept"
+            assert rel(lq, r["log_q"]) < tol, f"chain {c} step {i} op {op}: log_q {lq} {r['log_q']}"
+            assert rel(lqb, r["log_q_back"]) < tol, f"chain {c} step {i} op {op}: log_q_back"
+            assert rel(ll_new, r["ll_new"]) < tol, f"chain {c} step {i} op {op}: ll"
+            assert rel(pr_new, r["prior_new"]) < tol, f"chain {c} step {i} op {op}: prior"
+        fin = ctx.get_state(c)
+        assert np.array_equal(fin.cluster_of, tr["state"].cluster_of)
+        assert np.array_equal(fin.src, tr["state"].src)
+        assert np.array_equal(fin.counts, tr["state"].counts)
+        assert np.array_equal(fin.W, tr["state"].W)
+        post = ctx.posterior(c)
+        assert rel(tr["ll"], post["ll"]) < tol and rel(tr["prior"], post["prior"]) < tol
+        a, rj = ctx.op_stats(c)
+        assert np.array_equal(a, tr["accepts"]) and np.array_equal(rj, tr["rejects"])
+    return near_ties
+
+
+def philox_lockstep(prob, st0, cfgs, n_steps, lib=None, team: int = 1, tol=TOL_ORACLE, procs: int = 1):
     """Device chains and oracle chains on the same Philox streams: identical operator
     choices, accept decisions and states; fp64 values within `tol` relative."""
     ctx = DeviceContext(prob, len(cfgs), team=team, _lib=lib)
     try:
-        ocs = []
         for c, cfg in enumerate(cfgs):
             ctx.configure(c, cfg)
             ctx.set_state(c, st0[c])
-            s = st0[c].copy()
-            s.counts = None
-            ocs.append(CH.OracleChain(prob, cfg, s, draws=PhiloxDraws(cfg.seed)))
         rec = ctx.run(n_steps, records=True)
-        near_ties = 0
-        for c, oc in enumerate(ocs):
-            for i in range(n_steps):
-                o = oc.step()
-                r = rec[c, i]
-                assert r["op"] == o.op, f"chain {c} step {i}: operator {r['op']} vs {o.op}"
-                if np.isfinite(o.mh_ratio) and abs(o.log_u - o.mh_ratio) < 1e-9:
-                    near_ties += 1
-                assert bool(r["accept"]) == o.accept, f"chain {c} step {i} op {o.op}: accept"
-                assert rel(o.log_q, r["log_q"]) < tol, f"chain {c} step {i} op {o.op}: log_q {o.log_q} {r['log_q']}"
-                assert rel(o.log_q_back, r["log_q_back"]) < tol, f"chain {c} step {i} op {o.op}: log_q_back"
-                assert rel(o.ll_new, r["ll_new"]) < tol, f"chain {c} step {i} op {o.op}: ll"
-                assert rel(o.prior_new, r["prior_new"]) < tol, f"chain {c} step {i} op {o.op}: prior"
-            fin = ctx.get_state(c)
-            assert np.array_equal(fin.cluster_of, oc.state.cluster_of)
-            assert np.array_equal(fin.src, oc.state.src)
-            assert np.array_equal(fin.counts, oc.state.counts)
-            assert np.array_equal(fin.W, oc.state.W)
-            post = ctx.posterior(c)
-            assert rel(oc.ll, post["ll"]) < tol and rel(oc.prior, post["prior"]) < tol
-            a, rj = ctx.op_stats(c)
-            assert np.array_equal(a, oc.accepts) and np.array_equal(rj, oc.rejects)
-        return near_ties
+        trajs = oracle_trajectories([(prob, cfg, st0[c], n_steps) for c, cfg in enumerate(cfgs)], procs)
+        return compare_with_trajectories(ctx, rec, trajs, tol)
     finally:
         ctx.close()

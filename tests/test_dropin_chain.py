@@ -17,9 +17,13 @@ from sbayes_b200.packed import ChainConfig
 pytestmark = pytest.mark.ref
 
 
-def _lib():
-    import torch
-    if torch.cuda.is_available():
+# every test runs twice: in the fibre emulator (GPU-less container) and, `gpu`-marked, on the
+# B200 through the CUDA library (the reference then comes from oracle/_ref, see oracle/make_ref.py)
+BACKENDS = ["emu", pytest.param("cuda", marks=pytest.mark.gpu)]
+
+
+def _lib(backend):
+    if backend == "cuda":
         return None
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim"))
     import build as HB
@@ -55,14 +59,15 @@ def _reference_problem():
     return prob, data, model
 
 
+@pytest.mark.parametrize("backend", BACKENDS)
 @pytest.mark.parametrize("T,Tp", [(1.0, 1.0), (1.2, 1.1)])
-def test_dropin_chain_matches_oracle(T, Tp):
+def test_dropin_chain_matches_oracle(T, Tp, backend):
     from sbayes_b200.chain import MCMCChain
     r = H.ref()
     prob0, data, model = _reference_problem()
     opcfg = r.config.OperatorsConfig(clusters=70, weights=10, source=20)
     lg = CountingLogger()
-    chain = MCMCChain(model, data, opcfg, [lg], temperature=T, prior_temperature=Tp, seed=321, team=2, _lib=_lib())
+    chain = MCMCChain(model, data, opcfg, [lg], temperature=T, prior_temperature=Tp, seed=321, team=2, _lib=_lib(backend))
     prob = chain.prob
     st0 = synth.initial_state(prob, seed=3, objects_per_cluster=6)
     st0.counts = M.rebuild_counts(prob, st0)
@@ -104,14 +109,15 @@ def test_install_rebinds_the_reference_names():
     r = H.ref()
     orig = r.mcmc_chain.MCMCChain
     try:
-        C.install()
-        assert r.mcmc_chain.MCMCChain is C.MCMCChain and r.mcmc_setup.MCMCChain is C.MCMCChain
+        cls = C.install()
+        assert issubclass(cls, C.MCMCChain) and r.mcmc_chain.MCMCChain is cls and r.mcmc_setup.MCMCChain is cls
     finally:
         r.mcmc_chain.MCMCChain = orig
         r.mcmc_setup.MCMCChain = orig
 
 
-def test_dropin_mcmc_generate_samples_matches_oracle():
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_dropin_mcmc_generate_samples_matches_oracle(backend):
     """Boundary B1': `MCMC.generate_samples` (sbayes/sampling/mcmc.py:155-263) -- warm-up picks the
     best of several chains, sampling logs chain 0 at the reference's step indices."""
     import logging
@@ -122,7 +128,7 @@ def test_dropin_mcmc_generate_samples_matches_oracle():
     st0 = synth.initial_state(prob0, seed=3, objects_per_cluster=6)
 
     # ---- warm-up: 3 chains from the same sample, 25 steps, best log-likelihood wins ----------
-    warm = MCMC(model, data, opcfg, [], n_chains=3, logger=logging.getLogger("t"), seed=50, team=1, _lib=_lib())
+    warm = MCMC(model, data, opcfg, [], n_chains=3, logger=logging.getLogger("t"), seed=50, team=1, _lib=_lib(backend))
     prob = warm.prob
     st0.counts = M.rebuild_counts(prob, st0)
     sample0 = H.sample_from_state(prob, model, data, st0)
@@ -141,7 +147,7 @@ def test_dropin_mcmc_generate_samples_matches_oracle():
 
     # ---- sampling: 50 steps, 5 samples -> logged after the steps with index 0, 10, 20, 30, 40 --
     lg = CountingLogger()
-    smp = MCMC(model, data, opcfg, [lg], logger=logging.getLogger("t"), seed=77, team=2, _lib=_lib())
+    smp = MCMC(model, data, opcfg, [lg], logger=logging.getLogger("t"), seed=77, team=2, _lib=_lib(backend))
     sample0.i_step = 0
     out = smp.generate_samples(n_steps=50, n_samples=5, initial_sample=sample0)
     assert [row[0] for row in lg.rows] == [0, 10, 20, 30, 40] and out.i_step == 49
@@ -163,11 +169,12 @@ def test_dropin_mcmc_generate_samples_matches_oracle():
     smp.close()
 
 
-def test_device_model_matches_reference_model():
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_device_model_matches_reference_model(backend):
     """Boundary B2 (model API): Model.likelihood / Model.prior of a reference Sample on the device"""
     from sbayes_b200.chain import DeviceModel
     prob0, data, model = _reference_problem()
-    dm = DeviceModel(model, data, _lib=_lib())
+    dm = DeviceModel(model, data, _lib=_lib(backend))
     for seed in (3, 4):
         st = synth.initial_state(dm.prob, seed=seed, objects_per_cluster=6)
         st.counts = M.rebuild_counts(dm.prob, st)
@@ -187,13 +194,14 @@ def test_install_rebinds_mcmc_too():
     orig = (r.mcmc_chain.MCMCChain, mm.MCMC)
     try:
         C.install()
-        assert mm.MCMC is C.MCMC and r.mcmc_setup.MCMC is C.MCMC
+        assert issubclass(mm.MCMC, C.MCMC) and r.mcmc_setup.MCMC is mm.MCMC
     finally:
         r.mcmc_chain.MCMCChain = orig[0]; r.mcmc_setup.MCMCChain = orig[0]
         mm.MCMC = orig[1]; r.mcmc_setup.MCMC = orig[1]
 
 
-def test_device_operator_api_matches_oracle_proposals():
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_device_operator_api_matches_oracle_proposals(backend):
     """Boundary B2 (operator API): `op.function(sample) -> (sample', log_q, log_q_back)` of every
     scheduled operator, executed on the device, against the oracle's proposal on the same draws."""
     from oracle import operators as O
@@ -202,7 +210,7 @@ def test_device_operator_api_matches_oracle_proposals():
     r = H.ref()
     prob0, data, model = _reference_problem()
     opcfg = r.config.OperatorsConfig(clusters=70, weights=10, source=20)
-    ops = device_operator_schedule(opcfg, model, data, seed=4242, _lib=_lib())
+    ops = device_operator_schedule(opcfg, model, data, seed=4242, _lib=_lib(backend))
     ref_ops = r.operators.get_operator_schedule(operators_config=opcfg, model=model, data=data)
     engine = next(iter(ops.values())).device_engine
     prob = engine.prob
@@ -238,3 +246,35 @@ def test_device_operator_api_matches_oracle_proposals():
             sample = new
     assert n_changed >= 15
     engine.ctx.close()
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_restarted_step_index_gets_fresh_draws(backend):
+    """The reference restarts `i_step` on the SAME chain object (every warm-up attempt of
+    MCMCChainProcess.initialize_sample starts at 0, mcmc_setup.py:503-523).  The device addresses
+    its draws by (key, step), so the key must change with every restart: two runs from the same
+    sample must not replay the same operator choices and uniforms."""
+    from sbayes_b200.chain import MCMCChain
+    r = H.ref()
+    prob0, data, model = _reference_problem()
+    opcfg = r.config.OperatorsConfig(clusters=70, weights=10, source=20)
+    chain = MCMCChain(model, data, opcfg, [], seed=11, team=1, _lib=_lib(backend))
+    st0 = synth.initial_state(chain.prob, seed=3, objects_per_cluster=6)
+    st0.counts = M.rebuild_counts(chain.prob, st0)
+    sample0 = H.sample_from_state(chain.prob, model, data, st0)
+    outs = []
+    for attempt in range(3):
+        out = chain.run(n_steps=60, logging_interval=10 ** 9, initial_sample=sample0)
+        outs.append(H.state_from_sample(chain.prob, out))
+        chain.reset_posterior_cache()
+    assert chain._epoch == 2
+    for a in range(3):
+        for b in range(a + 1, 3):
+            assert not (np.array_equal(outs[a].src, outs[b].src) and np.array_equal(outs[a].W, outs[b].W)), \
+                "restarted runs replayed the same draws"
+    # a continuation (i_step goes on where the last run ended) keeps its key
+    cont = chain.run(n_steps=10, logging_interval=10 ** 9, initial_sample=sample0)
+    e = chain._epoch
+    chain.run(n_steps=10, logging_interval=10 ** 9, initial_sample=cont)
+    assert chain._epoch == e
+    chain.close()

@@ -1,4 +1,6 @@
 """GPU debugging helper: Philox lockstep against the oracle on small problems, reporting the first mismatch."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # repo root (bench.py, sbayes_b200/, oracle/)
 import sys
 sys.path.insert(0, "tests")
 import numpy as np

@@ -1,4 +1,6 @@
 """Statistics-pass time against the shared-memory budget of the histogram kernel (tuning helper)."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # repo root (bench.py, sbayes_b200/, oracle/)
 import os, subprocess, sys
 for kb in (40, 56, 75, 100, 150, 200):
     env = dict(os.environ, SB_EVAL_SMEM_KB=str(kb))

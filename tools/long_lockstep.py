@@ -1,5 +1,7 @@
 """One-off extended lockstep of the device chains with the fp64 oracle (same Philox streams) at
 the bench shape and at the config-3 shape (checker: tests/parity.py)."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # repo root (bench.py, sbayes_b200/, oracle/)
 import sys, time
 sys.path.insert(0, "tests")
 import parity

@@ -1,5 +1,7 @@
 """Map ncu SASS-level stall samples back to CUDA source lines (profiling helper).
 usage: tools_ncu_lines.py <report.ncu-rep> <lib.so> [kernel-substring]"""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # repo root (bench.py, sbayes_b200/, oracle/)
 import csv, re, subprocess, sys, os, tempfile, collections
 rep, lib = sys.argv[1], sys.argv[2]
 kern = sys.argv[3] if len(sys.argv) > 3 else "sb_run_kernel"

@@ -1,4 +1,6 @@
 """Selected raw metrics of one ncu report as text (profiling helper).  usage: tools_ncu_metrics.py <report.ncu-rep>"""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # repo root (bench.py, sbayes_b200/, oracle/)
 import csv, subprocess, sys
 KEYS = ['gpu__time_duration.sum', 'sm__cycles_elapsed.avg ', 'dram__bytes_read.sum ', 'dram__bytes_write.sum ', 'dram__throughput.avg.pct_of_peak_sustained_elapsed',
         'lts__t_bytes.sum ', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts.sum',

@@ -1,6 +1,8 @@
 """Executed warp instructions and stall samples of an ncu capture, aggregated by device function
 (the function whose body contains the outermost sb_core.cuh line of each SASS instruction).
 usage: tools_ncu_regions.py <report.ncu-rep> <lib.so> [kernel-substring]"""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # repo root (bench.py, sbayes_b200/, oracle/)
 import csv, re, subprocess, sys, os, tempfile, collections
 rep, lib = sys.argv[1], sys.argv[2]
 kern = sys.argv[3] if len(sys.argv) > 3 else "sb_run_kernel"

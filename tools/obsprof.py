@@ -1,5 +1,7 @@
 """Short run of the observation-likelihood kernel for an ncu capture (profiling helper).
 usage: tools_obsprof.py <case> [chains]"""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # repo root (bench.py, sbayes_b200/, oracle/)
 import sys
 import tools_scale as TS
 from sbayes_b200 import synth

@@ -1,4 +1,6 @@
 """Observation-likelihood kernel time against the feature-tile width (tuning helper)."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # repo root (bench.py, sbayes_b200/, oracle/)
 import os, subprocess, sys
 for ft in (16, 32, 64, 128):
     env = dict(os.environ, SB_OBS_FT=str(ft))

@@ -1,5 +1,7 @@
 """Per-phase cycle breakdown of the step kernel (needs a library built with SB_CFLAGS=-DSB_PHASE_PROF).
 usage: tools_phases.py <team> <steps> [c2|c4] [chains]"""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # repo root (bench.py, sbayes_b200/, oracle/)
 import ctypes as C, sys
 import numpy as np
 import bench

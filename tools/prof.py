@@ -1,4 +1,6 @@
 """Per-operator device time of the step kernel at several team sizes (profiling helper)."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # repo root (bench.py, sbayes_b200/, oracle/)
 import sys, time, json
 import numpy as np
 import bench

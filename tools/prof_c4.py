@@ -1,5 +1,7 @@
 """Per-operator device time of the step kernel at the c4 shape (profiling helper).
 usage: tools_prof_c4.py <chains> <steps> [team]"""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # repo root (bench.py, sbayes_b200/, oracle/)
 import sys, time
 import numpy as np, torch
 from sbayes_b200 import synth

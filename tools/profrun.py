@@ -1,5 +1,7 @@
 """Short run of the step kernel for an ncu capture (profiling helper).
 usage: tools_profrun.py <team> <steps> [chains]"""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # repo root (bench.py, sbayes_b200/, oracle/)
 import sys
 import bench
 from sbayes_b200.backend import DeviceContext

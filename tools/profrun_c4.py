@@ -1,5 +1,7 @@
 """Short run of the step kernel at the config-4 shape for an ncu capture (profiling helper).
 usage: tools_profrun_c4.py <chains> <steps>"""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # repo root (bench.py, sbayes_b200/, oracle/)
 import sys
 from sbayes_b200 import synth
 from sbayes_b200.backend import DeviceContext

@@ -1,5 +1,7 @@
 """Exploratory timing of the step kernel and the full evaluation at the other BASELINE shapes
 (profiling helper).  usage: tools_scale.py <case>[,<case>...]   cases: c3 c4 c4s c5q c5"""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # repo root (bench.py, sbayes_b200/, oracle/)
 import sys, time
 import numpy as np
 import torch

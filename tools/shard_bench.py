@@ -1,6 +1,8 @@
 """Object-sharded full evaluation of BASELINE config 5 (200 000 x 1000 x 8, K=16, 64 families)
 under torchrun: every rank generates and holds N/world objects, evaluate() = statistics pass +
 int32 all-reduce + terms + fp64 all-reduce.  usage: torchrun --nproc-per-node W tools_shard_bench.py [N_total]"""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # repo root (bench.py, sbayes_b200/, oracle/)
 import json, os, sys, time
 import numpy as np
 import torch

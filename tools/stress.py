@@ -1,6 +1,8 @@
 """Long-run invariants of the step kernel (stress helper): after many steps the incrementally
 maintained counts equal a bulk rebuild and the cached posterior equals the uncached evaluation,
 for several shapes / team sizes.  usage: tools_stress.py"""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # repo root (bench.py, sbayes_b200/, oracle/)
 import numpy as np
 from oracle import model as M
 from sbayes_b200 import synth
