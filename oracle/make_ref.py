@@ -27,13 +27,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.environ.get("SBAYES_REFERENCE", "/root/reference")
 DST = os.path.join(HERE, "_ref")
 PARTS = ["sbayes", os.path.join("test", "test_files"), os.path.join("experiments", "south_america")]
-SKIP = shutil.ignore_patterns("__pycache__", "*.pyc", "*.pdf", "*.png", "*.jpg", "results*")
+SKIP = shutil.ignore_patterns("__pycache__", "*.pyc", "*.pdf", "*.png", "*.jpg")
 
 
 def _same_tree(a: str, b: str) -> bool:
     if not os.path.isdir(b):
         return False
-    cmp = filecmp.dircmp(a, b, ignore=["__pycache__", "results"])
+    cmp = filecmp.dircmp(a, b, ignore=["__pycache__"])
 
     def ok(c):
         if c.left_only and any(not n.endswith((".pyc", ".pdf", ".png", ".jpg")) for n in c.left_only):
