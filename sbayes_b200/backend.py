@@ -15,7 +15,9 @@ from .packed import Problem, ChainState, ChainConfig, NA, N_OPS
 
 N_SITES = 14
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libsbayes_b200.so")
+# SBAYES_B200_LIB: another build of the SAME CUDA library (profiling variant with phase counters); there is no
+# non-CUDA implementation to point it at
+LIB_PATH = os.environ.get("SBAYES_B200_LIB") or os.path.join(_HERE, "csrc", "libsbayes_b200.so")
 
 
 class SbError(RuntimeError):

@@ -8,7 +8,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(CSRC, "libsbayes_b200.so")
+# SB_LIB_OUT: profiling variants (e.g. SB_CFLAGS=-DSB_PHASE_PROF) are built beside the product library
+OUT = os.environ.get("SB_LIB_OUT") or os.path.join(CSRC, "libsbayes_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "-shared", "-I" + os.path.join(ROOT, "include")]

@@ -172,6 +172,26 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
     for (int o = 0; o < N; o++) memcpy(&x[(size_t)o * P.ldx], d->x + (size_t)o * F, F);
     for (size_t i = 0; i < x.size(); i++) if (x[i] != SB_NA_U8 && x[i] >= S) return fail(c, "state index out of range");
     TRY(up(c, &P.x, x));
+    {
+        // (one combo's pair table, 8 B x pairs x (S+1)^2, has to leave room for more than itself in shared memory)
+        bool pairs = (S + 1) * (S + 1) <= 256 && (size_t)((F + 1) / 2 + 15) / 16 * 16 * (S + 1) * (S + 1) * 8 <= (size_t)64 * 1024;
+#ifdef SB_HOSTSIM
+        if (getenv("SB_NO_PAIRS")) pairs = false;
+#else
+        if (getenv("SB_NO_PAIRS")) pairs = false;      // tuning knob
+#endif
+        if (pairs) {
+            const int np = (F + 1) / 2;
+            P.ldp = (np + 15) / 16 * 16;
+            std::vector<uint8_t> xp((size_t)N * P.ldp, (uint8_t)((S + 1) * (S + 1) - 1));
+            for (int o = 0; o < N; o++)
+                for (int i = 0; i < np; i++) {
+                    const int a = x[(size_t)o * P.ldx + 2 * i], b = 2 * i + 1 < F ? x[(size_t)o * P.ldx + 2 * i + 1] : SB_NA_U8;
+                    xp[(size_t)o * P.ldp + i] = (uint8_t)((a == SB_NA_U8 ? S : a) * (S + 1) + (b == SB_NA_U8 ? S : b));
+                }
+            TRY(up(c, &P.xp, xp));
+        }
+    }
     std::vector<int32_t> gid(d->conf_gid, d->conf_gid + (size_t)nc * N);
     for (int i = 0; i < nc; i++) for (int o = 0; o < N; o++) if (gid[(size_t)i * N + o] >= P.conf_ng[i]) return fail(c, "confounder group id out of range");
     TRY(up(c, &P.conf_gid, gid));
@@ -217,8 +237,17 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
             }
             TRY(up(c, &P.obj_pack, pack));
         }
-        // per-combo pass tables: 16 B per (combo, feature, state) and CTA
-        P.use_tables = (size_t)P.n_combos * F * S * 16 <= ((size_t)8 << 20);
+        {   // objects sorted by combo (stable counting sort) for the tiled passes
+            std::vector<int32_t> start(P.n_combos + 1, 0), perm(N);
+            for (int o = 0; o < N; o++) start[combo_id[o] + 1]++;
+            for (int j = 0; j < P.n_combos; j++) start[j + 1] += start[j];
+            std::vector<int32_t> fill(start.begin(), start.end() - 1);
+            for (int o = 0; o < N; o++) perm[fill[combo_id[o]]++] = o;
+            TRY(up(c, &P.perm, perm)); TRY(up(c, &P.combo_start, start));
+        }
+        // per-combo pass tables: 16 B per (combo, feature, state) and CTA; kept whole (shared memory or the
+        // CTA's HBM slice) while they are small, built tile by tile in shared memory otherwise
+        P.use_tables = 1;
 #ifdef SB_HOSTSIM
         if (getenv("SB_NO_TABLES")) P.use_tables = 0;
 #endif
@@ -290,6 +319,9 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
         const size_t nGF = (size_t)P.G_tot * F, nT = P.use_tables ? (size_t)P.n_combos * F * S : 1;
         size_t bytes[A_N];
         bytes[A_TAB0] = nT * 16; bytes[A_TAB1] = 0;      // both pass tables interleaved in A_TAB0
+        // smallest useful tile: one combo's dual table or its pair table (whichever is larger) + the unit entry
+        const size_t pair_combo = P.xp ? (size_t)P.ldp * (S + 1) * (S + 1) * 8 : 0;
+        const size_t one_combo = std::max((size_t)F * S * 16, pair_combo) + 32;
         bytes[A_WQ] = nH * 8; bytes[A_COUNTS] = nG * 4; bytes[A_NN] = nGF * 4;
         bytes[A_RT] = nGF * 8; bytes[A_RP] = nGF * 8; bytes[A_WP] = alias_w ? 0 : nH * 8; bytes[A_W1] = alias_w ? 0 : nH * 8; bytes[A_LW] = nH * 8;
         bytes[A_H0] = nH * 4; bytes[A_H1] = nH * 4; bytes[A_DCNT] = nG * 4; bytes[A_LLGF] = nGF * 8; bytes[A_BST] = nGF * 8;
@@ -298,6 +330,8 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
         bytes[A_APPLM] = P.use_mask ? (size_t)F * 8 : 0;
         bytes[A_MCL] = K < 32767 ? (size_t)N * 2 : 0; bytes[A_MCOMBO] = P.n_combos < 65535 ? (size_t)N * 2 : 0; bytes[A_MOSEL] = (size_t)N;
         bytes[A_COMBOT] = (size_t)P.n_combos * (P.n_conf + 1) * 4;
+        // per-(combo, feature) ratio rows of the pair pass (HBM slice only; used when the passes are tiled)
+        bytes[A_RS] = P.xp ? (size_t)P.n_combos * F * (S + 1) * 8 : 0;
         pl.alias_w = alias_w;
         pl.xblk_rows = team_for_xblk > 0 ? (N + team_for_xblk - 1) / team_for_xblk : 0;
         bytes[A_XBLK] = (size_t)pl.xblk_rows * P.ldx;
@@ -312,8 +346,6 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
         // when the pass tables cannot live in shared memory anyway (large N x F), the passes gather
         // them through L1: leave most of the SM's 256 KB to the cache (measured at config 4:
         // +10 % steps/s, profiles/r2e_c4_smem_cap.txt)
-        FixedSmem fx_probe = sb_fixed_smem(P.G_tot, K, F, C, c->smem_members, 0);
-        if (P.use_tables && nT * 16 + 4096 > budget) budget = std::min(budget, std::max((size_t)64 * 1024, (size_t)fx_probe.end + 32 * 1024));
         if (getenv("SB_SMEM_CAP_KB")) budget = std::min((size_t)max_optin, (size_t)atol(getenv("SB_SMEM_CAP_KB")) * 1024);   // tuning knob
 #endif
         FixedSmem fx0 = sb_fixed_smem(P.G_tot, K, F, C, c->smem_members, 0);
@@ -321,11 +353,59 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
         // arrays that only exist in shared memory (the global originals serve otherwise)
         auto smem_only = [](int a) { return a == A_XBLK || a == A_ALPHA || a == A_ASUM || a == A_APPLM || a == A_MCL || a == A_MCOMBO || a == A_MOSEL || a == A_COMBOT; };
         size_t soff = 0, goff = 0;
+        const bool force_tiled =
+#ifdef SB_HOSTSIM
+            getenv("SB_HOSTSIM_TILED") != nullptr;
+#else
+            getenv("SB_FORCE_TILED") != nullptr;
+#endif
+        size_t avail = budget > fx0.end + 256 ? (budget - fx0.end - 256) & ~(size_t)15 : 0;
+        // does the whole pass table find room behind the arrays that precede it?
+        bool tiled = false;
+        if (P.use_tables) {
+            size_t pre = 0;
+            for (int a = 0; a < A_TAB0; a++) { size_t b = (bytes[a] + 15) & ~(size_t)15; if (pre + b <= avail) pre += b; }
+            tiled = force_tiled || pre + ((bytes[A_TAB0] + 15) & ~(size_t)15) > avail;
+        }
+#ifndef SB_HOSTSIM
+        if (tiled && !getenv("SB_SMEM_CAP_KB")) {
+            // tiled placement: the replicas live in the HBM slice and are reached through L1, so a part of the
+            // SM's 256 KB is left to the cache (measured at config 4, profiles/r3g_c4_tile_sweep.txt: 168 KB of
+            // shared memory 205 us per step, all 227 KB 225 us) -- unless one combo's table needs more
+            const size_t want = std::max((size_t)168 * 1024, one_combo + fx0.end + 256 + 4096);
+            budget = std::min(budget, want);
+            avail = budget > fx0.end + 256 ? (budget - fx0.end - 256) & ~(size_t)15 : 0;
+        }
+#endif
+        size_t tile_bytes = 0, tile_full = 0;
+        if (tiled) {
+            // the table is built tile by tile in shared memory (sb_core.cuh: tiled_pass).  The tile buffer is
+            // reserved first (at least one combo's dual table, 96 KB when the table is that large), the other
+            // arrays follow in priority order.
+            const size_t full = std::max((bytes[A_TAB0] + 15) & ~(size_t)15, (pair_combo * P.n_combos + 47) & ~(size_t)15);
+            if (avail < one_combo) return fail(c, "problem too large: one combo's pass table (16 B x features x states) does not fit in shared memory");
+            size_t tile_target = (size_t)96 * 1024;
+#ifndef SB_HOSTSIM
+            if (getenv("SB_TILE_KB")) tile_target = (size_t)atol(getenv("SB_TILE_KB")) * 1024;     // tuning knob
+#endif
+            tile_bytes = std::min(avail, std::max(one_combo, std::min(full, tile_target)));
+            if (force_tiled) tile_bytes = std::min(tile_bytes, std::max(one_combo, ((full / 3) + 15) & ~(size_t)15));   // tests: several tiles
+            tile_bytes = (tile_bytes + 15) & ~(size_t)15;
+            tile_full = full;
+        }
+        const size_t room_others = avail - tile_bytes;
         for (int a = 0; a < A_N; a++) {
             size_t b = (bytes[a] + 15) & ~(size_t)15;
             pl.glob_off[a] = goff;
+            if (a == A_TAB0 && tiled) continue;            // placed below; no copy in the HBM slice
+            if (a == A_RS) { if (tiled) goff += b; continue; }      // HBM slice only
             if (!smem_only(a)) goff += b;
-            if (b > 0 && soff + b + fx0.end + 256 <= budget) { pl.in_smem[a] = 1; pl.smem_off[a] = (unsigned)soff; soff += b; }
+            if (b > 0 && soff + b <= room_others) { pl.in_smem[a] = 1; pl.smem_off[a] = (unsigned)soff; soff += b; }
+        }
+        if (tiled) {
+            (void)tile_full;     // (the tile keeps its target size: what is left over serves the cache, see above)
+            pl.tiled = 1; pl.tile_doubles = (unsigned)(tile_bytes / 8);
+            pl.in_smem[A_TAB0] = 1; pl.smem_off[A_TAB0] = (unsigned)soff; soff += tile_bytes;
         }
         if (!pl.in_smem[A_XBLK]) pl.xblk_rows = 0;
         pl.sel_off = goff; goff += ((size_t)N + 15) & ~(size_t)15;
@@ -987,6 +1067,11 @@ static int counts_common(sb_ctx *c, int chain, int32_t *counts_out, float *ms, b
 }
 SB_API int sb_counts_rebuild_hist(sb_ctx *c, int chain, int32_t *counts_out, float *ms) { return counts_common(c, chain, counts_out, ms, false); }
 SB_API int sb_counts_rebuild_mma(sb_ctx *c, int chain, int32_t *counts_out, float *ms) { return counts_common(c, chain, counts_out, ms, true); }
+
+#ifdef SB_HOSTSIM
+// emulator builds only (not part of the ABI): calls of the tiled passes per kind {alter, wide, jump, alter on feature pairs}
+SB_API long sb_hostsim_tiled_calls(int kind) { return kind >= 0 && kind < 4 ? uc4::g_tiled_calls[kind] + uc8::g_tiled_calls[kind] : -1; }
+#endif
 
 #if defined(SB_PHASE_PROF) && !defined(SB_HOSTSIM)
 // debug builds only (not part of the ABI): phase cycle counters of the step kernel

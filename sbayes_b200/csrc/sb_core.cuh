@@ -198,6 +198,7 @@ struct Rep {
     int32_t *H[2];                                    // [n_pat*2, F, C]; H[hcur] committed, the other one candidate
     double *w1, *wp, *wq, *lw;                        // [n_pat*2, F, C] weight tables
     SbD2 *tab;                                        // [n_combos, F, S] pass tables, the two of them interleaved (build_tables)
+    double *rs;                                       // [n_combos, F, S+1] ratio rows of the tiled pair pass (HBM slice)
     const uint8_t *xblk;                              // the CTA's own block of observation rows, or null
     int xlo, xhi;
     double *lh, *bk_lh;                               // [G_tot] per-group log-likelihood
@@ -236,6 +237,8 @@ struct RunC {
     int *smem_mem;     // smem member list (geo)
     double *smem_best; // smem Prim keys (geo)
     int smem_cap;
+    double *tile;      // smem tile buffer of the tiled passes (null: the whole pass table is resident, rp.tab)
+    int tile_cap;      // its size in doubles
 };
 
 struct Run {
@@ -377,55 +380,79 @@ SB_DEV void team_range(const Run &R, int n, int &lo, int &hi) {
 // extra[0..1] are summed over the team on the way (free ride on the same barrier).
 SB_DEV int team_pick(Run &R, const double *val, int n, double u, double &total, double *extra = nullptr) {
     int lo, hi; team_range(R, n, lo, hi);
-    double s[3] = {0.0, extra ? extra[0] : 0.0, extra ? extra[1] : 0.0};
-    for (int i = lo + sb_tid(); i < hi; i += sb_nthr()) s[0] += val[i];
+    const int nthr = sb_nthr(), tid = sb_tid();
+    // every thread owns a contiguous chunk of the CTA's block
+    int ch = (hi - lo + nthr - 1) / nthr;
+    int a = lo + tid * ch, b = a + ch; if (a > hi) a = hi; if (b > hi) b = hi;
+    double cs = 0.0;
+    for (int i = a; i < b; i++) cs += val[i];
+    double s[3] = {cs, extra ? extra[0] : 0.0, extra ? extra[1] : 0.0};
     block_sum<3>(R, s);
-    double *buf = R.c->tred + (size_t)R.par * R.tsize * SB_REDW;
-    R.par ^= 1;
-    if (sb_tid() == 0) { buf[R.rank * SB_REDW] = s[0]; buf[R.rank * SB_REDW + 1] = s[1]; buf[R.rank * SB_REDW + 2] = s[2]; }
-    team_sync(R);
-    total = 0.0;
-    double e0 = 0.0, e1 = 0.0;
-    for (int r = 0; r < R.tsize; r++) { total += buf[r * SB_REDW]; e0 += buf[r * SB_REDW + 1]; e1 += buf[r * SB_REDW + 2]; }
-    if (extra) { extra[0] = e0; extra[1] = e1; }
-    if (!(total > 0.0)) return -1;
-    double target = u * total;
-    int B = (n + R.tsize - 1) / R.tsize;
-    int rb = -1; double prefix = 0.0, acc = 0.0;
-    for (int r = 0; r < R.tsize; r++) {
-        double sr = buf[r * SB_REDW];
-        if (sr > 0.0) { rb = r; prefix = acc; if (acc + sr > target) break; }
-        acc += sr;
+    int rb = 0; double tloc;
+    if (R.tsize > 1) {
+        double *buf = R.c->tred + (size_t)R.par * R.tsize * SB_REDW;
+        R.par ^= 1;
+        if (tid == 0) { buf[R.rank * SB_REDW] = s[0]; buf[R.rank * SB_REDW + 1] = s[1]; buf[R.rank * SB_REDW + 2] = s[2]; }
+        team_sync(R);
+        total = 0.0;
+        double e0 = 0.0, e1 = 0.0;
+        for (int r = 0; r < R.tsize; r++) { total += buf[r * SB_REDW]; e0 += buf[r * SB_REDW + 1]; e1 += buf[r * SB_REDW + 2]; }
+        if (extra) { extra[0] = e0; extra[1] = e1; }
+        if (!(total > 0.0)) return -1;
+        const double target = u * total;
+        rb = -1; double prefix = 0.0, acc = 0.0;
+        for (int r = 0; r < R.tsize; r++) {
+            double sr = buf[r * SB_REDW];
+            if (sr > 0.0) { rb = r; prefix = acc; if (acc + sr > target) break; }
+            acc += sr;
+        }
+        tloc = target - prefix;
+        if (rb != R.rank) {       // the block that holds the target: every CTA scans it (no second barrier)
+            const int B = (n + R.tsize - 1) / R.tsize;
+            lo = rb * B; hi = lo + B; if (hi > n) hi = n;
+            ch = (hi - lo + nthr - 1) / nthr;
+            a = lo + tid * ch; b = a + ch; if (a > hi) a = hi; if (b > hi) b = hi;
+            cs = 0.0;
+            for (int i = a; i < b; i++) cs += val[i];
+        }
+    } else {
+        total = s[0];
+        if (extra) { extra[0] = s[1]; extra[1] = s[2]; }
+        if (!(total > 0.0)) return -1;
+        tloc = u * total;
     }
-    int blo = rb * B, bhi = blo + B; if (bhi > n) bhi = n;
-    double tloc = target - prefix;
-    if (sb_warp() == 0) {
-        int len = bhi - blo, ch = (len + 31) / 32, lane = sb_lane();
-        int a = blo + lane * ch, b = a + ch; if (a > bhi) a = bhi; if (b > bhi) b = bhi;
-        double cs = 0.0;
-        for (int i = a; i < b; i++) cs += val[i];
-        double incl = cs;
-        for (int off = 1; off < 32; off <<= 1) {
-            double t = sb_shfl_f64(incl, lane - off);
-            if (lane >= off) incl += t;
+    // block-wide exclusive scan of the chunk sums: warp scan, warp totals through shared memory
+    const int lane = sb_lane(), w = sb_warp(), nw = sb_nwarps();
+    double incl = cs;
+    for (int off = 1; off < 32; off <<= 1) {
+        double t = sb_shfl_f64(incl, lane - off);
+        if (lane >= off) incl += t;
+    }
+    double *wt = R.c->sred + R.spar * (32 * SB_REDW);
+    R.spar ^= 1;
+    if (lane == 31) wt[w] = incl;
+    sb_cta_sync();
+    double wpre = 0.0;
+    for (int v = 0; v < w; v++) wpre += wt[v];
+    const double excl = wpre + (incl - cs);
+    // the first thread whose chunk carries the running sum past the target; if rounding lets none do so,
+    // the last thread with a positive chunk
+    const unsigned hit = sb_ballot(cs > 0.0 && excl + cs > tloc), pos = sb_ballot(cs > 0.0);
+    if (lane == 0) { R.c->sint[w] = hit ? (w << 5) + sb_ffs(hit) - 1 : -1; R.c->sint[32 + w] = pos ? (w << 5) + 31 - sb_clz(pos) : -1; }
+    sb_cta_sync();
+    int sel_t = -1, last_t = -1;
+    for (int v = 0; v < nw; v++) { const int h = R.c->sint[v], q = R.c->sint[32 + v]; if (sel_t < 0 && h >= 0) sel_t = h; if (q >= 0) last_t = q; }
+    if (sel_t < 0) sel_t = last_t;
+    if (tid == (sel_t < 0 ? 0 : sel_t)) {
+        double run = excl; int found = -1, last = -1;
+        for (int i = a; i < b; i++) {
+            const double vi = val[i];
+            if (vi > 0.0) { last = i; run += vi; if (run > tloc) { found = i; break; } }
         }
-        unsigned hit = sb_ballot(incl > tloc && cs > 0.0);
-        unsigned pos = sb_ballot(cs > 0.0);
-        int sel_lane = hit ? (sb_ffs(hit) - 1) : (pos ? 31 - sb_clz(pos) : 0);
-        int found = -1;
-        if (lane == sel_lane) {
-            double run = incl - cs; int last = -1;
-            for (int i = a; i < b; i++) {
-                double vi = val[i];
-                if (vi > 0.0) { last = i; run += vi; if (run > tloc) { found = i; break; } }
-            }
-            if (found < 0) found = last;
-        }
-        found = sb_shfl_i32(found, sel_lane);
-        if (lane == 0) R.c->sint[64] = found;
+        R.c->sint[64] = found >= 0 ? found : last;
     }
     sb_cta_sync();
-    int o = R.c->sint[64];
+    const int o = R.c->sint[64];
     sb_cta_sync();
     return o;
 }
@@ -458,6 +485,37 @@ SB_DEV int team_compact(Run &R, int n, int32_t *list, Pred pred) {
         sb_cta_sync();
     }
     team_sync(R);
+    return total;
+}
+
+// CTA-local ordered compaction of [lo, hi): list[0..n) receives, in increasing order, the i with
+// pred(i); other(i) is called for the rest.  Every warp owns a contiguous segment (two passes over
+// the predicate, two CTA barriers).  Returns n in every thread.  pred must be pure.
+template <class Pred, class Other>
+SB_DEV int cta_compact(Run &R, int lo, int hi, int32_t *list, Pred pred, Other other) {
+    const int nw = sb_nwarps(), w = sb_warp(), lane = sb_lane();
+    const int seg = ((hi - lo + nw - 1) / nw + 31) & ~31;
+    const int a = lo + w * seg, b = a + seg < hi ? a + seg : hi;
+    int cnt = 0;
+    for (int i0 = a; i0 < b; i0 += 32) {
+        const int i = i0 + lane;
+        const bool p = i < b && pred(i);
+        if (i < b && !p) other(i);
+        cnt += sb_popc(sb_ballot(p));
+    }
+    sb_cta_sync();                              // sint may still be read from an earlier use
+    if (lane == 0) R.c->sint[w] = cnt;
+    sb_cta_sync();
+    int base = 0, total = 0;
+    for (int v = 0; v < nw; v++) { const int c = R.c->sint[v]; if (v < w) base += c; total += c; }
+    for (int i0 = a; i0 < b; i0 += 32) {
+        const int i = i0 + lane;
+        const bool p = i < b && pred(i);
+        const unsigned bal = sb_ballot(p);
+        if (p) list[base + sb_popc(bal & ((1u << lane) - 1u))] = i;
+        base += sb_popc(bal);
+    }
+    sb_cta_sync();
     return total;
 }
 
@@ -902,7 +960,285 @@ SB_DEV void obj_marginals_lane(const Run &R, int o, Prod &p0, Prod &p1) {
 // (built redundantly by every CTA); uniform across the team
 SB_DEV bool pass_uses_tables(const Run &R, long long n_obj) {
     const SbProblem &P = *R.P;
+    // tiled: a CTA builds only the tables of the combos its objects (in combo order) belong to
+    if (R.c->tile) return P.use_tables && n_obj * 3 > (long long)(P.n_combos + R.tsize) * P.S * 2;
     return P.use_tables && n_obj * 3 > (long long)P.n_combos * P.S * 2 * R.tsize;
+}
+
+// -----------------------------------------------------------------------------------------
+// Tiled passes (problems whose per-combo pass tables do not fit in shared memory as a whole:
+// BASELINE configs 4 and 5).  The objects are walked in combo order (P.perm), split over the team
+// by position, so a CTA meets few combos; it builds the tables of those combos in shared memory a
+// tile of combos at a time and gathers from shared memory only: per observation one byte of the
+// packed row (16-byte loads), one 8- or 16-byte shared-memory load and one or two multiplies.
+//   TK_ALTER  one table, the ratio b / a of the two mixtures (the posterior of AlterCluster only
+//             needs log m1 - log m0 = sum_f log(b_f / a_f), operators.py:1060-1073)
+//   TK_WIDE   both mixtures (compute_raw_cluster_probs adds EPS to m0 + m1, operators.py:1444-1471)
+//   TK_JUMP   get_jump_lh (operators.py:1679-1722): conf + w0 pT[src], conf + w0 pT[tgt]
+// An object is processed by L lanes (L = 1 when the CTA has at least as many objects as threads).
+// -----------------------------------------------------------------------------------------
+enum { TK_ALTER = 0, TK_WIDE, TK_JUMP, TK_ALTER2 };      // TK_ALTER2: TK_ALTER on feature pairs (P.xp)
+#ifdef SB_HOSTSIM
+static long g_tiled_calls[4];      // emulator builds: how often each kind ran (the tests assert coverage)
+#endif
+
+SB_DEV int combo_of_pos(const SbProblem &P, int p) {
+    int lo = 0, hi = P.n_combos - 1;
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (sb_ldg(P.combo_start + mid) <= p) lo = mid; else hi = mid - 1; }
+    return lo;
+}
+
+struct Row16 { uint32_t w[4]; };
+SB_DEV Row16 load_row16(const uint8_t *p) {      // p is 16-byte aligned
+    Row16 r;
+#ifdef SB_HOSTSIM
+    memcpy(&r, p, 16);
+#else
+    const uint4 t = *(const uint4 *)p; r.w[0] = t.x; r.w[1] = t.y; r.w[2] = t.z; r.w[3] = t.w;
+#endif
+    return r;
+}
+
+// tables of the combos [j0, j1) into the tile buffer; tile[0..1] = 1.0 is the entry a missing value reads
+template <int KIND>
+SB_DEV void build_tile(Run &R, int k, int k2, int j0, int j1) {
+    const SbProblem &P = *R.P;
+    const int F = P.F, S = P.S, C = P.C;
+    constexpr int W = KIND == TK_ALTER ? 1 : 2;
+    double *tile = R.c->tile + 2;
+    const bool powT = KIND == TK_WIDE && R.T != 1.0;
+    for (int idx = sb_tid(); idx < (j1 - j0) * F; idx += sb_nthr()) {
+        const int jj = idx / F, f = idx % F, j = j0 + jj;
+        const int pat = R.c->combo_pat[j];
+        const double *w0 = R.c->rp.wq + ((size_t)(pat * 2 + 0) * F + f) * C;
+        const double *w1 = R.c->rp.wq + ((size_t)(pat * 2 + 1) * F + f) * C;
+        int gC[SB_UC]; double rC[SB_UC];
+        SB_FOR_C1(c, C) {
+            gC[c] = R.c->combo_rows[(size_t)j * P.n_conf + c - 1];
+            rC[c] = gC[c] < 0 ? 0.0 : (KIND == TK_JUMP ? R.c->rp.rT[(size_t)gC[c] * F + f] : R.c->rp.rP[(size_t)gC[c] * F + f]);
+        }
+        const double rk = R.c->rp.rT[(size_t)k * F + f], w10 = w1[0];
+        const double rk2 = KIND == TK_JUMP ? R.c->rp.rT[(size_t)k2 * F + f] : 0.0;
+        double *t = tile + ((size_t)jj * F + f) * S * W;
+        for (int x = 0; x < S; x++) {
+            if (KIND == TK_JUMP) {
+                double conf = 0.0;
+                SB_FOR_C1(c, C) if (gC[c] >= 0) conf += w1[c] * (num_T(R, gC[c], f, x) * rC[c]);
+                t[2 * x] = conf + w10 * (num_T(R, k, f, x) * rk);
+                t[2 * x + 1] = conf + w10 * (num_T(R, k2, f, x) * rk2);
+            } else {
+                double l0 = num_T(R, k, f, x) * rk;
+                if (powT) l0 = pow_inv(l0, R.invT, false);
+                double a0 = 0.0, a1 = l0 * w10;
+                SB_FOR_C1(c, C) {
+                    if (gC[c] >= 0) {
+                        double l = num_P(R, gC[c], f, x) * rC[c];
+                        a0 += l * w0[c]; a1 += l * w1[c];
+                    }
+                }
+                if (KIND == TK_ALTER) t[x] = a1 / a0;
+                else { t[2 * x] = a0; t[2 * x + 1] = a1; }
+            }
+        }
+    }
+    if (sb_tid() == 0) { R.c->tile[0] = 1.0; R.c->tile[1] = 1.0; }
+    sb_cta_sync();
+}
+
+// sixteen features of one row against one combo's table: products of the gathered entries
+template <int W>
+SB_DEV void chunk_products(const double *unit, const double *tc, int S, int fbase, const Row16 &r, Prod &a, Prod &b) {
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        double va[8], vb[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int x = (r.w[2 * half + (i >> 2)] >> (8 * (i & 3))) & 0xFF;
+            const double *ptr = x == SB_NA_U8 ? unit : tc + (size_t)((fbase + 8 * half + i) * S + x) * W;
+            if (W == 1) va[i] = *ptr;
+            else { const SbD2 v = *(const SbD2 *)ptr; va[i] = v.a; vb[i] = v.b; }
+        }
+        a.m *= ((va[0] * va[1]) * (va[2] * va[3])) * ((va[4] * va[5]) * (va[6] * va[7]));
+        prod_renorm(a);
+        if (W == 2) {
+            b.m *= ((vb[0] * vb[1]) * (vb[2] * vb[3])) * ((vb[4] * vb[5]) * (vb[6] * vb[7]));
+            prod_renorm(b);
+        }
+    }
+}
+
+// ratio of the two mixtures of AlterCluster for one (combo, feature): r[x] for x < S, r[S] = 1 (missing value)
+template <int SM>
+SB_DEV void ratio_row(const Run &R, int k, int j, int f, double (&r)[SM + 1]) {
+    const SbProblem &P = *R.P;
+    const int F = P.F, S = P.S, C = P.C;
+#pragma unroll
+    for (int x = 0; x <= SM; x++) r[x] = 1.0;
+    if (f >= F) return;
+    // Branch-free: the loads behind one component (S counts, S concentrations) are issued together, a
+    // component without a group for this combo reads row 0 and is multiplied by a zero reciprocal (its
+    // terms are exact zeros, so the sums equal those of build_tables)
+    const int32_t *SB_RESTRICT counts = R.c->rp.counts;
+    const double *SB_RESTRICT alpha = R.c->alpha;
+    const int pat = R.c->combo_pat[j];
+    const double *SB_RESTRICT w0 = R.c->rp.wq + ((size_t)(pat * 2 + 0) * F + f) * C;
+    const double *SB_RESTRICT w1 = R.c->rp.wq + ((size_t)(pat * 2 + 1) * F + f) * C;
+    double a0[SM], a1[SM];
+    {
+        const double rk = R.c->rp.rT[(size_t)k * F + f], w10 = w1[0];
+        const size_t cb = ((size_t)k * F + f) * S, ab = ((size_t)arow(P, k) * F + f) * S;
+        int cn[SM]; double al[SM];
+#pragma unroll
+        for (int x = 0; x < SM; x++) { const int xx = x < S ? x : S - 1; cn[x] = counts[cb + xx]; al[x] = alpha[ab + xx]; }
+#pragma unroll
+        for (int x = 0; x < SM; x++) {
+            const double u = unif_at(R, f, x < S ? x : S - 1);
+            a0[x] = 0.0;
+            a1[x] = ((u + (al[x] - u) * R.invTp + (double)cn[x] * R.invT) * rk) * w10;
+        }
+    }
+    SB_FOR_C1(c, C) {
+        const int gq = R.c->combo_rows[(size_t)j * P.n_conf + c - 1], g = gq < 0 ? 0 : gq;
+        const double rq = R.c->rp.rP[(size_t)g * F + f], rc = gq < 0 ? 0.0 : rq, w0c = w0[c], w1c = w1[c];
+        const size_t cb = ((size_t)g * F + f) * S, ab = ((size_t)arow(P, g) * F + f) * S;
+        int cn[SM]; double al[SM];
+#pragma unroll
+        for (int x = 0; x < SM; x++) { const int xx = x < S ? x : S - 1; cn[x] = counts[cb + xx]; al[x] = alpha[ab + xx]; }
+        if (gq >= 0) {
+#pragma unroll
+            for (int x = 0; x < SM; x++) {
+                const double l = (al[x] + (double)cn[x]) * rc;
+                a0[x] += l * w0c; a1[x] += l * w1c;
+            }
+        }
+    }
+#pragma unroll
+    for (int x = 0; x < SM; x++) if (x < S) r[x] = a1[x] / a0[x];
+}
+
+// ratio rows of the combos [j0, j1) into the CTA's scratch in HBM (all rows in flight at once: the loads
+// of counts / reciprocals behind a row are L2 round trips), then, tile by tile, the pair tables from them:
+// t[j][pair][a * (S+1) + b] = r[2 pair][a] * r[2 pair + 1][b]; pairs beyond the last feature (row padding) hold 1.0
+template <int SM>
+SB_DEV void build_ratio_rows(Run &R, int k, int j0, int j1) {
+    const SbProblem &P = *R.P;
+    const int F = P.F, S1 = P.S + 1;
+    for (int idx = sb_tid(); idx < (j1 - j0) * F; idx += sb_nthr()) {
+        const int j = j0 + idx / F, f = idx % F;
+        double r[SM + 1];
+        ratio_row<SM>(R, k, j, f, r);
+        double *dst = R.c->rp.rs + ((size_t)j * F + f) * S1;
+#pragma unroll
+        for (int x = 0; x <= SM; x++) if (x < S1) dst[x] = x == P.S ? 1.0 : r[x];
+    }
+    sb_cta_sync();
+}
+template <int SM>
+SB_DEV void build_tile_pairs(Run &R, int j0, int j1) {
+    const SbProblem &P = *R.P;
+    const int F = P.F, S = P.S, S1 = S + 1, PS = S1 * S1, ldp = P.ldp;
+    double *tile = R.c->tile + 2;
+    for (int idx = sb_tid(); idx < (j1 - j0) * ldp; idx += sb_nthr()) {
+        const int jj = idx / ldp, pr = idx % ldp, fa = 2 * pr, fb = fa + 1;
+        const double *sa = R.c->rp.rs + ((size_t)(j0 + jj) * F + fa) * S1, *sb = sa + S1;
+        double ra[SM + 1], rb[SM + 1];
+#pragma unroll
+        for (int x = 0; x <= SM; x++) { ra[x] = (fa < F && x < S1) ? sa[x] : 1.0; rb[x] = (fb < F && x < S1) ? sb[x] : 1.0; }
+        double *t = tile + ((size_t)jj * ldp + pr) * PS;
+#pragma unroll
+        for (int a = 0; a <= SM; a++) {
+            if (a > S) continue;
+#pragma unroll
+            for (int b = 0; b <= SM; b++)
+                if (b <= S) t[a * S1 + b] = ra[a] * rb[b];
+        }
+    }
+    sb_cta_sync();
+}
+
+// sixteen feature pairs of one row against one combo's pair table
+SB_DEV void chunk_pairs(const double *tc, int PS, int pbase, const Row16 &r, Prod &a) {
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        double va[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int code = (r.w[2 * half + (i >> 2)] >> (8 * (i & 3))) & 0xFF;
+            va[i] = tc[(size_t)(pbase + 8 * half + i) * PS + code];
+        }
+        a.m *= ((va[0] * va[1]) * (va[2] * va[3])) * ((va[4] * va[5]) * (va[6] * va[7]));
+        prod_renorm(a);
+    }
+}
+
+// sel(o): is object o part of the pass; tail(o, on, a, b) receives, in one lane per object of the
+// CTA's positions, the products over the features (a = ratio product for TK_ALTER; a, b = the two
+// mixtures otherwise).  CTA-local barriers only.
+template <int KIND, class Sel, class Tail>
+SB_DEV void tiled_pass(Run &R, int k, int k2, Sel sel, Tail tail) {
+    const SbProblem &P = *R.P;
+    const int F = P.F, S = P.S;
+    constexpr int W = (KIND == TK_ALTER || KIND == TK_ALTER2) ? 1 : 2;
+    constexpr bool PAIRS = KIND == TK_ALTER2;
+    int plo, phi; team_range(R, P.N, plo, phi);
+#ifdef SB_HOSTSIM
+    if (sb_tid() == 0 && R.rank == 0) g_tiled_calls[KIND]++;
+#endif
+    if (plo >= phi) return;
+    const int PS = (S + 1) * (S + 1);
+    const int per_combo = PAIRS ? P.ldp * PS : F * S * W;
+    const int cap = (R.c->tile_cap - 2) / per_combo;              // combos per tile (>= 1: the host checks)
+    const int j_lo = combo_of_pos(P, plo), j_hi = combo_of_pos(P, phi - 1);
+    int L = 1;
+    while (L < 32 && (phi - plo) * L * 2 <= sb_nthr()) L <<= 1;
+    const int q = sb_lane() & (L - 1), gpw = 32 / L, ngroups = sb_nwarps() * gpw;
+    const int nchunks = (PAIRS ? P.ldp : P.ldx) >> 4;
+    const double *unit = R.c->tile;
+    if (PAIRS) {
+        if (S <= 4) build_ratio_rows<4>(R, k, j_lo, j_hi + 1);
+        else if (S <= 6) build_ratio_rows<6>(R, k, j_lo, j_hi + 1);
+        else if (S <= 8) build_ratio_rows<8>(R, k, j_lo, j_hi + 1);
+        else build_ratio_rows<15>(R, k, j_lo, j_hi + 1);
+        PH(R, 34);
+    }
+    for (int j0 = j_lo; j0 <= j_hi; j0 += cap) {
+        const int j1 = j0 + cap <= j_hi + 1 ? j0 + cap : j_hi + 1;
+        if (PAIRS) {
+            if (S <= 4) build_tile_pairs<4>(R, j0, j1);
+            else if (S <= 6) build_tile_pairs<6>(R, j0, j1);
+            else if (S <= 8) build_tile_pairs<8>(R, j0, j1);
+            else build_tile_pairs<15>(R, j0, j1);
+        } else build_tile<PAIRS ? TK_ALTER : KIND>(R, k, k2, j0, j1);
+        PH(R, 32);
+        int pb = sb_ldg(P.combo_start + j0), pe = sb_ldg(P.combo_start + j1);
+        if (pb < plo) pb = plo;
+        if (pe > phi) pe = phi;
+        for (int p0 = pb + sb_warp() * gpw; p0 < pe; p0 += ngroups) {   // warp-uniform trip count
+            const int p = p0 + sb_lane() / L;
+            const bool active = p < pe;
+            const int o = active ? sb_ldg(P.perm + p) : 0;
+            const bool on = active && sel(o);
+            Prod a = prod_one(), b = prod_one();
+            if (on) {
+                const double *tc = unit + 2 + (size_t)(m_combo(R, o) - j0) * per_combo;
+                const uint8_t *xr = PAIRS ? P.xp + (size_t)o * P.ldp : x_row(R, o);
+                Row16 nx = load_row16(xr + (q < nchunks ? q : 0) * 16);
+                for (int ch = q; ch < nchunks; ch += L) {
+                    const Row16 cur = nx;
+                    if (ch + L < nchunks) nx = load_row16(xr + (ch + L) * 16);   // requested before the gathers of the current chunk
+                    if (PAIRS) chunk_pairs(tc, PS, ch * 16, cur, a);
+                    else chunk_products<W>(unit, tc, S, ch * 16, cur, a, b);
+                }
+            }
+            for (int off = L >> 1; off > 0; off >>= 1) {
+                a.m *= sb_shfl_f64(a.m, sb_lane() ^ off); a.e += sb_shfl_i32(a.e, sb_lane() ^ off); prod_renorm(a);
+                if (W == 2) { b.m *= sb_shfl_f64(b.m, sb_lane() ^ off); b.e += sb_shfl_i32(b.e, sb_lane() ^ off); prod_renorm(b); }
+            }
+            if (active && q == 0) tail(o, on, a, b);
+        }
+        sb_cta_sync();
+        PH(R, 33);
+    }
 }
 
 // AlterCluster.compute_cluster_posterior (operators.py:1035-1073) from the marginals (one lane)
@@ -1256,7 +1592,21 @@ SB_DEV void posterior_pass(Run &R, int k, int view, bool flat, bool use_geo, int
     const SbProblem &P = *R.P;
     int lo, hi; team_range(R, P.N, lo, hi);
     const bool geo = use_geo && P.geo && !flat;
-    const bool tables = !flat && pass_uses_tables(R, n_obj);
+    const bool tables = !flat && pass_uses_tables(R, n_obj) && !(R.c->tile && geo);
+    if (tables && R.c->tile) {
+        // tiled: objects in combo order, tables built tile by tile in shared memory (ratio form)
+        auto tail = [&](int o, bool on, const Prod &a, const Prod &) {
+            double post = 0.0;
+            if (on) { post = sb_expit(prod_log(a) * R.invT); post = (post + SB_SMOOTH) / (1.0 + 2.0 * SB_SMOOTH); }
+            lane_out(o, on, post);
+        };
+        if (P.xp) tiled_pass<TK_ALTER2>(R, k, 0, sel, tail);
+        else tiled_pass<TK_ALTER>(R, k, 0, sel, tail);
+        // the values of an object block were written by the CTAs that own its positions
+        if (R.tsize > 1) team_sync(R); else sb_cta_sync();
+        PH(R, 21);
+        return;
+    }
     if (tables) build_tables(R, k, false);
     PH(R, 20);
     if ((tables || flat) && !geo && hi - lo >= 32 * sb_nwarps()) {
@@ -1267,6 +1617,25 @@ SB_DEV void posterior_pass(Run &R, int k, int view, bool flat, bool use_geo, int
             if (a.on && !flat) obj_marginals_lane(R, o, a.p0, a.p1);
             lane_out(o, a.on != 0, a.on ? posterior_tail(R, a, flat, geo) : 0.0);
         }
+        sb_cta_sync();
+        PH(R, 21);
+        return;
+    }
+    if (!flat && hi - lo >= 8 * sb_nwarps()) {
+        // few selected objects among many (the members of one cluster): compact them first, then a warp per
+        // selected object; the others get their zero in the compaction sweep
+        int32_t *list = R.c->st.list_a + lo;
+        const int n = cta_compact(R, lo, hi, list, [&](int o) { return (bool)sel(o); }, [&](int o) { lane_out(o, false, 0.0); });
+        batch_items<Marg>(0, n,
+            [&](int i) {
+                const int o = list[i];
+                Marg a; a.on = 1; a.geo = 0.0;
+                if (tables) obj_marginals<true>(R, o, k, false, a.p0, a.p1);
+                else obj_marginals<false>(R, o, k, false, a.p0, a.p1);
+                if (geo) a.geo = geo_delta(R, o, k, view, m_size);
+                return a;
+            },
+            [&](int i, const Marg &a) { lane_out(list[i], true, posterior_tail(R, a, flat, geo)); });
         sb_cta_sync();
         PH(R, 21);
         return;
@@ -1371,8 +1740,9 @@ SB_DEV void wide_probs(Run &R, double *p, int k, int n_av, int view, bool use_ge
     const double eps = 0.01 / (double)P.N;
     int lo, hi; team_range(R, n_av, lo, hi);
     const bool geo = use_geo && P.geo && !R.sfp;
-    const bool tables = !R.sfp && pass_uses_tables(R, n_av);
-    if (tables) build_tables(R, k, true);
+    const bool tables = !R.sfp && pass_uses_tables(R, n_av) && !(R.c->tile && geo);
+    const bool tiled = tables && R.c->tile;
+    if (tables && !tiled) build_tables(R, k, true);
     auto tail = [&](int i, const Marg &a) {
         double raw = 0.5;
         if (!R.sfp) {
@@ -1382,7 +1752,18 @@ SB_DEV void wide_probs(Run &R, double *p, int k, int n_av, int view, bool use_ge
         }
         p[i] = raw + SB_EPS32;
     };
-    if (tables && !geo && hi - lo >= 32 * sb_nwarps()) {
+    if (tiled) {
+        // tiled: per-object values in combo order into the idle val buffer, then into list order
+        double *pobj = R.c->st.val[R.vpar ^ 1];
+        tiled_pass<TK_WIDE>(R, k, 0, [&](int o) { int c = m_cl(R, o); return c < 0 || c == k; },
+            [&](int o, bool on, const Prod &a, const Prod &b) {
+                if (!on) return;
+                double m0 = exp(prod_log(a) * R.invT), m1 = exp(prod_log(b) * R.invT);
+                pobj[o] = m1 / (m0 + m1 + SB_EPS32) + SB_EPS32;
+            });
+        if (R.tsize > 1) team_sync(R); else sb_cta_sync();
+        for (int i = lo + sb_tid(); i < hi; i += sb_nthr()) p[i] = pobj[R.c->st.list_b[i]];
+    } else if (tables && !geo && hi - lo >= 32 * sb_nwarps()) {
         // many objects per warp: a lane per object (see posterior_pass)
         for (int i = lo + sb_tid(); i < hi; i += sb_nthr()) {
             Marg a; a.on = 1; a.geo = 0.0;
@@ -1507,13 +1888,17 @@ SB_DEV Prop op_cluster_jump(Run &R) {
     if (R.c->rp.sizes[k_src] <= P.min_size || R.c->rp.sizes[k_tgt] >= P.max_size) return pr;
     int lo, hi; team_range(R, P.N, lo, hi);
     double *val = R.c->st.val[R.vpar];
-    batch_items<JumpAcc>(lo, hi,
-        [&](int o) {
-            JumpAcc a; a.on = m_cl(R, o) == k_src; a.ps = prod_one(); a.pj = prod_one();
-            if (a.on) jump_marginals(R, o, k_src, k_tgt, a.ps, a.pj);
-            return a;
-        },
-        [&](int o, const JumpAcc &a) { val[o] = a.on ? jump_tail(R, a.ps, a.pj) : 0.0; });
+    if (R.c->tile && pass_uses_tables(R, R.c->rp.sizes[k_src])) {
+        tiled_pass<TK_JUMP>(R, k_src, k_tgt, [&](int o) { return m_cl(R, o) == k_src; },
+            [&](int o, bool on, const Prod &a, const Prod &b) { val[o] = on ? jump_tail(R, a, b) : 0.0; });
+        if (R.tsize > 1) team_sync(R);
+    } else {
+        int32_t *list = R.c->st.list_a + lo;
+        const int n = cta_compact(R, lo, hi, list, [&](int o) { return m_cl(R, o) == k_src; }, [&](int o) { val[o] = 0.0; });
+        batch_items<JumpAcc>(0, n,
+            [&](int i) { JumpAcc a; a.on = 1; jump_marginals(R, list[i], k_src, k_tgt, a.ps, a.pj); return a; },
+            [&](int i, const JumpAcc &a) { val[list[i]] = jump_tail(R, a.ps, a.pj); });
+    }
     sb_cta_sync();
     PH(R, 18);
     double total;
@@ -1530,13 +1915,16 @@ SB_DEV Prop op_cluster_jump(Run &R) {
     double lqs, lqbs;
     resample_sources(R, pr, 1, R.c->slist, k_tgt, k_src, true, lqs, lqbs);
     double s[2] = {0.0, 0.0};
-    batch_items<JumpAcc>(lo, hi,
-        [&](int j) {
-            JumpAcc a; a.on = cl_of(R, j, 1) == k_tgt; a.ps = prod_one(); a.pj = prod_one();
-            if (a.on) jump_marginals(R, j, k_tgt, k_src, a.ps, a.pj);
-            return a;
-        },
-        [&](int j, const JumpAcc &a) { if (a.on) { double v = jump_tail(R, a.ps, a.pj); s[0] += v; if (j == o) s[1] = v; } });
+    if (R.c->tile && pass_uses_tables(R, R.c->rp.sizes[k_tgt] + 1)) {
+        tiled_pass<TK_JUMP>(R, k_tgt, k_src, [&](int j) { return cl_of(R, j, 1) == k_tgt; },
+            [&](int j, bool on, const Prod &a, const Prod &b) { if (on) { double v = jump_tail(R, a, b); s[0] += v; if (j == o) s[1] = v; } });
+    } else {
+        int32_t *list = R.c->st.list_a + lo;
+        const int n = cta_compact(R, lo, hi, list, [&](int j) { return cl_of(R, j, 1) == k_tgt; }, [&](int) {});
+        batch_items<JumpAcc>(0, n,
+            [&](int i) { JumpAcc a; a.on = 1; jump_marginals(R, list[i], k_tgt, k_src, a.ps, a.pj); return a; },
+            [&](int i, const JumpAcc &a) { double v = jump_tail(R, a.ps, a.pj); s[0] += v; if (list[i] == o) s[1] = v; });
+    }
     team_sum<2>(R, s);
     PH(R, 19);
     pr.lq = lq_obj + lqs;
@@ -1947,7 +2335,10 @@ SB_DEV void setup_replica(Run &R, const SbLaunch &L, char *smem, char *glob) {
     if (sb_tid() == 0) {
         auto at = [&](int a) -> char * { return pl.in_smem[a] ? smem + pl.smem_off[a] : glob + pl.glob_off[a]; };
         Rep &rp = c->rp;
-        rp.tab = (SbD2 *)at(A_TAB0);
+        rp.tab = pl.tiled ? nullptr : (SbD2 *)at(A_TAB0);
+        rp.rs = pl.tiled ? (double *)(glob + pl.glob_off[A_RS]) : nullptr;
+        c->tile = pl.tiled ? (double *)(smem + pl.smem_off[A_TAB0]) : nullptr;
+        c->tile_cap = pl.tiled ? (int)pl.tile_doubles : 0;
         rp.wq = (double *)at(A_WQ); rp.lw = (double *)at(A_LW);
         rp.wp = pl.alias_w ? rp.wq : (double *)at(A_WP); rp.w1 = pl.alias_w ? rp.wq : (double *)at(A_W1);
         c->alpha = pl.in_smem[A_ALPHA] ? (const double *)(smem + pl.smem_off[A_ALPHA]) : P.alpha;

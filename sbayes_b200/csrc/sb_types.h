@@ -58,6 +58,15 @@ struct SbProblem {
     // one word per object for the streaming kernels (null unless C <= 4, G_tot < 255, n_pat < 256):
     // byte 0 = has-pattern index, bytes 1..3 = stacked group row of components 1..3 (255 = none)
     const uint32_t *obj_pack;
+    // objects sorted by combo (stable): the tiled proposal passes walk `perm` so that the objects a CTA
+    // processes share few combos and only those combos' pass tables are built, tile by tile, in shared memory
+    const int32_t *perm;         // [N]
+    const int32_t *combo_start;  // [n_combos + 1] first position of every combo in perm
+    // two features per byte for the ratio pass of AlterCluster: xp[o, i] = x[o, 2i] * (S+1) + x[o, 2i+1] with
+    // a missing value coded as state S (null unless (S+1)^2 <= 256); rows padded to 16 bytes with the
+    // code of two missing values
+    const uint8_t *xp;           // [N, ldp]
+    int ldp;
     // lfact[i] = lgamma(i + 1) for i < lfact_n: with unit concentrations (uniform priors, the default)
     // the Dirichlet-categorical terms of the evaluation are table look-ups instead of lgamma calls
     const double *lfact;
@@ -96,7 +105,7 @@ struct SbShared {
 // replica arrays that may live in shared memory (placement priority = enum order)
 // (the small per-object lookups first: every item of every pass reads them)
 enum { A_MCL = 0, A_MCOMBO, A_MOSEL, A_COMBOT, A_APPLM, A_TAB0, A_TAB1, A_COUNTS, A_NN, A_RT, A_RP, A_WQ, A_ALPHA, A_XBLK,
-       A_WP, A_W1, A_LW, A_H0, A_H1, A_DCNT, A_LLGF, A_ASUM, A_BST, A_BK_LLGF, A_BK_RP, A_BK_RT, A_N };
+       A_WP, A_W1, A_LW, A_H0, A_H1, A_DCNT, A_LLGF, A_ASUM, A_BST, A_BK_LLGF, A_BK_RP, A_BK_RT, A_RS, A_N };
 
 // a pair of doubles read with one 16-byte access (the two pass tables, interleaved)
 struct alignas(16) SbD2 { double a, b; };
@@ -111,6 +120,11 @@ struct SbPlace {
     unsigned smem_bytes;         // total dynamic shared memory
     int xblk_rows;               // objects per CTA block cached in A_XBLK (0 = not cached)
     int alias_w;                 // every chain has prior temperature 1: wp == w1 == wq, stored once
+    // tiled passes: the per-combo pass tables of the whole problem do not fit in shared memory; A_TAB0 is
+    // then a tile buffer of `tile_doubles` doubles in shared memory that holds the tables of a few combos
+    // at a time (sb_core.cuh: tiled_pass), and nothing of it lives in the HBM slice
+    int tiled;
+    unsigned tile_doubles;
 };
 
 struct SbSlot {

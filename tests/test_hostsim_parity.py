@@ -111,3 +111,33 @@ def test_emulated_lockstep_lane_per_object_pass(lib, env):
     parity.philox_lockstep(prob, st0, cfgs, 150, lib=lib, team=2)
     env["SB_HOSTSIM_SMEM"] = str(24 * 1024)          # and with the tables in the HBM slice
     parity.philox_lockstep(prob, st0, cfgs, 80, lib=lib, team=1)
+
+
+class _ClusterHeavy(ChainConfig):
+    """mostly gibbsish grow / shrink, wide and jump steps: the operators with passes over many objects"""
+
+    def op_weight_vector(self, n_clusters):
+        import numpy as np
+        w = np.array([0.02, 0.02, 0.02, 0.1, 0.3, 0.2, 0.2, 0.05, 0.05, 0.04])
+        return w / w.sum()
+
+
+@pytest.mark.parametrize("team,block,pairs", [(1, 32, True), (1, 64, False), (2, 32, True), (5, 32, False), (3, 64, True)])
+def test_emulated_lockstep_tiled_passes(lib, env, team, block, pairs):
+    """the pass tables do not fit in shared memory as a whole (BASELINE configs 4 / 5): objects in
+    combo order, tables built tile by tile in shared memory, ratio form for AlterCluster, dual
+    tables for the wide operator and the jump; one or several lanes per object"""
+    import ctypes
+    env["SB_HOSTSIM_TILED"] = "1"
+    env["SB_HOSTSIM_BLOCK"] = str(block)
+    if not pairs:
+        env["SB_NO_PAIRS"] = "1"       # single-feature ratio tables (what problems with more than 15 states use)
+    prob, _ = synth.make_problem(N=110, F=21, S=4, K=3, n_fam=5, seed=31, max_size=60, jagged_states=True)
+    cfgs = [_ClusterHeavy(seed=700), _ClusterHeavy(temperature=1.3, prior_temperature=1.15, seed=701)]
+    st0 = [synth.initial_state(prob, seed=45 + i, objects_per_cluster=25) for i in range(2)]
+    lib.sb_hostsim_tiled_calls.restype = ctypes.c_long
+    before = [lib.sb_hostsim_tiled_calls(k) for k in range(4)]
+    parity.philox_lockstep(prob, st0, cfgs, 150, lib=lib, team=team)
+    after = [lib.sb_hostsim_tiled_calls(k) for k in range(4)]
+    ran = [a > b for a, b in zip(after, before)]
+    assert ran[1] and ran[2] and ran[3 if pairs else 0] and not ran[0 if pairs else 3], (before, after)   # alter, wide and jump all ran tiled

@@ -12,7 +12,7 @@ NPH = 48
 NAMES = {1: "op choice", 2: "grow_candidates", 20: "build_tables", 21: "pass (batch)", 4: "team_pick", 5: "cand sizes/pre-open",
          6: "proposal_open", 7: "R1 remove", 8: "R2 draw", 9: "R3 add+sum", 10: "proposal_rows", 11: "geo", 13: "bwd team_sum",
          14: "subset", 15: "G1", 16: "G delta+sum", 17: "G2", 18: "jump fwd", 19: "jump bwd+sum", 22: "weights loop",
-         23: "weight_tables", 24: "sp+wp", 29: "op tail", 30: "posterior+MH", 31: "commit/close"}
+         23: "weight_tables", 24: "sp+wp", 32: "tile build", 33: "tile pass", 34: "ratio rows", 29: "op tail", 30: "posterior+MH", 31: "commit/close"}
 team, nsteps = int(sys.argv[1]), int(sys.argv[2])
 shape = sys.argv[3] if len(sys.argv) > 3 else "c2"
 if shape == "c4":      # config 4: 5000 x 200 x 6, many chains per GPU
