@@ -29,6 +29,8 @@
  *                        operators (sbayes/sampling/operators.py:423-1827)
  *   sb_posterior         MCMCChain._ll / _prior and Sample.last_lh / last_prior
  *                        (sbayes/sampling/mcmc_chain.py:87,108)
+ *   sb_posteriors / sb_set_temperatures   the scalars swap_chains reads and the temperatures it exchanges,
+ *                        for all chains of the ctx in one call (sbayes/mcmc_setup.py:263-269,389-403)
  *   sb_op_stats          Operator.accepts / rejects / step_times (sbayes/sampling/operators.py:278-293)
  *   sb_swap              swap_chains (sbayes/mcmc_setup.py:365-418) over the chains of one ctx
  *   sb_swap_scalars      the same decision procedure on host scalars (no ctx): used when the
@@ -120,6 +122,8 @@ int sb_chain_config(sb_ctx *ctx, int chain, const sb_chain_cfg *cfg);
 int sb_set_state(sb_ctx *ctx, int chain, const int32_t *cluster_of, const float *W, const uint8_t *src,
                  int64_t i_step);
 int sb_get_state(sb_ctx *ctx, int chain, int32_t *cluster_of, float *W, uint8_t *src, int32_t *counts);
+int sb_posteriors(sb_ctx *ctx, sb_posterior_t *out /* [n_chains] */);   /* sb_posterior of every chain, one copy */
+int sb_set_temperatures(sb_ctx *ctx, const double *temps, const double *prior_temps);   /* [n_chains] each */
 int sb_eval(sb_ctx *ctx, int chain, sb_posterior_t *out);          /* full uncached evaluation */
 int sb_posterior(sb_ctx *ctx, int chain, sb_posterior_t *out);     /* cached values of the current state */
 /* Stand-alone full evaluation of EVERY chain of the ctx (HBM-bound statistics pass + terms):

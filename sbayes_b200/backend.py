@@ -62,7 +62,7 @@ EXPORTS = ["sb_create", "sb_destroy", "sb_last_error", "sb_chain_config", "sb_se
            "sb_posterior", "sb_run", "sb_run_async", "sb_sync", "sb_op_stats", "sb_swap", "sb_get_slots",
            "sb_set_slots", "sb_counts_rebuild_mma", "sb_counts_rebuild_hist", "sb_info", "sb_stream",
            "sb_eval_batch", "sb_eval_stats", "sb_eval_terms", "sb_stats_buffer", "sb_eval_set_mode", "sb_obs_loglik",
-           "sb_swap_scalars", "sb_clock_khz"]
+           "sb_swap_scalars", "sb_clock_khz", "sb_posteriors", "sb_set_temperatures"]
 
 
 def _bind(lib):
@@ -77,6 +77,8 @@ def _bind(lib):
     lib.sb_get_state.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.sb_eval.argtypes = [vp, i32, C.POINTER(_Posterior)]
     lib.sb_posterior.argtypes = [vp, i32, C.POINTER(_Posterior)]
+    lib.sb_posteriors.argtypes = [vp, vp]
+    lib.sb_set_temperatures.argtypes = [vp, vp, vp]
     lib.sb_run.argtypes = [vp, i64, C.POINTER(_Tape), vp]
     lib.sb_run_async.argtypes = [vp, i64]
     lib.sb_sync.argtypes = [vp]
@@ -301,6 +303,17 @@ class DeviceContext:
         out = _Posterior()
         self._ck(self.lib.sb_posterior(self.h, chain, C.byref(out)))
         return {k: getattr(out, k) for k, _ in _Posterior._fields_}
+
+    def posteriors(self) -> list:
+        """cached posterior terms of every chain (one device-to-host copy)"""
+        out = (_Posterior * self.n_chains)()
+        self._ck(self.lib.sb_posteriors(self.h, C.cast(out, C.c_void_p)))
+        return self._posts(out)
+
+    def set_temperatures(self, temps, prior_temps):
+        t, tp = np.ascontiguousarray(temps, np.float64), np.ascontiguousarray(prior_temps, np.float64)
+        assert t.shape == (self.n_chains,) and tp.shape == (self.n_chains,)
+        self._ck(self.lib.sb_set_temperatures(self.h, _ptr(t), _ptr(tp)))
 
     def run(self, n_steps: int, tape: Optional[dict] = None, records: bool = False):
         """Advance every chain by n_steps.  `tape` = dict(vals, off, len, wide_rows) replays

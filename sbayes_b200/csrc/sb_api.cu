@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <map>
 #include <functional>
+#include <cstddef>
 
 // the step kernel, instantiated for up to 4 and up to 8 mixture components (the loops over
 // components are unrolled to that width; the narrow one is what the reference's configs need)
@@ -58,6 +59,8 @@ struct sb_ctx {
     SbSlot *d_slots = nullptr;
     unsigned long long *d_bars = nullptr;
     double *d_tred = nullptr;
+    double *d_post_all = nullptr;        // [n_chains, 8] the post blocks of all states, one allocation
+    std::vector<int> h_slot_state;       // host mirror of SbSlot::state (changed only by sb_swap / sb_set_slots)
     uint8_t *d_src_tmp = nullptr;
     int32_t *d_counts_tmp = nullptr;
     // stand-alone evaluation (sb_eval.cuh): the int32 statistics of all states are one block
@@ -482,6 +485,9 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
     c->h_states.resize(n_chains);
     c->stats_stride = (nG + nH + (size_t)K + 3) & ~(size_t)3;
     TRY(mk(c, &c->d_stats, c->stats_stride * (size_t)n_chains));
+    TRY(mk(c, &c->d_post_all, (size_t)n_chains * 8));
+    c->h_slot_state.resize(n_chains);
+    for (int i = 0; i < n_chains; i++) c->h_slot_state[i] = i;
     for (int i = 0; i < n_chains; i++) {
         SbShared &s = c->h_states[i];
         TRY(mk(c, &s.cluster_of, N)); TRY(mk(c, &s.W, (size_t)F * C));
@@ -489,7 +495,7 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
         TRY(mk(c, &s.osel, N));
         s.counts = c->d_stats + (size_t)i * c->stats_stride; s.sizes = s.counts + nG; s.H = s.sizes + K;   // counts | sizes | H
         TRY(mk(c, &s.list_a, N)); TRY(mk(c, &s.list_b, N)); TRY(mk(c, &s.flag_a, N)); TRY(mk(c, &s.flag_b, N));
-        TRY(mk(c, &s.post, 8));
+        s.post = c->d_post_all + (size_t)i * 8;
     }
     TRY(mk(c, &c->d_rep, c->rep_alloc * (size_t)c->grid));
     TRY(mk(c, &c->d_states, n_chains)); TRY(h2d(c, c->d_states, c->h_states.data(), sizeof(SbShared) * n_chains));
@@ -754,7 +760,39 @@ SB_API int sb_set_slots(sb_ctx *c, const int32_t *state_of_slot) {
         if (s < 0 || s >= c->n_chains || seen[s]) return fail(c, "state_of_slot must be a permutation");
         seen[s] = 1;
     }
-    for (int i = 0; i < c->n_chains; i++) TRY(h2d(c, &c->d_slots[i].state, &state_of_slot[i], sizeof(int)));
+    for (int i = 0; i < c->n_chains; i++) { TRY(h2d(c, &c->d_slots[i].state, &state_of_slot[i], sizeof(int))); c->h_slot_state[i] = state_of_slot[i]; }
+    return 0;
+}
+
+// cached posterior terms of EVERY chain (by slot) in one device-to-host copy: what the MC3 swap reads
+// between two launches (sbayes/mcmc_setup.py:389-390)
+SB_API int sb_posteriors(sb_ctx *c, sb_posterior_t *out) {
+    TRY(check_chain(c, 0));
+    std::vector<double> post((size_t)c->n_chains * 8);
+    TRY(d2h(c, post.data(), c->d_post_all, sizeof(double) * post.size()));
+    for (int i = 0; i < c->n_chains; i++) {
+        const double *p = &post[(size_t)c->h_slot_state[i] * 8];
+        out[i].ll = p[0]; out[i].size_prior = p[1]; out[i].geo_prior = p[2]; out[i].weights_prior = p[3]; out[i].source_prior = p[4];
+        out[i].prior = p[1] + p[2] + p[3] + p[4];
+    }
+    return 0;
+}
+
+// new temperatures for every chain (an accepted MC3 swap across GPUs exchanges temperatures, not states):
+// stream-ordered copies of 16 bytes per chain, no host synchronisation
+SB_API int sb_set_temperatures(sb_ctx *c, const double *temps, const double *prior_temps) {
+    TRY(check_chain(c, 0));
+    for (int i = 0; i < c->n_chains; i++) {
+        if (!(temps[i] > 0) || !(prior_temps[i] > 0)) return fail(c, "temperatures must be positive");
+        if (c->h_cfg[i].temperature == temps[i] && c->h_cfg[i].prior_temperature == prior_temps[i]) continue;
+        c->h_cfg[i].temperature = temps[i]; c->h_cfg[i].prior_temperature = prior_temps[i];
+#ifdef SB_HOSTSIM
+        c->d_slots[i].cfg.temperature = temps[i]; c->d_slots[i].cfg.prior_temperature = prior_temps[i];
+#else
+        static_assert(offsetof(sb_chain_cfg, prior_temperature) == 8, "temperature pair must be adjacent");
+        CK(cudaMemcpyAsync(&c->d_slots[i].cfg.temperature, &c->h_cfg[i].temperature, 16, cudaMemcpyHostToDevice, c->stream));
+#endif
+    }
     return 0;
 }
 
@@ -836,6 +874,7 @@ SB_API int sb_swap(sb_ctx *c, int attempts, int only_neighbours, uint64_t seed, 
                     sas.data(), nullptr, &acc)) return fail(c, "swap failed");
     for (int i = 0; i < n; i++) {
         if (sas[i] != slots[i].state) TRY(h2d(c, &c->d_slots[i].state, &sas[i], sizeof(int)));
+        c->h_slot_state[i] = sas[i];
         if (state_of_slot) state_of_slot[i] = sas[i];
     }
     if (n_accepted) *n_accepted = acc;

@@ -40,11 +40,16 @@ class DeviceMC3:
         self.base_cfg = base_cfg
         self.swap_seed, self.attempts, self.only_neighbours = swap_seed, attempts, only_neighbours
         self.round = 0
-        # global chain g = rank * n_local + local index; initially chain g sits at slot g
+        # global chain g = local index * world + rank (initially chain g sits at slot g): every rank holds
+        # an interleaved sample of the ladder, so the hot chains -- which accept more and do more work per
+        # step -- are spread over the GPUs instead of sitting on the last rank
         self.chain_at_slot = list(range(self.n_total))
         self.ctx = DeviceContext(prob, n_local, device=device, team=team, _lib=_lib)
         self.swap_matrix = np.zeros((self.n_total, self.n_total), np.int64)
         self._apply_temperatures()
+
+    def global_chain(self, local: int) -> int:
+        return local * self.world + self.rank
 
     def _slot_of_chain(self):
         s = [0] * self.n_total
@@ -52,10 +57,13 @@ class DeviceMC3:
             s[ch] = slot
         return s
 
-    def _apply_temperatures(self):
+    def _apply_temperatures(self, first: bool = True):
         soc = self._slot_of_chain()
-        for l in range(self.n_local):
-            g = self.rank * self.n_local + l
+        gl = [self.global_chain(l) for l in range(self.n_local)]
+        if not first:       # after a swap only the temperatures move: one call, no host synchronisation
+            self.ctx.set_temperatures([float(self.temps[soc[g]]) for g in gl], [float(self.prior_temps[soc[g]]) for g in gl])
+            return
+        for l, g in enumerate(gl):
             cfg = replace(self.base_cfg, temperature=float(self.temps[soc[g]]),
                           prior_temperature=float(self.prior_temps[soc[g]]), seed=self.base_cfg.seed + g)
             self.ctx.configure(l, cfg)
@@ -65,11 +73,7 @@ class DeviceMC3:
             self.ctx.set_state(l, st, i_step)
 
     def local_scalars(self) -> np.ndarray:
-        out = np.zeros((self.n_local, 2))
-        for l in range(self.n_local):
-            p = self.ctx.posterior(l)
-            out[l] = (p["ll"], p["prior"])
-        return out
+        return np.array([(p["ll"], p["prior"]) for p in self.ctx.posteriors()], dtype=np.float64).reshape(self.n_local, 2)
 
     def gather_scalars(self, local: np.ndarray) -> np.ndarray:
         if self.world == 1:
@@ -80,7 +84,8 @@ class DeviceMC3:
         t = torch.from_numpy(np.ascontiguousarray(local)).to(dev).reshape(-1)
         out = torch.empty(self.world * t.numel(), dtype=t.dtype, device=dev)
         dist.all_gather_into_tensor(out, t)
-        return out.cpu().numpy().reshape(self.n_total, 2)
+        # rank-major order of the collective -> global chain order (g = local * world + rank)
+        return out.cpu().numpy().reshape(self.world, self.n_local, 2).transpose(1, 0, 2).reshape(self.n_total, 2)
 
     def round_trip(self, swap_interval: int):
         """One MC3 round: `swap_interval` steps on every local chain, then the swap."""
@@ -98,7 +103,7 @@ class DeviceMC3:
         for i, j in acc:
             self.swap_matrix[i, j] += 1
         if acc:
-            self._apply_temperatures()
+            self._apply_temperatures(first=False)
         return acc
 
     def cold_chain(self) -> int:

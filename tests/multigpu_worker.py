@@ -56,7 +56,7 @@ def main():
     def ladder(r, w):
         n_local = n_total // w
         mc3 = DeviceMC3(prob, n_local, ChainConfig(seed=500), dT=0.3, dTp=0.1, swap_seed=11, rank=r, world=w, device=local)
-        mc3.set_states(sts[r * n_local:(r + 1) * n_local])
+        mc3.set_states([sts[mc3.global_chain(l)] for l in range(n_local)])      # chain g = local * world + rank
         acc = [mc3.round_trip(40) for _ in range(5)]
         post = mc3.local_scalars()
         fin = [mc3.ctx.get_state(c) for c in range(n_local)]
@@ -66,7 +66,7 @@ def main():
     acc1, post1, fin1 = ladder(0, 1)
     assert acc == acc1, "swap decisions differ between the split and the single-GPU ladder"
     for l in range(n_total // world):
-        g = rank * (n_total // world) + l
+        g = l * world + rank
         assert np.array_equal(post[l], post1[g])
         assert np.array_equal(fin[l].cluster_of, fin1[g].cluster_of) and np.array_equal(fin[l].src, fin1[g].src)
     dist.barrier()

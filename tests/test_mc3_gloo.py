@@ -26,7 +26,7 @@ def _run_ladder(lib, prob, states, cfg, rank, world, rounds=4, interval=25):
     from sbayes_b200.mc3 import DeviceMC3
     n_local = 4 // world
     mc3 = DeviceMC3(prob, n_local, cfg, dT=0.4, dTp=0.2, swap_seed=17, rank=rank, world=world, _lib=lib)
-    mc3.set_states(states[rank * n_local:(rank + 1) * n_local])
+    mc3.set_states([states[mc3.global_chain(l)] for l in range(n_local)])      # chain g = local * world + rank
     log = []
     for _ in range(rounds):
         log.append(mc3.round_trip(interval))
@@ -72,7 +72,7 @@ def test_two_rank_ladder_equals_single_process():
         assert res[r]["acc"] == single["acc"] and res[r]["slots"] == single["slots"]
         assert np.array_equal(res[r]["swaps"], single["swaps"])
         for l in range(2):
-            g = r * 2 + l
+            g = l * 2 + r
             assert np.array_equal(res[r]["cluster_of"][l], single["cluster_of"][g])
             assert np.array_equal(res[r]["src"][l], single["src"][g])
             assert np.array_equal(res[r]["post"][l], single["post"][g])
