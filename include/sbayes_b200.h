@@ -18,6 +18,9 @@
  *                        (sbayes/sampling/state.py:492-552, sbayes/sampling/counts.py:35-52)
  *   sb_get_state         reading Sample.clusters/weights/source/feature_counts
  *                        (sbayes/sampling/loggers.py:157-301,426-442)
+ *   sb_export_samples    the same for several chains in one call, plus the values of the ModelCache nodes the
+ *                        loggers read: cluster_size_prior, geo_prior[K], source_prior[N], weights_prior,
+ *                        group_likelihoods (sbayes/sampling/state.py:396-449, loggers.py:249-252)
  *   sb_eval              Model.likelihood(sample, caching=False) + Model.prior(sample,
  *                        caching=False) (sbayes/model/model.py:47-51,
  *                        sbayes/model/likelihood.py:47-101, sbayes/model/prior.py:74-88)
@@ -31,6 +34,7 @@
  *                        (sbayes/sampling/mcmc_chain.py:87,108)
  *   sb_posteriors / sb_set_temperatures   the scalars swap_chains reads and the temperatures it exchanges,
  *                        for all chains of the ctx in one call (sbayes/mcmc_setup.py:263-269,389-403)
+ *   sb_gibbs_sweep       GibbsSampleSource._propose with ObjectSelector.ALL (sbayes/sampling/operators.py:496-574)
  *   sb_op_stats          Operator.accepts / rejects / step_times (sbayes/sampling/operators.py:278-293)
  *   sb_swap              swap_chains (sbayes/mcmc_setup.py:365-418) over the chains of one ctx
  *   sb_swap_scalars      the same decision procedure on host scalars (no ctx): used when the
@@ -114,6 +118,18 @@ typedef struct sb_posterior {
     double ll, prior, size_prior, geo_prior, weights_prior, source_prior;
 } sb_posterior_t;
 
+/* host buffers of sb_export_samples for n chains; any pointer may be NULL */
+typedef struct sb_sample_out {
+    int32_t *cluster_of;      /* [n, N] */
+    float *W;                 /* [n, F, C] */
+    uint8_t *src;             /* [n, N, F] */
+    int32_t *counts;          /* [n, G_tot, F, S] */
+    double *post;             /* [n, 8] {ll, size prior, geo prior, weights prior, source prior, i_step, 0, 0} */
+    double *group_ll;         /* [n, G_tot] ModelCache.group_likelihoods, stacked like the counts */
+    double *geo_prior;        /* [n, K]     ModelCache.geo_prior */
+    double *source_prior;     /* [n, N]     ModelCache.source_prior */
+} sb_sample_out;
+
 int sb_create(const sb_problem_desc *desc, int device, int n_chains, int team_ctas, sb_ctx **out);
 void sb_destroy(sb_ctx *ctx);
 const char *sb_last_error(const sb_ctx *ctx);       /* ctx may be NULL: error of the last failed sb_create */
@@ -124,6 +140,7 @@ int sb_set_state(sb_ctx *ctx, int chain, const int32_t *cluster_of, const float 
 int sb_get_state(sb_ctx *ctx, int chain, int32_t *cluster_of, float *W, uint8_t *src, int32_t *counts);
 int sb_posteriors(sb_ctx *ctx, sb_posterior_t *out /* [n_chains] */);   /* sb_posterior of every chain, one copy */
 int sb_set_temperatures(sb_ctx *ctx, const double *temps, const double *prior_temps);   /* [n_chains] each */
+int sb_export_samples(sb_ctx *ctx, int32_t n, const int32_t *chains, const sb_sample_out *out);   /* batched sb_get_state + cache-node values */
 int sb_eval(sb_ctx *ctx, int chain, sb_posterior_t *out);          /* full uncached evaluation */
 int sb_posterior(sb_ctx *ctx, int chain, sb_posterior_t *out);     /* cached values of the current state */
 /* Stand-alone full evaluation of EVERY chain of the ctx (HBM-bound statistics pass + terms):
@@ -141,6 +158,12 @@ int sb_eval_terms(sb_ctx *ctx, int64_t n_global, sb_posterior_t *out, float *ms)
  * sbayes/sampling/conditionals.py:300-367); obj_ll_out [n_chains, N] / sums_out [n_chains] = sums
  * of log lh per object / chain.  Any output may be NULL. */
 int sb_obs_loglik(sb_ctx *ctx, float *lh_out, double *obj_ll_out, double *sums_out, float *ms);
+/* Full-sweep source Gibbs of every chain (GibbsSampleSource over ALL objects, sbayes/sampling/operators.py:
+ * 496-574; initializer: sbayes/sampling/initializers.py:285-310).  mode 0: resample and commit the source of every
+ * observation (Philox draws (chain seed, step)), log_q_out[n_chains] = sum log q[new], n_changed_out[n_chains];
+ * mode 1: log_q_out = sum log q[previous sources] under the current counts (log_q_back after a mode-0 sweep);
+ * mode 2: the same for the committed sources.  Outputs may be NULL. */
+int sb_gibbs_sweep(sb_ctx *ctx, uint64_t step, int mode, double *log_q_out, int64_t *n_changed_out, float *ms);
 int sb_stats_buffer(sb_ctx *ctx, uint64_t *dev_ptr, int64_t *n_int32, int64_t *stride, int64_t *layout3);
 int sb_run(sb_ctx *ctx, int64_t n_steps, const sb_tape *tape, sb_step_record *records);
 int sb_run_async(sb_ctx *ctx, int64_t n_steps);                     /* enqueue only; sb_sync waits */

@@ -410,6 +410,41 @@ def source_posterior(prob: Problem, st: ChainState, S: np.ndarray, cfg: ChainCon
     return normalize_last(ell ** (1.0 / T) * w ** (1.0 / Tp))
 
 
+def gibbs_sweep(prob: Problem, st: ChainState, cfg: ChainConfig, step: int, block: int = 512):
+    """GibbsSampleSource._propose with ObjectSelector.ALL (operators.py:496-552): every source of
+    every object resampled from its conditional given the CURRENT counts; the uniforms are the
+    Philox stream (cfg.seed, step, SITE_GIBBS, o * ceil(F/2) + f // 2), two features per call.  Returns (new state with rebuilt counts,
+    log_q, log_q_back, number of reassigned observations)."""
+    from .draws import PhiloxDraws, SITE_GIBBS
+    from . import philox
+    d = PhiloxDraws(cfg.seed)
+    d.begin_step(step)
+    if st.counts is None:
+        st = ChainState(st.cluster_of, st.W, st.src, M.rebuild_counts(prob, st))
+    new_src = np.empty_like(st.src)
+    log_q = 0.0
+    for a in range(0, prob.N, block):
+        S = np.arange(a, min(prob.N, a + block))
+        p = source_posterior(prob, st, S, cfg)
+        # one Philox call per pair of adjacent features: words 0,1 -> even feature, words 2,3 -> odd feature
+        hF = (prob.F + 1) // 2
+        idx = (S[:, None].astype(np.int64) * hF + (np.arange(prob.F)[None, :] // 2)).reshape(-1)
+        w = philox.words(d.seed, d.step, SITE_GIBBS, 0, idx)
+        odd = np.tile(np.arange(prob.F) % 2 == 1, len(S))
+        u = np.where(odd, philox.u01_double(w[2], w[3]), philox.u01_double(w[0], w[1])).reshape(len(S), prob.F)
+        new = sample_sources(p, u, prob.na[S])
+        new_src[S] = new
+        log_q += log_prob_of(p, new)
+    st_new = ChainState(st.cluster_of.copy(), st.W.copy(), new_src, None)
+    st_new.counts = M.rebuild_counts(prob, st_new)
+    log_q_back = 0.0
+    for a in range(0, prob.N, block):
+        S = np.arange(a, min(prob.N, a + block))
+        log_q_back += log_prob_of(source_posterior(prob, st_new, S, cfg), st.src[S])
+    n_changed = int(np.count_nonzero((new_src != st.src) & ~prob.na))
+    return st_new, log_q, log_q_back, n_changed
+
+
 def select_source_subset(prob: Problem, st: ChainState, draws, groups_mode: bool) -> np.ndarray:
     """select_object_subset (operators.py:461-494); returns sorted object indices."""
     N = prob.N

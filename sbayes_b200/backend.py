@@ -49,6 +49,11 @@ class _Tape(C.Structure):
                 ("n_vals", C.c_int64)]
 
 
+class _SampleOut(C.Structure):
+    _fields_ = [("cluster_of", C.c_void_p), ("W", C.c_void_p), ("src", C.c_void_p), ("counts", C.c_void_p), ("post", C.c_void_p),
+                ("group_ll", C.c_void_p), ("geo_prior", C.c_void_p), ("source_prior", C.c_void_p)]
+
+
 class _Posterior(C.Structure):
     _fields_ = [("ll", C.c_double), ("prior", C.c_double), ("size_prior", C.c_double), ("geo_prior", C.c_double),
                 ("weights_prior", C.c_double), ("source_prior", C.c_double)]
@@ -62,7 +67,8 @@ EXPORTS = ["sb_create", "sb_destroy", "sb_last_error", "sb_chain_config", "sb_se
            "sb_posterior", "sb_run", "sb_run_async", "sb_sync", "sb_op_stats", "sb_swap", "sb_get_slots",
            "sb_set_slots", "sb_counts_rebuild_mma", "sb_counts_rebuild_hist", "sb_info", "sb_stream",
            "sb_eval_batch", "sb_eval_stats", "sb_eval_terms", "sb_stats_buffer", "sb_eval_set_mode", "sb_obs_loglik",
-           "sb_swap_scalars", "sb_clock_khz", "sb_posteriors", "sb_set_temperatures"]
+           "sb_swap_scalars", "sb_clock_khz", "sb_posteriors", "sb_set_temperatures", "sb_gibbs_sweep",
+           "sb_export_samples"]
 
 
 def _bind(lib):
@@ -77,6 +83,8 @@ def _bind(lib):
     lib.sb_get_state.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.sb_eval.argtypes = [vp, i32, C.POINTER(_Posterior)]
     lib.sb_posterior.argtypes = [vp, i32, C.POINTER(_Posterior)]
+    lib.sb_gibbs_sweep.argtypes = [vp, u64, i32, vp, vp, vp]
+    lib.sb_export_samples.argtypes = [vp, i32, vp, C.POINTER(_SampleOut)]
     lib.sb_posteriors.argtypes = [vp, vp]
     lib.sb_set_temperatures.argtypes = [vp, vp, vp]
     lib.sb_run.argtypes = [vp, i64, C.POINTER(_Tape), vp]
@@ -245,6 +253,51 @@ class DeviceContext:
         self._ck(self.lib.sb_get_state(self.h, chain, _ptr(co), _ptr(W), _ptr(src), _ptr(counts)))
         return ChainState(co, W, src, counts)
 
+    def _host_buffer(self, shape, dtype):
+        """pinned host memory when torch sees a GPU (asynchronous device-to-host copies), plain numpy otherwise"""
+        try:
+            import torch
+            if torch.cuda.is_available():
+                return torch.empty(tuple(shape), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True).numpy()
+        except Exception:
+            pass
+        return np.empty(shape, dtype)
+
+    def export_samples(self, chains: Optional[Sequence[int]] = None, src: bool = True, counts: bool = True, caches: bool = True) -> list:
+        """The committed states of several chains in ONE device round trip (`sb_export_samples`): a list of dicts
+        {"state": ChainState, "post": {...}, "group_ll" [G_tot], "geo_prior" [K], "source_prior" [N], "i_step"}
+        -- the cache-node values are what the reference's loggers read from a Sample (loggers.py:249-252)."""
+        p = self.prob
+        chains = list(range(self.n_chains)) if chains is None else [int(c) for c in chains]
+        n = len(chains)
+        key = (n, src, counts, caches)
+        if getattr(self, "_exp_key", None) != key:          # the (pinned) buffers are reused from call to call
+            B = self._host_buffer
+            self._exp = dict(cluster_of=B((n, p.N), np.int32), W=B((n, p.F, p.C), np.float32), post=B((n, 8), np.float64),
+                             src=B((n, p.N, p.F), np.uint8) if src else None,
+                             counts=B((n, p.G_tot, p.F, p.S), np.int32) if counts else None,
+                             group_ll=B((n, p.G_tot), np.float64) if caches else None,
+                             geo_prior=B((n, p.K), np.float64) if caches else None,
+                             source_prior=B((n, p.N), np.float64) if caches else None)
+            self._exp_key = key
+        b = self._exp
+        o = _SampleOut()
+        for k in ("cluster_of", "W", "src", "counts", "post", "group_ll", "geo_prior", "source_prior"):
+            setattr(o, k, _ptr(b[k]))
+        ch = np.ascontiguousarray(chains, np.int32)
+        self._ck(self.lib.sb_export_samples(self.h, n, _ptr(ch), C.byref(o)))
+        out = []
+        for i in range(n):
+            post = b["post"][i]
+            st = ChainState(b["cluster_of"][i].copy(), b["W"][i].copy(), b["src"][i].copy() if src else None,
+                            b["counts"][i].copy() if counts else None)
+            out.append(dict(state=st, i_step=int(post[5]),
+                            post=dict(ll=float(post[0]), size_prior=float(post[1]), geo_prior=float(post[2]), weights_prior=float(post[3]),
+                                      source_prior=float(post[4]), prior=float(post[1] + post[2] + post[3] + post[4])),
+                            group_ll=b["group_ll"][i].copy() if caches else None, geo_prior=b["geo_prior"][i].copy() if caches else None,
+                            source_prior=b["source_prior"][i].copy() if caches else None))
+        return out
+
     def eval(self, chain: int) -> dict:
         """Full uncached evaluation (count rebuild + likelihood + all prior terms)."""
         out = _Posterior()
@@ -292,6 +345,17 @@ class DeviceContext:
         sums, ms = np.empty(self.n_chains, np.float64), np.zeros(1, np.float32)
         self._ck(self.lib.sb_obs_loglik(self.h, _ptr(lh), _ptr(ob), _ptr(sums), _ptr(ms)))
         return lh, ob, sums, float(ms[0])
+
+    def gibbs_sweep(self, seed=None, step: int = 1, mode: str = "draw", full: bool = False):
+        """Full-sweep source Gibbs of every chain (GibbsSampleSource over ALL objects).  mode "draw" resamples
+        and commits every source (draws addressed by (chain seed, `step`)), "score_previous" / "score" return
+        sum log q of the previous / committed sources under the current counts.  Returns the device ms, or with
+        full=True (log_q [n_chains], n_changed [n_chains], ms).  `seed` is accepted for symmetry with the
+        bench helper and offsets `step`."""
+        lq, ch, ms = np.zeros(self.n_chains, np.float64), np.zeros(self.n_chains, np.int64), np.zeros(1, np.float32)
+        st = int(step) + (int(seed) if seed is not None else 0)
+        self._ck(self.lib.sb_gibbs_sweep(self.h, st, {"draw": 0, "score_previous": 1, "score": 2}[mode], _ptr(lq), _ptr(ch), _ptr(ms)))
+        return (lq, ch, float(ms[0])) if full else float(ms[0])
 
     def stats_buffer(self):
         """(device address, int32 elements, per-state stride, (n_counts, n_hist, n_sizes))."""

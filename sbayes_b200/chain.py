@@ -160,16 +160,13 @@ class MCMCChain:
         self._restart = False
 
     def _download(self, template, i_step: int):
-        st = self.ctx.get_state(0)
-        post = self.ctx.posterior(0)
+        # one device round trip: state + the values of the reference's cache nodes (read by
+        # ParametersCSVLogger, loggers.py:157-262) as the device computed them -- no CPU re-evaluation
+        exp = self.ctx.export_samples([0])[0]
+        st, post = exp["state"], exp["post"]
         s = refbridge.sample_from_state(self.prob, self.model, self.data, st, type(template), i_step=i_step,
                                         chain=getattr(template, "chain", 0))
-        # fill the reference's cache nodes (read by ParametersCSVLogger, loggers.py:157-262)
-        self.model.prior(sample=s)
-        if not self.sample_from_prior:
-            self.model.likelihood(sample=s, caching=True)
-        s.last_lh = 0.0 if self.sample_from_prior else post["ll"]
-        s.last_prior = post["prior"]
+        refbridge.fill_cache_from_device(self.prob, s, exp, self.sample_from_prior)
         self._ll = s.last_lh / self.temperature
         self._prior = s.last_prior / self.prior_temperature
         self._uploaded, self._eval = s, post
@@ -281,14 +278,9 @@ class MCMC:
         return ev["ll"]
 
     def _download(self, template, chain: int, i_step: int):
-        st = self.ctx.get_state(chain)
-        post = self.ctx.posterior(chain)
-        s = refbridge.sample_from_state(self.prob, self.model, self.data, st, type(template), i_step=i_step, chain=chain)
-        self.model.prior(sample=s)
-        if not self.sample_from_prior:
-            self.model.likelihood(sample=s, caching=True)
-        s.last_lh = 0.0 if self.sample_from_prior else post["ll"]
-        s.last_prior = post["prior"]
+        exp = self.ctx.export_samples([chain])[0]
+        s = refbridge.sample_from_state(self.prob, self.model, self.data, exp["state"], type(template), i_step=i_step, chain=chain)
+        refbridge.fill_cache_from_device(self.prob, s, exp, self.sample_from_prior)
         self._ll[chain], self._prior[chain] = s.last_lh, s.last_prior
         return s
 

@@ -29,7 +29,7 @@
 #include "sb_counts.cuh"
 #include "sb_eval.cuh"
 using uc4::FixedSmem; using uc4::sb_fixed_smem; using uc4::Draws; using uc4::Philox4; using uc4::philox4x32_10; using uc4::u01_double;
-using uc4::sb_export_kernel;
+using uc4::sb_export_kernel; using uc4::sb_export_samples_kernel;
 
 #ifdef SB_HOSTSIM
 #define SB_API extern "C" __attribute__((visibility("default")))
@@ -59,6 +59,10 @@ struct sb_ctx {
     SbSlot *d_slots = nullptr;
     unsigned long long *d_bars = nullptr;
     double *d_tred = nullptr;
+    double *d_glh_all = nullptr, *d_geo_all = nullptr;   // [n_chains, G_tot], [n_chains, K] export copies, one allocation each
+    SbExport exp_;                       // staging buffers of sb_export_samples (allocated on first use)
+    int exp_ok = 0;
+    int32_t *d_exp_idx = nullptr;
     double *d_post_all = nullptr;        // [n_chains, 8] the post blocks of all states, one allocation
     std::vector<int> h_slot_state;       // host mirror of SbSlot::state (changed only by sb_swap / sb_set_slots)
     uint8_t *d_src_tmp = nullptr;
@@ -77,6 +81,7 @@ struct sb_ctx {
     SbObsPlan oplan;
     float *d_obs_out = nullptr;
     double *d_obs_part = nullptr, *d_obs_ll = nullptr, *d_obs_sums = nullptr;
+    unsigned long long *d_gibbs_changed = nullptr;
     std::vector<void *> allocs;
     sb_stream_t stream = 0;
     std::string err;
@@ -486,6 +491,7 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
     c->stats_stride = (nG + nH + (size_t)K + 3) & ~(size_t)3;
     TRY(mk(c, &c->d_stats, c->stats_stride * (size_t)n_chains));
     TRY(mk(c, &c->d_post_all, (size_t)n_chains * 8));
+    TRY(mk(c, &c->d_glh_all, (size_t)n_chains * P.G_tot)); TRY(mk(c, &c->d_geo_all, (size_t)n_chains * K));
     c->h_slot_state.resize(n_chains);
     for (int i = 0; i < n_chains; i++) c->h_slot_state[i] = i;
     for (int i = 0; i < n_chains; i++) {
@@ -496,6 +502,7 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
         s.counts = c->d_stats + (size_t)i * c->stats_stride; s.sizes = s.counts + nG; s.H = s.sizes + K;   // counts | sizes | H
         TRY(mk(c, &s.list_a, N)); TRY(mk(c, &s.list_b, N)); TRY(mk(c, &s.flag_a, N)); TRY(mk(c, &s.flag_b, N));
         s.post = c->d_post_all + (size_t)i * 8;
+        s.glh = c->d_glh_all + (size_t)i * P.G_tot; s.geo_out = c->d_geo_all + (size_t)i * K;
     }
     TRY(mk(c, &c->d_rep, c->rep_alloc * (size_t)c->grid));
     TRY(mk(c, &c->d_states, n_chains)); TRY(h2d(c, c->d_states, c->h_states.data(), sizeof(SbShared) * n_chains));
@@ -736,6 +743,56 @@ SB_API int sb_get_state(sb_ctx *c, int chain, int32_t *cluster_of, float *W, uin
     }
     if (counts) TRY(d2h(c, counts, s.counts, sizeof(int32_t) * P.G_tot * P.F * P.S));
     return 0;
+}
+
+// Batched sample export: the committed states of `n` chains (chains[] = chain indices) straight into the caller's
+// host buffers -- one gather kernel into staging buffers in the host layout, one asynchronous copy per array,
+// ONE synchronisation.  Besides what sb_get_state returns it delivers what the reference's loggers read from the
+// cache nodes of a Sample (sbayes/sampling/loggers.py:157-262, sbayes/sampling/state.py:396-449): posterior
+// parts, per-group log-likelihoods, per-cluster geo prior, per-object source prior.  Pinned host buffers make
+// the copies truly asynchronous; any pointer of `out` may be NULL.
+SB_API int sb_export_samples(sb_ctx *c, int32_t n, const int32_t *chains, const sb_sample_out *out) {
+    TRY(check_chain(c, 0));
+    if (n <= 0 || n > c->n_chains || !chains || !out) return fail(c, "bad export request");
+    const SbProblem &P = c->P;
+    const size_t N = P.N, F = P.F, C = P.C, nG = (size_t)P.G_tot * F * P.S, nc = c->n_chains;
+    if (!c->exp_ok) {
+        memset(&c->exp_, 0, sizeof(SbExport));
+        TRY(mk(c, &c->exp_.cluster_of, nc * N)); TRY(mk(c, &c->exp_.W, nc * F * C)); TRY(mk(c, &c->exp_.src, nc * N * F));
+        TRY(mk(c, &c->exp_.counts, nc * nG)); TRY(mk(c, &c->exp_.post, nc * 8)); TRY(mk(c, &c->exp_.glh, nc * P.G_tot));
+        TRY(mk(c, &c->exp_.geo, nc * P.K)); TRY(mk(c, &c->exp_.sp_obj, nc * N)); TRY(mk(c, &c->d_exp_idx, nc));
+        c->exp_ok = 1;
+    }
+    std::vector<int32_t> idx(n);
+    for (int i = 0; i < n; i++) {
+        if (chains[i] < 0 || chains[i] >= c->n_chains) return fail(c, "chain index out of range");
+        idx[i] = c->h_slot_state[chains[i]];
+    }
+    TRY(h2d(c, c->d_exp_idx, idx.data(), sizeof(int32_t) * n));
+    SbExport E = c->exp_;
+    E.state_idx = c->d_exp_idx; E.n = n;
+    E.want = (out->cluster_of ? 1u : 0u) | (out->W ? 2u : 0u) | (out->src ? 4u : 0u) | (out->counts ? 8u : 0u) | (out->post ? 16u : 0u) |
+             (out->group_ll ? 32u : 0u) | (out->geo_prior ? 64u : 0u) | (out->source_prior ? 128u : 0u);
+#ifdef SB_HOSTSIM
+    hostsim::launch([&]() { sb_export_samples_kernel(P, c->d_states, E); }, 2 * n, 64, 0);
+#define SB_D2H(dst, srcp, bytes) if (dst) memcpy(dst, srcp, bytes)
+#else
+    const int blocks = std::max(1, std::min(c->n_sm * 4 / n + 1, (int)((N + 7) / 8)));
+    sb_export_samples_kernel<<<dim3(blocks, n), 256, 0, c->stream>>>(P, c->d_states, E);
+    CK(cudaGetLastError());
+#define SB_D2H(dst, srcp, bytes) if (dst) CK(cudaMemcpyAsync(dst, srcp, bytes, cudaMemcpyDeviceToHost, c->stream))
+#endif
+    c->launches++;
+    SB_D2H(out->cluster_of, E.cluster_of, sizeof(int32_t) * n * N);
+    SB_D2H(out->W, E.W, sizeof(float) * n * F * C);
+    SB_D2H(out->src, E.src, (size_t)n * N * F);
+    SB_D2H(out->counts, E.counts, sizeof(int32_t) * n * nG);
+    SB_D2H(out->post, E.post, sizeof(double) * n * 8);
+    SB_D2H(out->group_ll, E.glh, sizeof(double) * n * P.G_tot);
+    SB_D2H(out->geo_prior, E.geo, sizeof(double) * n * P.K);
+    SB_D2H(out->source_prior, E.sp_obj, sizeof(double) * n * N);
+#undef SB_D2H
+    return dev_sync(c);
 }
 
 SB_API int sb_op_stats(sb_ctx *c, int chain, int64_t *accepts, int64_t *rejects, int64_t *cycles) {
@@ -987,6 +1044,73 @@ SB_API int sb_eval_batch(sb_ctx *c, sb_posterior_t *out, float *ms2) {
     return sb_eval_terms(c, 0, out, ms2 ? ms2 + 1 : nullptr);
 }
 
+// per-object partial sums / per-chain sums shared by the observation-likelihood and the Gibbs-sweep kernels
+static int ensure_obs_buffers(sb_ctx *c) {
+    if (c->d_obs_part) return 0;
+    const SbProblem &P = c->P;
+    if (sb_obs_make_plan(P, c->n_chains, c->n_sm, &c->oplan)) return fail(c, "per-tile tables (groups x states x 16 features) do not fit in shared memory");
+    TRY(mk(c, &c->d_obs_part, (size_t)c->n_chains * c->oplan.n_ftiles * P.N));
+    TRY(mk(c, &c->d_obs_ll, (size_t)c->n_chains * P.N)); TRY(mk(c, &c->d_obs_sums, (size_t)c->n_chains));
+    TRY(mk(c, &c->d_gibbs_changed, (size_t)c->n_chains));
+#ifndef SB_HOSTSIM
+    CK(cudaFuncSetAttribute((const void *)sb_obs_lik_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->oplan.smem));
+    CK(cudaFuncSetAttribute((const void *)sb_gibbs_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->oplan.smem));
+#endif
+    return 0;
+}
+
+// Full-sweep source Gibbs of every chain (GibbsSampleSource with ObjectSelector.ALL,
+// sbayes/sampling/operators.py:496-574; the initializer's use, sbayes/sampling/initializers.py:285-310).
+//   mode 0  resample the source of EVERY observation of every chain from its conditional given the current
+//           counts and weights (draws: Philox (chain seed, step, SITE_GIBBS, o * F + f)); commits the new
+//           sources; log_q_out[chain] = sum log q[new], n_changed_out[chain] = reassigned observations
+//   mode 1  log_q_out = sum log q[previous sources] under the CURRENT counts (the log_q_back of the proposal,
+//           to be called after a mode-0 sweep); mode 2: the same for the committed sources
+// The statistics pass runs first (the tables need the committed counts).  The cached posterior of the chains
+// (sb_posterior) is stale after a mode-0 sweep until the next sb_run / sb_eval.  Outputs may be NULL; ms
+// receives the device time of the sweep kernel + reduction.
+SB_API int sb_gibbs_sweep(sb_ctx *c, uint64_t step, int mode, double *log_q_out, int64_t *n_changed_out, float *ms) {
+    TRY(check_chain(c, 0));
+    if (mode < 0 || mode > 2) return fail(c, "unknown sweep mode");
+    const SbProblem &P = c->P;
+    TRY(ensure_obs_buffers(c));
+    TRY(sb_eval_stats(c, nullptr));
+    SbGibbsArgs G; memset(&G, 0, sizeof G);
+    G.P = P; G.states = c->d_states; G.slots = c->d_slots; G.n_states = c->n_chains; G.plan = c->oplan;
+    G.obj_part = c->d_obs_part; G.n_changed = c->d_gibbs_changed; G.step = step; G.mode = mode;
+    SbObsArgs A; memset(&A, 0, sizeof A);
+    A.P = P; A.states = c->d_states; A.n_states = c->n_chains; A.plan = c->oplan;
+    A.obj_part = c->d_obs_part; A.obj_ll = c->d_obs_ll; A.sums = c->d_obs_sums;
+    const int grid = c->n_chains * c->oplan.n_ftiles * c->oplan.n_oblk;
+    TRY(dev_zero(c, c->d_gibbs_changed, sizeof(unsigned long long) * c->n_chains));
+    TRY(dev_zero(c, c->d_eticket, sizeof(unsigned) * c->n_chains));
+#ifdef SB_HOSTSIM
+    if (ms) *ms = 0.f;
+    hostsim::launch([&]() { sb_gibbs_sweep_kernel(G); }, grid, 64, c->oplan.smem);
+    hostsim::launch([&]() { sb_obs_reduce_kernel(A, c->d_epartial, c->d_eticket); }, c->n_chains * SB_OBS_RPARTS, 64, 1024);
+    if (mode == 0) hostsim::launch([&]() { sb_flip_osel_kernel(c->d_states, c->n_chains, P.N); }, 2, 64, 0);
+#else
+    EvTimer t(c->stream, ms);
+    sb_gibbs_sweep_kernel<<<grid, SB_EVAL_BLOCK, c->oplan.smem, c->stream>>>(G);
+    CK(cudaGetLastError());
+    sb_obs_reduce_kernel<<<c->n_chains * SB_OBS_RPARTS, SB_EVAL_BLOCK, 1024, c->stream>>>(A, c->d_epartial, c->d_eticket);
+    CK(cudaGetLastError());
+    t.stop();
+    if (mode == 0) { sb_flip_osel_kernel<<<c->n_sm * 2, 256, 0, c->stream>>>(c->d_states, c->n_chains, P.N); CK(cudaGetLastError()); }
+#endif
+    c->launches += mode == 0 ? 3 : 2;
+    std::vector<double> sums(c->n_chains);
+    std::vector<unsigned long long> ch(c->n_chains);
+    TRY(d2h(c, sums.data(), c->d_obs_sums, sizeof(double) * c->n_chains));
+    TRY(d2h(c, ch.data(), c->d_gibbs_changed, sizeof(unsigned long long) * c->n_chains));
+    for (int i = 0; i < c->n_chains; i++) {
+        const int s = c->h_slot_state[i];
+        if (log_q_out) log_q_out[i] = sums[s];
+        if (n_changed_out) n_changed_out[i] = (int64_t)ch[s];
+    }
+    return 0;
+}
+
 // Observation likelihood of every chain (LikelihoodLogger._write_sample, sbayes/sampling/
 // loggers.py:354-359; likelihood_per_component_exact, sbayes/sampling/conditionals.py:300-367).
 // Runs the statistics pass first (the tables need the committed counts), then one streaming
@@ -997,15 +1121,8 @@ SB_API int sb_obs_loglik(sb_ctx *c, float *lh_out, double *obj_ll_out, double *s
     TRY(check_chain(c, 0));
     const SbProblem &P = c->P;
     const size_t nNF = (size_t)P.N * P.F;
-    if (!c->d_obs_out) {
-        if (sb_obs_make_plan(P, c->n_chains, c->n_sm, &c->oplan)) return fail(c, "observation-likelihood tables do not fit in shared memory");
-        TRY(mk(c, &c->d_obs_out, nNF * c->n_chains));
-        TRY(mk(c, &c->d_obs_part, (size_t)c->n_chains * c->oplan.n_ftiles * P.N));
-        TRY(mk(c, &c->d_obs_ll, (size_t)c->n_chains * P.N)); TRY(mk(c, &c->d_obs_sums, (size_t)c->n_chains));
-#ifndef SB_HOSTSIM
-        CK(cudaFuncSetAttribute((const void *)sb_obs_lik_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->oplan.smem));
-#endif
-    }
+    TRY(ensure_obs_buffers(c));
+    if (!c->d_obs_out) TRY(mk(c, &c->d_obs_out, nNF * c->n_chains));
     TRY(sb_eval_stats(c, nullptr));
     SbObsArgs A; memset(&A, 0, sizeof A);
     A.P = P; A.states = c->d_states; A.n_states = c->n_chains; A.plan = c->oplan;

@@ -2435,6 +2435,8 @@ SB_KERNEL_BIG sb_run_kernel(const SB_GRID_CONSTANT SbLaunch L) {
             const size_t nG = (size_t)L.P.G_tot * L.P.F * L.P.S;
             for (size_t i = sb_tid(); i < nG; i += sb_nthr()) R.c->st.counts[i] = R.c->rp.counts[i];
             for (int i = sb_tid(); i < L.P.F * L.P.C; i += sb_nthr()) R.c->st.W[i] = R.c->rp.W[i];
+            for (int g = sb_tid(); g < L.P.G_tot; g += sb_nthr()) R.c->st.glh[g] = R.sfp ? 0.0 : R.c->rp.lh[g];
+            for (int k = sb_tid(); k < L.P.K; k += sb_nthr()) R.c->st.geo_out[k] = L.P.geo ? R.c->rp.geo_val[k] : 0.0;
             if (sb_tid() == 0) {
                 R.c->st.post[0] = R.ll; R.c->st.post[1] = R.pr_size; R.c->st.post[2] = R.pr_geo; R.c->st.post[3] = R.pr_w;
                 R.c->st.post[4] = R.pr_src; R.c->st.post[5] = (double)R.i_step;
@@ -2443,6 +2445,52 @@ SB_KERNEL_BIG sb_run_kernel(const SB_GRID_CONSTANT SbLaunch L) {
         // an error seen by ANY CTA of the team (e.g. a bad source byte in its block of objects) is reported
         if (R.err && sb_tid() == 0) slot->err = R.err;
         team_sync(R);
+    }
+}
+
+// Batched sample export (sb_export_samples): the committed state of n chains gathered into staging buffers
+// in the host layout -- source rows unpadded and taken from whichever copy is committed -- plus the
+// per-object source prior (SourcePrior's cache node, sbayes/model/prior.py:596-611:
+// sum_f log w~[o, f, src[o,f]] with w~ = has * W / sum(has * W), normalize_weights likelihood.py:171-190).
+// grid = (blocks, n); one warp per object for the rows.
+SB_KERNEL sb_export_samples_kernel(SbProblem P, const SbShared *states, SbExport E) {
+    const int N = P.N, F = P.F, C = P.C;
+#ifdef SB_HOSTSIM
+    const int j = sb_cta() % E.n, blk = sb_cta() / E.n, nblk = sb_ncta() / E.n;
+#else
+    const int j = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
+#endif
+    const SbShared st = states[E.state_idx[j]];
+    const int t0 = blk * sb_nthr() + sb_tid(), stride = nblk * sb_nthr();
+    const size_t nG = (size_t)P.G_tot * F * P.S;
+    if (E.want & 1u) for (int o = t0; o < N; o += stride) E.cluster_of[(size_t)j * N + o] = st.cluster_of[o];
+    if (E.want & 2u) for (int i = t0; i < F * C; i += stride) E.W[(size_t)j * F * C + i] = st.W[i];
+    if (E.want & 8u) for (size_t i = t0; i < nG; i += stride) E.counts[(size_t)j * nG + i] = st.counts[i];
+    if (E.want & 16u) for (int i = t0; i < 8; i += stride) E.post[(size_t)j * 8 + i] = st.post[i];
+    if (E.want & 32u) for (int g = t0; g < P.G_tot; g += stride) E.glh[(size_t)j * P.G_tot + g] = st.glh[g];
+    if (E.want & 64u) for (int k = t0; k < P.K; k += stride) E.geo[(size_t)j * P.K + k] = st.geo_out[k];
+    if (!(E.want & (4u | 128u))) return;
+    const int wpb = sb_nwarps();
+    for (int o = blk * wpb + sb_warp(); o < N; o += nblk * wpb) {
+        const uint8_t *row = st.src[st.osel[o]] + (size_t)o * P.ldx;
+        const int bits = sb_ldg(P.pat_bits + sb_ldg(P.pat_id + o)), z = st.cluster_of[o] >= 0;
+        double acc = 0.0;
+        for (int f = sb_lane(); f < F; f += 32) {
+            const int c = row[f];
+            if (E.want & 4u) E.src[((size_t)j * N + o) * F + f] = (uint8_t)c;
+            if ((E.want & 128u) && c != SB_NA_U8) {
+                double t1 = 0.0, wc = 0.0;
+                for (int cc = 0; cc < C; cc++) {
+                    const double hw = (cc == 0 ? (double)z : (double)((bits >> cc) & 1)) * (double)st.W[f * C + cc];
+                    t1 += hw; if (cc == c) wc = hw;
+                }
+                acc += log(wc / t1);
+            }
+        }
+        if (E.want & 128u) {
+            acc = warp_sum(acc);
+            if (sb_lane() == 0) E.sp_obj[(size_t)j * N + o] = acc;
+        }
     }
 }
 

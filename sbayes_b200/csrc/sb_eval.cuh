@@ -681,6 +681,210 @@ SB_KERNEL sb_obs_reduce_kernel(const SB_GRID_CONSTANT SbObsArgs A, double *parti
     }
 }
 
+// -----------------------------------------------------------------------------------------
+// full-sweep source Gibbs: GibbsSampleSource over ALL objects (sbayes/sampling/operators.py:496-574,
+// the ObjectSelector.ALL path; used by the initializer, sbayes/sampling/initializers.py:285-310):
+//     q[o,f,c]  ~  l_c[o,f]^(1/T) * w~[o,f,c]^(1/Tp),   l_c = plain table of the group of o in c
+// for every observation of every chain in ONE streaming launch: 3 B per observation (state byte and
+// old source byte read, new source byte written; SURVEY.md 8d GIBBS).  Same decomposition as the
+// observation-likelihood kernel: CTA = (state, feature tile, object block), the tile's tables
+// (l^(1/T) per group row, w~^(1/Tp) per has-pattern) in shared memory, fp64.  The draw of an
+// pair of adjacent features is ONE Philox call addressed by (chain seed, step, SITE_GIBBS, o * ceil(F/2) + f/2):
+// words 0,1 make the uniform of the even feature, words 2,3 that of the odd one (oracle/operators.py: gibbs_sweep
+// mirrors the addressing); the conditional is that of source_posterior in sb_core.cuh.
+//   mode 0  draw: the new sources go to the non-committed copy of the rows (sb_flip_osel_kernel commits
+//           them), obj_part receives log q[new] per object and tile, n_changed the reassigned observations
+//   mode 1  score the NON-committed copy (the previous sources right after a draw) under the current
+//           tables: log_q_back of the proposal
+//   mode 2  score the committed sources
+// -----------------------------------------------------------------------------------------
+struct SbGibbsArgs {
+    SbProblem P;
+    const SbShared *states;
+    const SbSlot *slots;
+    int n_states;
+    SbObsPlan plan;
+    double *obj_part;               // [n_states, n_ftiles, N]
+    unsigned long long *n_changed;  // [n_states]
+    unsigned long long step;
+    int mode;
+};
+
+template <int UC>
+SB_DEV void ev_gibbs_body(const SbGibbsArgs &A) {
+    const SbProblem &P = A.P;
+    const SbObsPlan &pl = A.plan;
+    const int F = P.F, S = P.S, C = P.C, nconf = P.n_conf, N = P.N;
+    int w = sb_cta();
+    const int oblk = w % pl.n_oblk; w /= pl.n_oblk;
+    const int tile = w % pl.n_ftiles; w /= pl.n_ftiles;
+    const int s_idx = w;
+    const SbShared st = A.states[s_idx];
+    double T = 1.0, Tp = 1.0; int sfp = 0; unsigned long long seed = 0;
+    for (int i = 0; i < A.n_states; i++)
+        if (A.slots[i].state == s_idx) { T = A.slots[i].cfg.temperature; Tp = A.slots[i].cfg.prior_temperature; sfp = A.slots[i].cfg.sample_from_prior; seed = A.slots[i].cfg.seed; }
+    const double invT = 1.0 / T, invTp = 1.0 / Tp;
+    const bool unitT = T == 1.0, unitTp = Tp == 1.0;
+    const int ft = pl.ft;
+    const int f0 = tile * ft;
+    const int fv = F - f0 < ft ? F - f0 : ft;
+    const int Cp = ev_odd(C);
+    const int gs = ft * S, hs = ft * Cp;
+    double *lik = (double *)sb_smem();                             // [G_tot][ft][S]  l^(1/T), state index rotated by the feature
+    double *wt = lik + (size_t)P.G_tot * gs;                       // [n_pat*2][ft][Cp] w~^(1/Tp)
+    for (int i = sb_tid(); i < P.G_tot * ft; i += sb_nthr()) {
+        const int g = i / ft, fl = i % ft;
+        if (fl >= fv) continue;
+        const size_t ar = (size_t)ev_arow(P, g) * F + f0 + fl, cr = ((size_t)g * F + f0 + fl) * S;
+        int n = 0;
+        for (int s = 0; s < S; s++) n += st.counts[cr + s];
+        const double rP = 1.0 / (sb_ldg(P.asum + ar) + (double)n);
+        for (int s = 0; s < S; s++) {
+            double l = (sb_ldg(P.alpha + ar * S + s) + (double)st.counts[cr + s]) * rP;
+            if (sfp) l = 1.0;
+            else if (!unitT) l = l > 0.0 ? exp(invT * log(l)) : 0.0;
+            lik[(size_t)g * gs + fl * S + (s + fl) % S] = l;
+        }
+    }
+    for (int i = sb_tid(); i < P.n_pat * 2 * ft; i += sb_nthr()) {
+        const int pz = i / ft, fl = i % ft, z = pz & 1, bits = sb_ldg(P.pat_bits + (pz >> 1));
+        double t1 = 0.0;
+        if (fl < fv) for (int c = 0; c < C; c++) t1 += (c == 0 ? (double)z : (double)((bits >> c) & 1)) * (double)st.W[(f0 + fl) * C + c];
+        for (int c = 0; c < C; c++) {
+            const double hh = c == 0 ? (double)z : (double)((bits >> c) & 1);
+            double a = (fl < fv && t1 > 0.0) ? hh * (double)st.W[(f0 + fl) * C + c] / t1 : 0.0;
+            if (!unitTp) a = pow(a, invTp);
+            wt[(size_t)pz * hs + fl * Cp + c] = a;
+        }
+    }
+    sb_cta_sync();
+    const int lo = oblk * pl.rows_per_blk, hi = lo + pl.rows_per_blk < N ? lo + pl.rows_per_blk : N;
+    // a row of the tile is shared by ft/4 lanes; a lane takes two pairs of ADJACENT features (2 fg, 2 fg + 1) and
+    // (ft/2 + 2 fg, ft/2 + 2 fg + 1): one Philox call serves a pair (words 0,1 -> even feature, words 2,3 -> odd)
+    const int lpr = ft >> 2, rpw = 32 / lpr;
+    const int fg = sb_lane() % lpr, rw = sb_lane() / lpr;
+    int fls[4], rot[4];
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+    for (int j = 0; j < 4; j++) { fls[j] = (j >> 1) * (ft >> 1) + 2 * fg + (j & 1); rot[j] = fls[j] % S; }
+    const int hF = (F + 1) >> 1;                                     // Philox calls per row
+    uint8_t *src0 = st.src[0], *src1 = st.src[1];
+    double *opart = A.obj_part + ((size_t)s_idx * pl.n_ftiles + tile) * N;
+    const uint32_t k0 = (uint32_t)(seed & 0xFFFFFFFFull), k1 = (uint32_t)(seed >> 32);
+    const uint32_t st_lo = (uint32_t)(A.step & 0xFFFFFFFFull), st_hi = (uint32_t)(A.step >> 32);
+    unsigned changed = 0;
+    for (int o0 = lo + sb_warp() * rpw; o0 < hi; o0 += sb_nwarps() * rpw) {
+        const int o = o0 + rw;
+        const bool live = o < hi;
+        int gb[UC];
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+        for (int u = 0; u < UC; u++) gb[u] = -1;
+        double acc = 0.0;
+        if (live) {
+            const int k = st.cluster_of[o];
+            if (k >= 0) gb[0] = k * gs;
+            int pat;
+            if (P.obj_pack) {
+                const uint32_t pk = sb_ldg(P.obj_pack + o);
+                pat = (int)(pk & 255u);
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+                for (int u = 1; u < 4; u++) { const int g = (int)((pk >> (8 * u)) & 255u); if (g != 255) gb[u] = g * gs; }
+            } else {
+                const int combo = sb_ldg(P.combo_id + o);
+                const int32_t *rows = P.combo_rows + (size_t)combo * nconf;
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+                for (int u = 1; u < UC; u++)
+                    if (u <= nconf) { const int g = sb_ldg(rows + u - 1); if (g >= 0) gb[u] = g * gs; }
+                pat = sb_ldg(P.combo_pat + combo);
+            }
+            const double *wrow = wt + (size_t)(pat * 2 + (k >= 0 ? 1 : 0)) * hs;
+            const size_t off = (size_t)o * P.ldx + f0;
+            const int sel = st.osel[o];
+            const uint8_t *xr = P.x + off, *sr = (sel ? src1 : src0) + off;
+            uint8_t *so = (sel ? src0 : src1) + off;
+            double prod = 1.0;
+            uc4::Philox4 ph; ph.w[0] = ph.w[1] = ph.w[2] = ph.w[3] = 0;
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+            for (int j = 0; j < 4; j++) {
+                const int fl = fls[j];
+                if (A.mode == 0 && !(j & 1) && fl < fv)      // the pair's draw: (chain seed, step, SITE_GIBBS, o * ceil(F/2) + f / 2)
+                    ph = uc4::philox4x32_10((uint32_t)((size_t)o * hF + ((f0 + fl) >> 1)), (uint32_t)SITE_GIBBS, st_lo, st_hi, k0, k1);
+                if (fl >= fv) continue;
+                const int x = (int)sb_ldg(xr + fl), c_old = (int)sr[fl];
+                if (x == SB_NA_U8) { if (A.mode == 0) so[fl] = SB_NA_U8; continue; }
+                int xr_ = x + rot[j]; xr_ = xr_ >= S ? xr_ - S : xr_;
+                double q[UC], tot = 0.0;
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+                for (int u = 0; u < UC; u++) {
+                    q[u] = 0.0;
+                    if (u < C) { const double l = gb[u] >= 0 ? lik[gb[u] + fl * S + xr_] : 0.0; q[u] = l * wrow[fl * Cp + u]; tot += q[u]; }
+                }
+                // one division per observation: q = raw * (1 / total); the inverse-CDF test u < cum / last is taken
+                // as u * last < cum (the same decision except within an ulp of a boundary)
+                const double inv = 1.0 / tot;
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+                for (int u = 0; u < UC; u++) if (u < C) q[u] *= inv;
+                int pick;
+                if (A.mode == 0) {
+                    const double uu = (j & 1) ? uc4::u01_double(ph.w[2], ph.w[3]) : uc4::u01_double(ph.w[0], ph.w[1]);
+                    double last = 0.0, cum = 0.0;
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+                    for (int u = 0; u < UC; u++) if (u < C) last += q[u];
+                    const double ul = uu * last;
+                    pick = 0; bool got = false;
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+                    for (int u = 0; u < UC; u++) if (u < C) { cum += q[u]; if (!got && ul < cum) { pick = u; got = true; } }
+                    so[fl] = (uint8_t)pick;
+                    changed += pick != c_old ? 1u : 0u;
+                } else pick = A.mode == 1 ? (int)so[fl] : c_old;
+                double qp = 0.0;
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+                for (int u = 0; u < UC; u++) if (u == pick) qp = q[u];
+                prod *= qp;
+            }
+            acc = log(prod);
+        }
+        for (int d = lpr >> 1; d > 0; d >>= 1) acc += sb_shfl_f64(acc, sb_lane() ^ d);
+        if (live && fg == 0) opart[o] = acc;
+    }
+    if (A.mode == 0) {
+        for (int d = 16; d > 0; d >>= 1) changed += (unsigned)sb_shfl_i32((int)changed, sb_lane() ^ d);
+        if (sb_lane() == 0 && changed) sb_atomic_add_u64(A.n_changed + s_idx, (unsigned long long)changed);
+    }
+}
+
+SB_KERNEL sb_gibbs_sweep_kernel(const SB_GRID_CONSTANT SbGibbsArgs A) {
+    if (A.P.C <= 4) ev_gibbs_body<4>(A); else ev_gibbs_body<8>(A);
+}
+
+// commits the rows a draw wrote: osel[o] ^= 1 for every object of every state
+SB_KERNEL sb_flip_osel_kernel(const SbShared *states, int n_states, int N) {
+    const long long total = (long long)n_states * N;
+    for (long long i = (long long)sb_cta() * sb_nthr() + sb_tid(); i < total; i += (long long)sb_ncta() * sb_nthr()) {
+        const SbShared st = states[i / N];
+        st.osel[i % N] ^= 1;
+    }
+}
+
 // launch geometry of the histogram pass: the widest feature tile whose bins fit `budget` bytes of
 // shared memory, tiles balanced, and enough object blocks to fill the machine
 static inline int sb_eval_make_plan(const SbProblem &P, int n_states, int n_sm, size_t budget, SbEvalPlan *pl) {

@@ -100,6 +100,23 @@ struct SbShared {
     int32_t *list_a, *list_b;    // [N] compacted object lists
     uint8_t *flag_a, *flag_b;    // [N]
     double *post;                // [8] committed posterior terms {ll, size, geo, weights, source, i_step}
+    double *glh;                 // [G_tot] export copy of the per-group log-likelihoods (ModelCache.group_likelihoods)
+    double *geo_out;             // [K] export copy of the per-cluster geo prior (ModelCache.geo_prior)
+};
+
+// staging buffers of sb_export_samples: the samples of n chains in the layout of the host buffers
+struct SbExport {
+    int32_t *cluster_of;         // [n, N]
+    float *W;                    // [n, F, C]
+    uint8_t *src;                // [n, N, F] committed sources, rows unpadded
+    int32_t *counts;             // [n, G_tot, F, S]
+    double *post;                // [n, 8]
+    double *glh;                 // [n, G_tot]
+    double *geo;                 // [n, K]
+    double *sp_obj;              // [n, N] per-object source prior
+    const int32_t *state_idx;    // [n] which state each requested chain runs
+    int n;
+    unsigned want;               // bit mask of the arrays to fill (enum order above: bit 0 = cluster_of ...)
 };
 
 // replica arrays that may live in shared memory (placement priority = enum order)

@@ -96,3 +96,27 @@ def sample_from_state(prob: P.Problem, model, data, st: P.ChainState, sample_cls
     s.i_step = i_step
     s.everything_changed()
     return s
+
+
+def fill_cache_from_device(prob: P.Problem, sample, exp: dict, sample_from_prior: bool = False):
+    """Bring the reference's cache nodes of `sample` up to date with the values the DEVICE computed
+    (`DeviceContext.export_samples`), instead of re-evaluating `model.prior` / `model.likelihood` on the CPU:
+    `cluster_size_prior`, `geo_prior` [K], `weights_prior`, `source_prior` [N] (read by ParametersCSVLogger,
+    sbayes/sampling/loggers.py:249-252, and by `swap_chains` through `Model.prior`, sbayes/mcmc_setup.py:389-390)
+    and `group_likelihoods[component]` (what `Likelihood.__call__` sums, sbayes/model/likelihood.py:47-101).
+    `CacheNode.update_value` stamps a node with the current versions of its inputs (state.py:264-273)."""
+    c = sample.cache
+    post = exp["post"]
+    c.cluster_size_prior.update_value(post["size_prior"])
+    c.weights_prior.update_value(post["weights_prior"])
+    c.source_prior.update_value(np.array(exp["source_prior"], dtype=np.float64))
+    if prob.geo is not None:
+        c.geo_prior.update_value(np.array(exp["geo_prior"], dtype=np.float64))
+    if not sample_from_prior:
+        offs = prob.group_offsets()
+        names = ["clusters"] + list(prob.conf_names)
+        for i, name in enumerate(names):
+            c.group_likelihoods[name].update_value(np.array(exp["group_ll"][offs[i]:offs[i + 1]], dtype=np.float64))
+    sample.last_lh = 0.0 if sample_from_prior else post["ll"]
+    sample.last_prior = post["prior"]
+    return sample

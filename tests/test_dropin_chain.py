@@ -91,6 +91,18 @@ def test_dropin_chain_matches_oracle(T, Tp, backend):
     assert abs(out.last_lh - oc.ll) <= 1e-10 * max(1, abs(oc.ll))
     assert abs(out.last_prior - oc.prior) <= 1e-10 * max(1, abs(oc.prior))
     assert abs(chain._ll - oc.ll / T) <= 1e-10 * max(1, abs(oc.ll))
+    # the cache nodes of the returned Sample carry the DEVICE's values: the reference's cached calls return them
+    # without recomputing (this is what swap_chains and ParametersCSVLogger read), and they agree with its own
+    # uncached evaluation
+    c = out.cache
+    assert not c.source_prior.is_outdated() and not c.cluster_size_prior.is_outdated() and not c.weights_prior.is_outdated()
+    assert all(not n.is_outdated() for n in c.group_likelihoods.values())
+    assert abs(model.prior(out) - out.last_prior) <= 1e-9 * max(1, abs(out.last_prior))
+    assert abs(model.likelihood(out) - out.last_lh) <= 1e-9 * max(1, abs(out.last_lh))
+    ref_sp = H.ref().prior.SourcePrior.__call__(model.prior.source_prior, H.sample_from_state(prob, model, data, fin), caching=False)
+    assert abs(float(np.sum(c.source_prior.value)) - ref_sp) < 5e-7 * max(1, abs(ref_sp))
+    for row in lg.rows:
+        assert abs(row[3]) < 1e-12 or np.isfinite(row[3])
     # the returned Sample is a valid reference Sample: the reference's own model agrees
     assert abs(model.likelihood(out, caching=False) - out.last_lh) < 5e-7 * max(1, abs(out.last_lh))
     assert abs(model.prior(out, caching=False) - out.last_prior) < 5e-7 * max(1, abs(out.last_prior))
