@@ -13,8 +13,10 @@ Configurations (BASELINE.json `configs`; all data syntheti
       (strong scaling: "one per GPU" at N=8).
   c4  replicates 5,000 x 200 x 6, K=5, 20 families, 128 independent chains per GPU (1,024 over 8 GPUs, weak);
       one bench step = 200 MCMC steps on every chain.
-  c5  200,000 x 1,000 x 8, K=16, 64 families, objects sharded 25,000 per GPU (weak): the uncached
-      evaluation (statistics pass + int32 all-reduce + terms + fp64 all-reduce); value = evaluations/s.
+  c5  200,000 x 1,000 x 8, K=16, 64 families, objects sharded 25,000 per GPU (weak): ONE chain advanced by all
+      GPUs together (team barriers / reductions / statistics cross GPUs inside the step kernel through NVLink
+      peer memory); one bench step = 100 MCMC steps.  c5e: the uncached evaluation of the same matrix
+      (statistics pass + int32 all-reduce + terms + fp64 all-reduce); value = evaluations/s.
 
 `--impl reference` times the reference's own CPU implementation (the unmodified sBayes copy of
 oracle/make_ref.py, `MCMCChain.run`, one process per chain like its MC3) on the same workload.
@@ -38,7 +40,8 @@ CONFIGS = {
     "c2": dict(N=1000, F=100, S=4, K=5, n_fam=8, seed=2, kind="mc3", chains_per_gpu=4, dT=0.05, swap_interval=1000, scaling="weak"),
     "c3": dict(N=100, F=36, S=5, K=3, n_fam=6, seed=3, kind="mc3", chains_total=8, dT=0.05, swap_interval=1000, scaling="strong"),
     "c4": dict(N=5000, F=200, S=6, K=5, n_fam=20, seed=4, kind="replicates", chains_per_gpu=128, steps_per_launch=200, scaling="weak"),
-    "c5": dict(N=25000, F=1000, S=8, K=16, n_fam=64, seed=5, kind="sharded_eval", chains_per_gpu=1, scaling="weak"),
+    "c5": dict(N=25000, F=1000, S=8, K=16, n_fam=64, seed=5, kind="sharded_steps", chains_per_gpu=1, steps_per_launch=100, scaling="weak"),
+    "c5e": dict(N=25000, F=1000, S=8, K=16, n_fam=64, seed=5, kind="sharded_eval", chains_per_gpu=1, scaling="weak"),
 }
 METRIC = "mcmc_steps_per_sec"
 UNIT = "steps/s"
@@ -54,9 +57,9 @@ def chains_on_rank(w: dict, world: int) -> int:
 
 def make_problem(w: dict, rank: int = 0):
     from sbayes_b200 import synth
-    seed = w["seed"] + (rank if w["kind"] == "sharded_eval" else 0)        # c5: every rank generates its own block of objects
-    return synth.make_problem(N=w["N"], F=w["F"], S=w["S"], K=w["K"], n_fam=w["n_fam"], seed=seed,
-                              with_adjacency=w["kind"] != "sharded_eval")
+    sharded = w["kind"] in ("sharded_eval", "sharded_steps")
+    seed = w["seed"] + (rank if sharded else 0)        # c5: every rank generates its own block of objects
+    return synth.make_problem(N=w["N"], F=w["F"], S=w["S"], K=w["K"], n_fam=w["n_fam"], seed=seed, with_adjacency=not sharded)
 
 
 def make_states(prob, n: int, first: int):
@@ -85,6 +88,9 @@ def workload_text(name: str, w: dict, world: int) -> str:
         return base + f", MC3 {chains_on_rank(w, world)} chains/GPU ({chains_on_rank(w, world) * world} in the ladder), swap_interval {w['swap_interval']}, operators 70/10/20"
     if w["kind"] == "replicates":
         return base + f", {w['chains_per_gpu']} independent chains/GPU, {w['steps_per_launch']} MCMC steps per bench step, operators 70/10/20"
+    if w["kind"] == "sharded_steps":
+        return base + (f" per GPU: ONE chain over {w['N'] * world} objects sharded over {world} GPU(s), {w['steps_per_launch']} MCMC steps per "
+                       f"bench step, operators 70/10/20")
     return base + f" per GPU ({w['N'] * world} objects sharded over {world} GPU(s)), uncached likelihood + prior evaluation"
 
 
@@ -92,10 +98,11 @@ def config_dict(name: str, w: dict, world: int) -> dict:
     n_local = chains_on_rank(w, world)
     per = w.get("swap_interval", w.get("steps_per_launch", 1))
     return {"workload": workload_text(name, w, world), "config": name,
-            "mcmc_steps_per_bench_step": per * n_local * world if w["kind"] != "sharded_eval" else 0,
-            "chains": n_local * world,
+            "mcmc_steps_per_bench_step": {"sharded_eval": 0, "sharded_steps": per}.get(w["kind"], per * n_local * world),
+            "chains": 1 if w["kind"].startswith("sharded") else n_local * world,
             "parallelism": {"mc3": f"chains x{world} (temperature ladder interleaved over ranks, swap scalars over NCCL all_gather)",
                             "replicates": f"chains x{world} (no collective)",
+                            "sharded_steps": f"objects x{world} (team barriers, reductions and count statistics through NVLink peer memory inside the step kernel)",
                             "sharded_eval": f"objects x{world} (int32 all-reduce of counts, fp64 all-reduce of the source prior)"}[w["kind"]],
             "l2": "flushed between timed bench steps (256 MiB write); the step kernel's state is L2-resident inside a step by design"}
 
@@ -272,6 +279,8 @@ def cpu_baseline(name: str, w: dict, n_chains: int, budget_s: float = 15.0) -> d
     """The reference's CPU path on this box's host cores, on a bounded sample of the same workload."""
     if w["kind"] == "sharded_eval":
         return cpu_eval_baseline(w, budget_s)
+    if w["kind"] == "sharded_steps":
+        return cpu_sharded_steps_baseline(w, w["N"], budget_s)
     if reference_available():
         rc = ReferenceChains(w, n_chains)
         try:
@@ -318,6 +327,14 @@ def run_reference(args):
     world = args.gpus
     n_chains = chains_on_rank(w, world) * world          # the repo arm runs this many chains at N GPUs: like for like
     cfg = config_dict(name, w, world)
+    if w["kind"] == "sharded_steps":
+        cb = cpu_sharded_steps_baseline(w, w["N"] * world, 12.0)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * w["steps_per_launch"] / cb["value"], "higher_is_better": True, "scaling": w["scaling"],
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
     if w["kind"] == "sharded_eval":
         cb = cpu_eval_baseline(w, 10.0)
         line = {"impl": "reference", "metric": "uncached_likelihood_evals_per_sec", "value": cb["value"] / world, "unit": "evals/s",
@@ -508,6 +525,8 @@ def run_ours(args):
 
     if w["kind"] == "sharded_eval":
         line = run_sharded_eval(args, name, w, rank, world, local, flush, peak, barrier, allmax, peaks)
+    elif w["kind"] == "sharded_steps":
+        line = run_sharded_steps(args, name, w, rank, world, local, flush, peak, barrier, allmax, gather, peaks)
     else:
         line = run_stepping(args, name, w, rank, world, local, flush, peak, barrier, allmax, gather, peaks)
     barrier()
@@ -617,17 +636,133 @@ def run_stepping(args, name, w, rank, world, local, flush, peak, barrier, allmax
                 # size with its own steps/s, and the config-5 object shard
                 fe.append(stepping_line("c4", CONFIGS["c4"], local, flush, peak))
                 from sbayes_b200.backend import DeviceContext
-                w5 = CONFIGS["c5"]
+                w5 = CONFIGS["c5e"]
                 p5, _ = make_problem(w5)
                 c5 = DeviceContext(p5, 1, device=local)
                 c5.configure(0, ChainConfig(seed=0))
                 c5.set_state(0, make_states(p5, 1, 0)[0])
-                fe.append(full_eval_line(c5, p5, 1, workload_text("c5", w5, 8), "c5", flush, peak))
+                fe.append(full_eval_line(c5, p5, 1, workload_text("c5e", w5, 8), "c5", flush, peak))
                 c5.close()
             line["full_eval"] = fe
         if not args.no_cpu and world == 1:
             line["cpu_baseline"] = cpu_baseline(name, w, n_local * world)
     mc3.close()
+    return line
+
+
+def assemble_sharded_problem(w, rank, world, local):
+    """every rank generates its block of objects; the packed observations and group ids are all-gathered so that
+    every rank holds the whole matrix (replicated read-only: 200 MB at 200 000 x 1 000)"""
+    import torch
+    import torch.distributed as dist
+    from dataclasses import replace
+    prob, _ = make_problem(w, rank)
+    if world == 1:
+        return prob
+    dev = torch.device("cuda", local)
+
+    def gather(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return np.concatenate([o.cpu().numpy() for o in out], axis=0)
+    x = gather(prob.x)
+    gids = [gather(g) for g in prob.conf_gid]
+    n_tot = x.shape[0]
+    return replace(prob, x=x, conf_gid=gids, max_size=max(prob.min_size + 1, n_tot // prob.K),
+                   adj_indptr=np.zeros(n_tot + 1, np.int32), adj_indices=np.zeros(0, np.int32))
+
+
+def cpu_sharded_steps_baseline(w, n_total, budget_s=15.0):
+    """c5 stepping: the reference can neither build this shape (O(N^2) distance matrix) nor run its
+    cluster operators at F = 1000 (underflow, F6); the timed CPU path is the oracle port on a 1,000-object block of
+    the same matrix, scaled linearly in the number of objects (flagged as extrapolated)."""
+    from oracle import chain as CH
+    from oracle.draws import PhiloxDraws
+    from sbayes_b200 import synth
+    from sbayes_b200.packed import ChainConfig
+    n_small = 1000
+    prob, _ = synth.make_problem(N=n_small, F=w["F"], S=w["S"], K=w["K"], n_fam=w["n_fam"], seed=w["seed"], with_adjacency=False)
+    oc = CH.OracleChain(prob, ChainConfig(seed=1), synth.initial_state(prob, seed=1000), draws=PhiloxDraws(1))
+    oc.step()
+    t0, n = time.perf_counter(), 0
+    while time.perf_counter() - t0 < budget_s:
+        oc.step(); n += 1
+    dt = (time.perf_counter() - t0) / n
+    return {"value": 1.0 / (dt * n_total / n_small), "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{n} MCMC steps of a {n_small}-object block ({dt * 1e3:.0f} ms per step), extrapolated linearly to {n_total} objects; "
+                      f"the reference itself cannot build or run this shape (SURVEY F6, F12)"}
+
+
+def run_sharded_steps(args, name, w, rank, world, local, flush, peak, barrier, allmax, gather, peaks):
+    import torch
+    from sbayes_b200 import synth
+    from sbayes_b200.packed import ChainConfig
+    from sbayes_b200.shard import ShardedChains
+    prob = assemble_sharded_problem(w, rank, world, local)
+    SPL = w["steps_per_launch"]
+    sc = ShardedChains(prob, 1, rank=rank, world=world, device=local, team=args.team)
+    sc.configure(0, ChainConfig(seed=77))
+    st = synth.initial_state(prob, seed=1000) if rank == 0 else None
+    sc.set_state(0, st)
+    info = sc.ctx.info()
+    stream = torch.cuda.ExternalStream(sc.ctx.stream(), device=torch.device("cuda", local))
+    for _ in range(args.warmup):
+        sc.run(SPL)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = sc.ctx.info()["launches"]
+    kern_ms = []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        sc.run_async(SPL)
+        e1.record(stream)
+        sc.sync()
+        kern_ms.append(e0.elapsed_time(e1))
+    barrier()
+    launches = sc.ctx.info()["launches"] - launches0
+    total_ms = allmax([sum(kern_ms)])[0]
+    per_rank = gather([float(np.mean(kern_ms))])
+    clocks = sampler.stop() if rank == 0 else None
+    value = SPL * args.steps / (total_ms / 1e3)
+    # end to end: rank 0 uploads the whole state from host memory, all ranks step, rank 0 reads the sample back
+    e2e_steps = max(1, min(args.steps, 3))
+    cur = sc.get_state(0)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        sc.set_state(0, cur)
+        sc.run(SPL)
+        cur = sc.get_state(0)
+    barrier()
+    e2e_s = allmax([time.perf_counter() - t0])[0]
+    line = None
+    if rank == 0:
+        kr = [p[0] for p in per_rank]
+        h2d = st.cluster_of.nbytes + st.W.nbytes + st.src.nbytes
+        d2h = h2d + prob.G_tot * prob.F * prob.S * 4 + 48
+        kern_s = total_ms / 1e3 / args.steps
+        post = sc.posterior(0)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": dict(config_dict(name, w, world), team_ctas_per_gpu=info["team"], grid=info["grid"], smem=info["smem"],
+                                                    objects=int(prob.N)),
+                "likelihood_evals_per_sec": value,
+                "e2e": {"value": SPL * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "per_rank": {"kern_ms": {"min": min(kr), "median": float(np.median(kr)), "max": max(kr)}},
+                "roofline": dict(roofline("sb_run_kernel", float(step_bytes(prob)) * SPL, kern_s, peak * world, None,
+                                          "one chain over all GPUs: algorithmic bytes = N_total*F per MCMC step, peak = GPUs x measured HBM peak"),
+                                 peak_source="MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"),
+                "posterior": {"ll": post["ll"], "prior": post["prior"]}}
+        if not args.no_cpu and world == 1:
+            line["cpu_baseline"] = cpu_sharded_steps_baseline(w, prob.N)
+    sc.close()
     return line
 
 

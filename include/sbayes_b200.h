@@ -36,6 +36,8 @@
  *                        for all chains of the ctx in one call (sbayes/mcmc_setup.py:263-269,389-403)
  *   sb_gibbs_sweep       GibbsSampleSource._propose with ObjectSelector.ALL (sbayes/sampling/operators.py:496-574)
  *   sb_op_stats          Operator.accepts / rejects / step_times (sbayes/sampling/operators.py:278-293)
+ *   sb_shard_handle / sb_shard_attach / sb_run_group   one chain advanced by several GPUs, objects sharded
+ *                        (the sums over objects of the proposals cross GPUs inside the step kernel)
  *   sb_swap              swap_chains (sbayes/mcmc_setup.py:365-418) over the chains of one ctx
  *   sb_swap_scalars      the same decision procedure on host scalars (no ctx): used when the
  *                        temperature ladder spans several GPUs / processes, and to replay the
@@ -177,6 +179,19 @@ int sb_swap(sb_ctx *ctx, int attempts, int only_neighbours, uint64_t seed, int64
 int sb_swap_scalars(int32_t n, const double *ll, const double *prior, const double *temps, const double *prior_temps,
                     int32_t attempts, int32_t only_neighbours, uint64_t seed, int64_t round, const int32_t *tape_pairs,
                     const double *tape_u, int32_t *state_at_slot, int32_t *accepted_pairs, int32_t *n_accepted);
+/* Objects of a chain sharded over the GPUs of one box (one ctx per GPU, each created with the SAME whole
+ * problem, chain count and team size): sb_shard_handle gives the 128-byte handle of a ctx's arena (the ranks
+ * exchange them, e.g. torch.distributed all_gather); sb_shard_attach(rank, world, handles[world * 128]) maps the
+ * peers' arenas (CUDA IPC between processes, peer access inside one process).  Afterwards rank 0's chain state IS
+ * the state of the chains (sb_set_state / sb_get_state / sb_export_samples on rank 0; ranks > 0 call
+ * sb_set_state(chain, NULL, NULL, NULL, 0) to mark the chain active), and sb_run / sb_run_async / sb_eval are
+ * COLLECTIVE: every rank calls them with the same arguments and the kernels meet on the device (team barriers and
+ * reductions through NVLink peer memory, no host collective per step).  sb_run_group launches all ranks of one
+ * process together.  Replaces the per-step sums over objects of sbayes/sampling/operators.py:1035-1073,496-552
+ * and sbayes/model/prior.py:596-611 for matrices too large for one GPU's pass. */
+int sb_shard_handle(sb_ctx *ctx, void *out128);
+int sb_shard_attach(sb_ctx *ctx, int rank, int world, const void *handles);
+int sb_run_group(sb_ctx **ctxs, int n, int64_t n_steps, sb_step_record *records_of_rank0);
 int sb_get_slots(sb_ctx *ctx, int32_t *state_of_slot);
 int sb_set_slots(sb_ctx *ctx, const int32_t *state_of_slot);
 int sb_counts_rebuild_mma(sb_ctx *ctx, int chain, int32_t *counts_out, float *ms);

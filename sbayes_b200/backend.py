@@ -68,7 +68,7 @@ EXPORTS = ["sb_create", "sb_destroy", "sb_last_error", "sb_chain_config", "sb_se
            "sb_set_slots", "sb_counts_rebuild_mma", "sb_counts_rebuild_hist", "sb_info", "sb_stream",
            "sb_eval_batch", "sb_eval_stats", "sb_eval_terms", "sb_stats_buffer", "sb_eval_set_mode", "sb_obs_loglik",
            "sb_swap_scalars", "sb_clock_khz", "sb_posteriors", "sb_set_temperatures", "sb_gibbs_sweep",
-           "sb_export_samples"]
+           "sb_export_samples", "sb_shard_handle", "sb_shard_attach", "sb_run_group"]
 
 
 def _bind(lib):
@@ -85,6 +85,9 @@ def _bind(lib):
     lib.sb_posterior.argtypes = [vp, i32, C.POINTER(_Posterior)]
     lib.sb_gibbs_sweep.argtypes = [vp, u64, i32, vp, vp, vp]
     lib.sb_export_samples.argtypes = [vp, i32, vp, C.POINTER(_SampleOut)]
+    lib.sb_shard_handle.argtypes = [vp, vp]
+    lib.sb_shard_attach.argtypes = [vp, i32, i32, vp]
+    lib.sb_run_group.argtypes = [vp, i32, i64, vp]
     lib.sb_posteriors.argtypes = [vp, vp]
     lib.sb_set_temperatures.argtypes = [vp, vp, vp]
     lib.sb_run.argtypes = [vp, i64, C.POINTER(_Tape), vp]
@@ -127,6 +130,18 @@ def load():
 
 def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def run_group(ctxs: Sequence["DeviceContext"], n_steps: int, records: bool = False):
+    """All ranks of a sharded chain held by ONE process advance together (`sb_run_group`)."""
+    lib = ctxs[0].lib
+    arr = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    rec = np.zeros((ctxs[0].n_chains, n_steps), RECORD_DTYPE) if records else None
+    rc = lib.sb_run_group(C.cast(arr, C.c_void_p), len(ctxs), int(n_steps), _ptr(rec))
+    if rc != 0:
+        msgs = [lib.sb_last_error(c.h).decode() for c in ctxs]
+        raise SbError(f"sb_run_group failed ({rc}): {msgs}")
+    return rec
 
 
 def swap_scalars(ll, prior, temps, prior_temps, state_at_slot, seed: int, round_: int, attempts: int = 100,
@@ -238,6 +253,21 @@ class DeviceContext:
             c.op_weights[i] = float(w[i])
         c.p_grow, c.seed = cfg.p_grow, int(cfg.seed)
         self._ck(self.lib.sb_chain_config(self.h, chain, C.byref(c)))
+
+    # ---- objects of a chain sharded over GPUs (include/sbayes_b200.h: sb_shard_*) -----------------
+    def shard_handle(self) -> np.ndarray:
+        h = np.zeros(128, np.uint8)
+        self._ck(self.lib.sb_shard_handle(self.h, _ptr(h)))
+        return h
+
+    def shard_attach(self, rank: int, world: int, handles: np.ndarray):
+        hs = np.ascontiguousarray(handles, np.uint8).reshape(world, 128)
+        self._ck(self.lib.sb_shard_attach(self.h, int(rank), int(world), _ptr(hs)))
+        self.shard_rank, self.shard_world = int(rank), int(world)
+
+    def mark_active(self, chain: int):
+        """rank > 0 of a sharded chain: the state itself is rank 0's"""
+        self._ck(self.lib.sb_set_state(self.h, chain, None, None, None, 0))
 
     def set_state(self, chain: int, st: ChainState, i_step: int = 0):
         co = np.ascontiguousarray(st.cluster_of, np.int32)

@@ -13,6 +13,7 @@
 #include <map>
 #include <functional>
 #include <cstddef>
+#include <unistd.h>
 
 // the step kernel, instantiated for up to 4 and up to 8 mixture components (the loops over
 // components are unrolled to that width; the narrow one is what the reference's configs need)
@@ -59,6 +60,18 @@ struct sb_ctx {
     SbSlot *d_slots = nullptr;
     unsigned long long *d_bars = nullptr;
     double *d_tred = nullptr;
+    // everything another GPU may have to reach when the objects of a chain are sharded over GPUs (per-chain
+    // state, reduction buffer, flags, statistics blocks) is carved from ONE allocation, the arena: a peer maps
+    // it once (CUDA IPC) and finds every array at the same offset as in its own arena
+    char *arena = nullptr; size_t arena_size = 0, arena_used = 0; bool arena_dry = false;
+    int xrank = 0, xworld = 1;
+    char *peer_arena[SB_MAX_RANKS] = {nullptr};
+    bool peer_opened[SB_MAX_RANKS] = {false};
+    unsigned long long xlaunches = 0;
+    unsigned long long *d_xflag = nullptr, *d_lrelease = nullptr;
+    int32_t *d_lstat = nullptr, *d_gstat = nullptr, *d_lcl = nullptr;
+    uint8_t *d_losel = nullptr;
+    int *d_xabort = nullptr;
     double *d_glh_all = nullptr, *d_geo_all = nullptr;   // [n_chains, G_tot], [n_chains, K] export copies, one allocation each
     SbExport exp_;                       // staging buffers of sb_export_samples (allocated on first use)
     int exp_ok = 0;
@@ -127,6 +140,17 @@ template <class T> static int up(sb_ctx *c, const T **dst, const std::vector<T> 
 }
 template <class T> static int mk(sb_ctx *c, T **dst, size_t n) { void *p; TRY(dev_alloc(c, &p, n * sizeof(T))); *dst = (T *)p; return 0; }
 
+// carve n elements from the arena (256-byte aligned); in the dry pass only the size is accumulated
+template <class T> static int amk(sb_ctx *c, T **dst, size_t n) {
+    const size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
+    if (!c->arena_dry) {
+        if (c->arena_used + bytes > c->arena_size) { c->err = "internal: arena overflow"; return -1; }
+        *dst = (T *)(c->arena + c->arena_used);
+    } else *dst = nullptr;
+    c->arena_used += bytes;
+    return 0;
+}
+
 static int fail(sb_ctx *c, const char *msg) { if (c) c->err = msg; else g_create_error = msg; return -1; }
 
 // ---------------------------------------------------------------------------------------
@@ -137,6 +161,7 @@ SB_API void sb_destroy(sb_ctx *c) {
 #ifndef SB_HOSTSIM
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    for (int p = 0; p < SB_MAX_RANKS; p++) if (c->peer_opened[p]) cudaIpcCloseMemHandle(c->peer_arena[p]);
 #endif
     dev_free_all(c);
 #ifndef SB_HOSTSIM
@@ -489,21 +514,39 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
     // per-chain shared state and per-CTA replica slices
     c->h_states.resize(n_chains);
     c->stats_stride = (nG + nH + (size_t)K + 3) & ~(size_t)3;
-    TRY(mk(c, &c->d_stats, c->stats_stride * (size_t)n_chains));
-    TRY(mk(c, &c->d_post_all, (size_t)n_chains * 8));
-    TRY(mk(c, &c->d_glh_all, (size_t)n_chains * P.G_tot)); TRY(mk(c, &c->d_geo_all, (size_t)n_chains * K));
     c->h_slot_state.resize(n_chains);
     for (int i = 0; i < n_chains; i++) c->h_slot_state[i] = i;
-    for (int i = 0; i < n_chains; i++) {
-        SbShared &s = c->h_states[i];
-        TRY(mk(c, &s.cluster_of, N)); TRY(mk(c, &s.W, (size_t)F * C));
-        for (int b = 0; b < 2; b++) { TRY(mk(c, &s.src[b], nS)); TRY(mk(c, &s.val[b], N)); }
-        TRY(mk(c, &s.osel, N));
-        s.counts = c->d_stats + (size_t)i * c->stats_stride; s.sizes = s.counts + nG; s.H = s.sizes + K;   // counts | sizes | H
-        TRY(mk(c, &s.list_a, N)); TRY(mk(c, &s.list_b, N)); TRY(mk(c, &s.flag_a, N)); TRY(mk(c, &s.flag_b, N));
-        s.post = c->d_post_all + (size_t)i * 8;
-        s.glh = c->d_glh_all + (size_t)i * P.G_tot; s.geo_out = c->d_geo_all + (size_t)i * K;
-    }
+    auto carve = [&]() -> int {
+        c->arena_used = 0;
+        TRY(amk(c, &c->d_tred, (size_t)c->n_teams * 2 * team * SB_MAX_RANKS * SB_REDW));
+        TRY(amk(c, &c->d_xflag, (size_t)c->n_teams * SB_MAX_RANKS));
+        TRY(amk(c, &c->d_stats, c->stats_stride * (size_t)n_chains));
+        TRY(amk(c, &c->d_lstat, c->stats_stride * (size_t)n_chains));
+        TRY(amk(c, &c->d_gstat, c->stats_stride * (size_t)n_chains));
+        TRY(amk(c, &c->d_post_all, (size_t)n_chains * 8));
+        TRY(amk(c, &c->d_glh_all, (size_t)n_chains * P.G_tot)); TRY(amk(c, &c->d_geo_all, (size_t)n_chains * K));
+        for (int i = 0; i < n_chains; i++) {
+            SbShared &s = c->h_states[i];
+            TRY(amk(c, &s.cluster_of, N)); TRY(amk(c, &s.W, (size_t)F * C));
+            for (int b = 0; b < 2; b++) { TRY(amk(c, &s.src[b], nS)); TRY(amk(c, &s.val[b], N)); }
+            TRY(amk(c, &s.osel, N));
+            TRY(amk(c, &s.list_a, N)); TRY(amk(c, &s.list_b, N)); TRY(amk(c, &s.flag_a, N)); TRY(amk(c, &s.flag_b, N));
+            if (!c->arena_dry) {
+                s.counts = c->d_stats + (size_t)i * c->stats_stride; s.sizes = s.counts + nG; s.H = s.sizes + K;   // counts | sizes | H
+                s.post = c->d_post_all + (size_t)i * 8;
+                s.glh = c->d_glh_all + (size_t)i * P.G_tot; s.geo_out = c->d_geo_all + (size_t)i * K;
+            }
+        }
+        return 0;
+    };
+    c->arena_dry = true;
+    TRY(carve());
+    c->arena_size = c->arena_used;
+    { void *p; TRY(dev_alloc(c, &p, c->arena_size)); c->arena = (char *)p; }
+    c->arena_dry = false;
+    TRY(carve());
+    c->peer_arena[0] = c->arena;
+    TRY(mk(c, &c->d_lrelease, (size_t)c->n_teams + 1)); TRY(mk(c, &c->d_xabort, 1));
     TRY(mk(c, &c->d_rep, c->rep_alloc * (size_t)c->grid));
     TRY(mk(c, &c->d_states, n_chains)); TRY(h2d(c, c->d_states, c->h_states.data(), sizeof(SbShared) * n_chains));
     std::vector<SbSlot> slots(n_chains);
@@ -514,7 +557,6 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
     }
     TRY(mk(c, &c->d_slots, n_chains)); TRY(h2d(c, c->d_slots, slots.data(), sizeof(SbSlot) * n_chains));
     TRY(mk(c, &c->d_bars, c->n_teams + 1));
-    TRY(mk(c, &c->d_tred, (size_t)c->n_teams * 2 * team * SB_REDW));
     TRY(mk(c, &c->d_src_tmp, nS)); TRY(mk(c, &c->d_counts_tmp, nG));
     // stand-alone evaluation kernels
     {
@@ -580,6 +622,13 @@ SB_API int sb_set_state(sb_ctx *c, int chain, const int32_t *cluster_of, const f
     const SbProblem &P = c->P;
     SbSlot slot; TRY(get_slot(c, chain, &slot));
     SbShared &s = c->h_states[slot.state];
+    if (!cluster_of && !W && !src) {
+        // a rank > 0 of a sharded chain: the state is rank 0's (sb_shard_attach); only mark the chain active here
+        if (c->xworld <= 1 || c->xrank == 0) return fail(c, "sb_set_state without arrays is for ranks > 0 of a sharded chain");
+        int one = 1;
+        return h2d(c, &c->d_slots[chain].active, &one, sizeof(int));
+    }
+    if (!cluster_of || !W || !src) return fail(c, "null state array");
     std::vector<int> size(P.K, 0);
     for (int o = 0; o < P.N; o++) {
         if (cluster_of[o] >= P.K) return fail(c, "cluster index out of range");
@@ -603,7 +652,11 @@ SB_API int sb_set_state(sb_ctx *c, int chain, const int32_t *cluster_of, const f
     return 0;
 }
 
-static int launch(sb_ctx *c, long long n_steps, const sb_tape *tape_dev, sb_step_record *rec_dev) {
+static int check_errors(sb_ctx *c);
+static int check_errors_fwd(sb_ctx *c) { return check_errors(c); }
+template <class T> static T *peer_ptr(sb_ctx *c, int p, T *own) { return (T *)(c->peer_arena[p] + ((char *)own - c->arena)); }
+
+static int prepare_launch(sb_ctx *c, long long n_steps, const sb_tape *tape_dev, sb_step_record *rec_dev, SbLaunch *Lp) {
     int alias_w = 1;
     for (const sb_chain_cfg &g : c->h_cfg) if (g.prior_temperature != 1.0) alias_w = 0;
     TRY(c->place_fn(c->team, alias_w));
@@ -611,19 +664,41 @@ static int launch(sb_ctx *c, long long n_steps, const sb_tape *tape_dev, sb_step
 #ifndef SB_HOSTSIM
     CK(cudaFuncSetAttribute(c->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
 #endif
-    SbLaunch L;
+    SbLaunch &L = *Lp;
     memset(&L, 0, sizeof(L));
     L.P = c->P; L.states = c->d_states; L.slots = c->d_slots; L.n_slots = c->n_chains; L.team = c->team;
     L.n_steps = n_steps; L.bars = c->d_bars; L.tred = c->d_tred; L.records = rec_dev; L.smem_members = c->smem_members;
     L.rep_base = c->d_rep; L.place = c->place; L.use_cluster = c->use_cluster; L.rep_stride = c->rep_alloc;
+    L.cta_base = 0; L.lgrid = c->grid;
+    L.xworld = c->xworld; L.xrank = c->xrank;
+    if (c->xworld > 1) {
+        // collective launch: every rank launches the same number of steps; the flag values of this launch lie
+        // above those of all earlier ones
+        L.use_cluster = 0;
+        L.xepoch_base = (++c->xlaunches) << 32;
+        for (int p = 0; p < c->xworld; p++) {
+            L.tred_peer[p] = peer_ptr(c, p, c->d_tred); L.xflag_peer[p] = peer_ptr(c, p, c->d_xflag);
+            L.lstat_peer[p] = peer_ptr(c, p, c->d_lstat); L.gstat_peer[p] = peer_ptr(c, p, c->d_gstat);
+        }
+        L.lrelease = c->d_lrelease; L.stats_stride = c->stats_stride; L.lcl = c->d_lcl; L.losel = c->d_losel; L.xabort = c->d_xabort;
+        TRY(dev_zero(c, c->d_lrelease, sizeof(unsigned long long) * (c->n_teams + 1)));
+        TRY(dev_zero(c, c->d_xabort, sizeof(int)));
+    }
     if (tape_dev) L.tape = *tape_dev;
     TRY(dev_zero(c, c->d_bars, sizeof(unsigned long long) * (c->n_teams + 1)));
     c->launches++;
+    return 0;
+}
+
+static int launch(sb_ctx *c, long long n_steps, const sb_tape *tape_dev, sb_step_record *rec_dev) {
+    SbLaunch L;
+    TRY(prepare_launch(c, n_steps, tape_dev, rec_dev, &L));
 #ifdef SB_HOSTSIM
+    if (c->xworld > 1) return fail(c, "emulator: chains sharded over ranks are launched together (sb_run_group)");
     if (c->P.C <= 4) hostsim::launch([&]() { uc4::sb_run_kernel(L); }, c->grid, c->block, c->smem);
     else hostsim::launch([&]() { uc8::sb_run_kernel(L); }, c->grid, c->block, c->smem);
 #else
-    if (c->use_cluster) {
+    if (c->use_cluster && c->xworld == 1) {
         cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
         cfg.gridDim = dim3(c->grid); cfg.blockDim = dim3(c->block); cfg.dynamicSmemBytes = c->smem; cfg.stream = c->stream;
         cudaLaunchAttribute at[1];
@@ -639,6 +714,140 @@ static int launch(sb_ctx *c, long long n_steps, const sb_tape *tape_dev, sb_step
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------
+// objects of a chain sharded over the GPUs of one box (BASELINE config 5)
+// ---------------------------------------------------------------------------------------
+struct ShardHandle {            // 128 bytes exchanged between the ranks (torch.distributed all_gather)
+    unsigned char ipc[64];      // cudaIpcMemHandle_t of the arena
+    uint64_t raw;               // the arena's address (same-process peers, emulator)
+    uint64_t size;
+    int32_t device, pid;
+    unsigned char pad[128 - 64 - 8 - 8 - 4 - 4];
+};
+static_assert(sizeof(ShardHandle) == 128, "handle is 128 bytes");
+
+SB_API int sb_shard_handle(sb_ctx *c, void *out128) {
+    TRY(check_chain(c, 0));
+    ShardHandle h; memset(&h, 0, sizeof h);
+    h.raw = (uint64_t)(uintptr_t)c->arena; h.size = c->arena_size; h.device = c->device;
+#ifndef SB_HOSTSIM
+    h.pid = (int32_t)getpid();
+    cudaIpcMemHandle_t ih;
+    CK(cudaIpcGetMemHandle(&ih, c->arena));
+    static_assert(sizeof(ih) == 64, "ipc handle size");
+    memcpy(h.ipc, &ih, 64);
+#endif
+    memcpy(out128, &h, sizeof h);
+    return 0;
+}
+
+// Makes this ctx rank `rank` of `world` ranks that advance the SAME chains together, every rank processing
+// its block of the objects.  Every rank was created with the same (whole) problem, chain count and team size.
+// handles = the 128-byte handles of all ranks in rank order (sb_shard_handle).  The per-chain state of rank 0
+// becomes THE state of the chains: the other ranks reach it through the mapped arena of rank 0.
+SB_API int sb_shard_attach(sb_ctx *c, int rank, int world, const void *handles) {
+    TRY(check_chain(c, 0));
+    if (world < 1 || world > SB_MAX_RANKS || rank < 0 || rank >= world) return fail(c, "bad rank / world");
+    if (c->xworld > 1) return fail(c, "ctx is already attached");
+    if (world == 1) return 0;
+    if (c->P.geo) return fail(c, "the cost-based geo prior is not supported with sharded objects");
+    const ShardHandle *H = (const ShardHandle *)handles;
+    for (int p = 0; p < world; p++) {
+        if (H[p].size != c->arena_size) return fail(c, "the ranks were not created with the same problem / chains / team");
+        if (p == rank) { c->peer_arena[p] = c->arena; continue; }
+#ifdef SB_HOSTSIM
+        c->peer_arena[p] = (char *)(uintptr_t)H[p].raw;
+#else
+        if (H[p].pid == (int32_t)getpid()) {      // ranks of one process: plain peer access
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, c->device, H[p].device));
+            if (!can) return fail(c, "no peer access between the GPUs");
+            cudaError_t e = cudaDeviceEnablePeerAccess(H[p].device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { c->err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e); return -2; }
+            cudaGetLastError();
+            c->peer_arena[p] = (char *)(uintptr_t)H[p].raw;
+        } else {
+            cudaIpcMemHandle_t ih; memcpy(&ih, H[p].ipc, 64);
+            void *ptr = nullptr;
+            CK(cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess));
+            c->peer_arena[p] = (char *)ptr; c->peer_opened[p] = true;
+        }
+#endif
+    }
+    c->xrank = rank; c->xworld = world;
+    const size_t N = c->P.N;
+    TRY(mk(c, &c->d_lcl, (size_t)c->n_chains * N)); TRY(mk(c, &c->d_losel, (size_t)c->n_chains * N));
+    if (rank != 0) {
+        // the chains' state is rank 0's: same offsets inside rank 0's arena
+        for (SbShared &st : c->h_states) {
+            st.cluster_of = peer_ptr(c, 0, st.cluster_of); st.W = peer_ptr(c, 0, st.W); st.osel = peer_ptr(c, 0, st.osel);
+            for (int b = 0; b < 2; b++) { st.src[b] = peer_ptr(c, 0, st.src[b]); st.val[b] = peer_ptr(c, 0, st.val[b]); }
+            st.counts = peer_ptr(c, 0, st.counts); st.H = peer_ptr(c, 0, st.H); st.sizes = peer_ptr(c, 0, st.sizes);
+            st.list_a = peer_ptr(c, 0, st.list_a); st.list_b = peer_ptr(c, 0, st.list_b);
+            st.flag_a = peer_ptr(c, 0, st.flag_a); st.flag_b = peer_ptr(c, 0, st.flag_b);
+            st.post = peer_ptr(c, 0, st.post); st.glh = peer_ptr(c, 0, st.glh); st.geo_out = peer_ptr(c, 0, st.geo_out);
+        }
+        TRY(h2d(c, c->d_states, c->h_states.data(), sizeof(SbShared) * c->n_chains));
+    }
+    c->use_cluster = 0;
+    return dev_sync(c);
+}
+
+// Launches `n` attached ctxs of ONE process together (all ranks of a sharded chain) and waits for all of them:
+// the single-process way to drive a box, and the only way in the emulator (one fibre pool runs all ranks).
+SB_API int sb_run_group(sb_ctx **ctxs, int n, int64_t n_steps, sb_step_record *records0) {
+    if (!ctxs || n < 1 || n > SB_MAX_RANKS) return -1;
+    std::vector<SbLaunch> L(n);
+    sb_step_record *rd = nullptr;
+    sb_ctx *c0 = ctxs[0];
+    const size_t n_rec = (size_t)c0->n_chains * (size_t)n_steps;
+    size_t keep0 = c0->allocs.size();
+    if (records0 && n_rec) TRY(mk(c0, &rd, n_rec));
+    int r = 0;
+    for (int i = 0; i < n && !r; i++) {
+#ifndef SB_HOSTSIM
+        cudaSetDevice(ctxs[i]->device);
+#endif
+        r = prepare_launch(ctxs[i], n_steps, nullptr, ctxs[i]->xrank == 0 ? rd : nullptr, &L[i]);
+    }
+#ifdef SB_HOSTSIM
+    if (!r) {
+        int total = 0;
+        for (int i = 0; i < n; i++) { L[i].cta_base = total; L[i].lgrid = ctxs[i]->grid; total += ctxs[i]->grid; }
+        size_t smem = 0;
+        for (int i = 0; i < n; i++) smem = std::max(smem, ctxs[i]->smem);
+        hostsim::launch([&]() {
+            const int cta = hostsim::cta();
+            int i = 0;
+            while (i + 1 < n && cta >= L[i + 1].cta_base) i++;
+            if (ctxs[i]->P.C <= 4) uc4::sb_run_kernel(L[i]); else uc8::sb_run_kernel(L[i]);
+        }, total, c0->block, smem);
+    }
+#else
+    for (int i = 0; i < n && !r; i++) {
+        sb_ctx *c = ctxs[i];
+        cudaSetDevice(c->device);
+        void *args[] = {&L[i]};
+        cudaError_t e = cudaLaunchCooperativeKernel(c->kernel, dim3(c->grid), dim3(c->block), args, c->smem, c->stream);
+        if (e != cudaSuccess) { c->err = std::string("cudaLaunchCooperativeKernel: ") + cudaGetErrorString(e); r = -2; }
+    }
+    for (int i = 0; i < n; i++) { cudaSetDevice(ctxs[i]->device); cudaError_t e = cudaStreamSynchronize(ctxs[i]->stream); if (e != cudaSuccess && !r) { ctxs[i]->err = cudaGetErrorString(e); r = -2; } }
+    cudaSetDevice(c0->device);
+#endif
+    if (!r && rd) r = d2h(c0, records0, rd, sizeof(sb_step_record) * n_rec);
+    while (c0->allocs.size() > keep0) {
+#ifdef SB_HOSTSIM
+        free(c0->allocs.back());
+#else
+        cudaFree(c0->allocs.back());
+#endif
+        c0->allocs.pop_back();
+    }
+    if (r) return r;
+    for (int i = 0; i < n; i++) TRY(check_errors_fwd(ctxs[i]));
+    return 0;
+}
+
 static int check_errors(sb_ctx *c) {
     std::vector<SbSlot> slots(c->n_chains);
     TRY(d2h(c, slots.data(), c->d_slots, sizeof(SbSlot) * c->n_chains));
@@ -646,9 +855,10 @@ static int check_errors(sb_ctx *c) {
         if (slots[i].err) {
             static const char *msg[] = {"", "non-finite posterior accepted (sbayes/sampling/mcmc_chain.py:231-236)",
                                         "source component out of range in state", "cluster larger than the geo-prior member list",
-                                        "wide operator could not change the cluster"};
+                                        "wide operator could not change the cluster",
+                                        "a rank of the sharded chain did not arrive at a team barrier (timeout)"};
             char buf[256];
-            snprintf(buf, sizeof buf, "chain %d: %s", i, msg[std::min(slots[i].err, 4)]);
+            snprintf(buf, sizeof buf, "chain %d: %s", i, msg[std::min(slots[i].err, 5)]);
             c->err = buf;
             int zero = 0; h2d(c, &c->d_slots[i].err, &zero, sizeof(int));
             return -3;

@@ -239,6 +239,14 @@ struct RunC {
     int smem_cap;
     double *tile;      // smem tile buffer of the tiled passes (null: the whole pass table is resident, rp.tab)
     int tile_cap;      // its size in doubles
+    // objects sharded over GPUs (SbLaunch: xworld > 1)
+    double *tredp[SB_MAX_RANKS];               // this team's reduction buffer in every rank's memory
+    unsigned long long *xflagp[SB_MAX_RANKS];  // this team's flag row in every rank's memory
+    unsigned long long *lrel;                  // release word of the local barrier phase
+    int32_t *lcl;                              // rank-local replica of cluster_of of the current chain (or null)
+    uint8_t *losel;                            // ... of osel
+    int32_t *lstatp[SB_MAX_RANKS], *gstatp[SB_MAX_RANKS];   // statistics blocks of the current chain in every rank's memory
+    int *xabort;
 };
 
 struct Run {
@@ -249,6 +257,8 @@ struct Run {
     int sfp;
     int propose_only;            // operator API: commit every proposal the operator does not reject itself (no MH test)
     int tsize, rank, par, vpar, spar, use_cluster, hcur;
+    int lsize, lrank, xrank, xworld;     // CTAs of the team on this GPU, index among them; GPU index / count (object sharding)
+    unsigned long long xbase;
     unsigned long long epoch;
     int nd;            // number of dirty rows of the open proposal
     // candidate membership view
@@ -282,6 +292,53 @@ SB_HD FixedSmem sb_fixed_smem(int G, int K, int F, int C, int cap, unsigned base
     return o;
 }
 
+// Barrier of a team that spans several GPUs (thread 0 of every CTA).  Phase 1: L2 ticket among the CTAs of
+// this GPU.  Phase 2 (the last CTA to arrive): one release store into every other rank's flag row (peer memory
+// over NVLink), then an acquire spin on the own row until every rank has arrived.  Phase 3: release word for
+// the CTAs of this GPU.  System-scope fences on both sides order the team's peer-memory traffic around the
+// barrier.  Flags only ever grow (launch base + barrier count), so nothing has to be reset between launches.
+// A wait that exceeds ~4 s sets the abort word: every later barrier falls through and the host reports an error
+// instead of the GPUs hanging on each other.
+SB_DEV void xteam_wait(Run &R) {
+    if (sb_ld_volatile_i32(R.c->xabort)) return;
+    const long long t_lim = 8000000000LL;
+    sb_threadfence_system();
+    const unsigned long long arrived = sb_atomic_add_u64(R.c->bar, 1ull) + 1ull;
+    const unsigned long long ev = R.xbase + R.epoch;
+    if (arrived == R.epoch * (unsigned long long)R.lsize) {
+        for (int p = 0; p < R.xworld; p++)
+            if (p != R.xrank) sb_st_release_sys_u64(R.c->xflagp[p] + R.xrank, ev);
+        for (int p = 0; p < R.xworld; p++) {
+            if (p == R.xrank) continue;
+            const long long t0 = sb_clock();
+            while (sb_ld_acquire_sys_u64(R.c->xflagp[R.xrank] + p) < ev) {
+                sb_spin();
+                if (sb_clock() - t0 > t_lim || sb_ld_volatile_i32(R.c->xabort)) { *R.c->xabort = 1; break; }
+            }
+        }
+        sb_threadfence_system();
+        sb_st_release_sys_u64(R.c->lrel, ev);
+    } else {
+        const long long t0 = sb_clock();
+        while (sb_ld_acquire_sys_u64(R.c->lrel) < ev) {
+            sb_spin();
+            if (sb_clock() - t0 > 2 * t_lim || sb_ld_volatile_i32(R.c->xabort)) { *R.c->xabort = 1; break; }
+        }
+    }
+    sb_threadfence_system();
+}
+
+// a CTA's slot of the team reduction buffer (thread 0): with the objects sharded over GPUs the buffer is
+// replicated and the slot is stored into every rank's copy, so that everybody reads locally after the barrier
+SB_DEV void tred_put(Run &R, int par, const double *v, int K) {
+    const size_t off = ((size_t)par * R.tsize + R.rank) * SB_REDW;
+    if (R.xworld > 1) {
+        for (int p = 0; p < R.xworld; p++)
+            for (int k = 0; k < K; k++) R.c->tredp[p][off + k] = v[k];
+    } else
+        for (int k = 0; k < K; k++) R.c->tred[off + k] = v[k];
+}
+
 SB_DEV void team_sync(Run &R) {
 #ifndef SB_HOSTSIM
     if (R.use_cluster && R.tsize > 1) {      // hardware barrier over all threads of the cluster
@@ -294,13 +351,17 @@ SB_DEV void team_sync(Run &R) {
     if (R.tsize > 1) {
         R.epoch++;
         if (sb_tid() == 0) {
-            sb_threadfence();
-            sb_atomic_add_u64(R.c->bar, 1ull);
-            unsigned long long target = R.epoch * (unsigned long long)R.tsize;
-            while (sb_ld_acquire_u64(R.c->bar) < target) sb_spin();
-            sb_threadfence();
+            if (R.xworld > 1) xteam_wait(R);
+            else {
+                sb_threadfence();
+                sb_atomic_add_u64(R.c->bar, 1ull);
+                unsigned long long target = R.epoch * (unsigned long long)R.tsize;
+                while (sb_ld_acquire_u64(R.c->bar) < target) sb_spin();
+                sb_threadfence();
+            }
         }
         sb_cta_sync();
+        if (R.xworld > 1 && sb_ld_volatile_i32(R.c->xabort)) R.err = 5;
     }
 }
 
@@ -356,9 +417,8 @@ SB_DEV void team_sum(Run &R, double (&v)[K]) {
     block_sum<K, PROD>(R, v);
     if (R.tsize == 1) return;
     double *buf = R.c->tred + (size_t)R.par * R.tsize * SB_REDW;
+    if (sb_tid() == 0) tred_put(R, R.par, v, K);
     R.par ^= 1;
-    if (sb_tid() == 0)
-        for (int k = 0; k < K; k++) buf[R.rank * SB_REDW + k] = v[k];
     team_sync(R);
 #pragma unroll
     for (int k = 0; k < K; k++) {
@@ -391,8 +451,8 @@ SB_DEV int team_pick(Run &R, const double *val, int n, double u, double &total, 
     int rb = 0; double tloc;
     if (R.tsize > 1) {
         double *buf = R.c->tred + (size_t)R.par * R.tsize * SB_REDW;
+        if (tid == 0) tred_put(R, R.par, s, 3);
         R.par ^= 1;
-        if (tid == 0) { buf[R.rank * SB_REDW] = s[0]; buf[R.rank * SB_REDW + 1] = s[1]; buf[R.rank * SB_REDW + 2] = s[2]; }
         team_sync(R);
         total = 0.0;
         double e0 = 0.0, e1 = 0.0;
@@ -466,8 +526,8 @@ SB_DEV int team_compact(Run &R, int n, int32_t *list, Pred pred) {
     for (int i = lo + sb_tid(); i < hi; i += sb_nthr()) c[0] += pred(i) ? 1.0 : 0.0;
     block_sum<1>(R, c);
     double *buf = R.c->tred + (size_t)R.par * R.tsize * SB_REDW;
+    if (sb_tid() == 0) tred_put(R, R.par, c, 1);
     R.par ^= 1;
-    if (sb_tid() == 0) buf[R.rank * SB_REDW] = c[0];
     team_sync(R);
     int base = 0, total = 0;
     for (int r = 0; r < R.tsize; r++) { int v = (int)buf[r * SB_REDW]; if (r < R.rank) base += v; total += v; }
@@ -541,8 +601,8 @@ SB_DEV void batch_items(int lo, int hi, WarpFn warp_fn, LaneFn lane_fn) {
 // -----------------------------------------------------------------------------------------
 // views: committed (0) or candidate (1) membership
 // -----------------------------------------------------------------------------------------
-SB_DEV int m_cl(const Run &R, int o) { return R.c->mcl ? (int)R.c->mcl[o] : R.c->st.cluster_of[o]; }
-SB_DEV int m_osel(const Run &R, int o) { return R.c->mosel ? (int)R.c->mosel[o] : (int)R.c->st.osel[o]; }
+SB_DEV int m_cl(const Run &R, int o) { return R.c->mcl ? (int)R.c->mcl[o] : (R.c->lcl ? R.c->lcl[o] : R.c->st.cluster_of[o]); }
+SB_DEV int m_osel(const Run &R, int o) { return R.c->mosel ? (int)R.c->mosel[o] : (R.c->losel ? (int)R.c->losel[o] : (int)R.c->st.osel[o]); }
 SB_DEV int m_combo(const Run &R, int o) { return R.c->mcombo ? (int)R.c->mcombo[o] : sb_ldg(R.P->combo_id + o); }
 SB_DEV int m_pat(const Run &R, int o) { return R.c->combo_pat[m_combo(R, o)]; }
 SB_DEV int cl_of(const Run &R, int o, int view) {
@@ -2173,10 +2233,22 @@ SB_DEV void rebuild_state(Run &R) {
     const int N = P.N, F = P.F, S = P.S, C = P.C;
     const size_t nG = (size_t)P.G_tot * F * S;
     const int nH = P.n_pat * 2 * F * C;
-    const int stride = R.tsize * sb_nthr(), t0 = R.rank * sb_nthr() + sb_tid();
-    for (size_t i = t0; i < nG; i += stride) R.c->st.counts[i] = 0;
-    for (int i = t0; i < nH; i += stride) R.c->st.H[i] = 0;
-    for (int k = t0; k < P.K; k += stride) R.c->st.sizes[k] = 0;
+    // where the bins are accumulated and where the replicas are filled from: the chain's statistics block
+    // (counts | sizes | H), or -- objects sharded over GPUs -- this GPU's partial block and, after the
+    // exchange below, its copy of the reduced block
+    int32_t *acc_counts = R.c->st.counts, *acc_sizes = R.c->st.sizes, *acc_H = R.c->st.H;
+    const int32_t *fin_counts = acc_counts, *fin_sizes = acc_sizes, *fin_H = acc_H;
+    if (R.xworld > 1) {
+        acc_counts = R.c->lstatp[R.xrank]; acc_sizes = acc_counts + nG; acc_H = acc_sizes + P.K;
+        fin_counts = R.c->gstatp[R.xrank]; fin_sizes = fin_counts + nG; fin_H = fin_sizes + P.K;
+    }
+    {
+        // zeroed by the CTAs that will add to it (all of the team / the CTAs of this GPU)
+        const int zs = (R.xworld > 1 ? R.lsize : R.tsize) * sb_nthr(), z0 = (R.xworld > 1 ? R.lrank : R.rank) * sb_nthr() + sb_tid();
+        for (size_t i = z0; i < nG; i += zs) acc_counts[i] = 0;
+        for (int i = z0; i < nH; i += zs) acc_H[i] = 0;
+        for (int k = z0; k < P.K; k += zs) acc_sizes[k] = 0;
+    }
     team_sync(R);
     // histogram pass: warp per object, lanes over features (coalesced byte reads)
     int lo, hi; team_range(R, N, lo, hi);
@@ -2193,17 +2265,30 @@ SB_DEV void rebuild_state(Run &R) {
             if (c >= C) { R.err = 2; continue; }
             int g = -1;
             SB_FOR_C(cc, C) if (cc == c) g = gC[cc];
-            if (g >= 0) sb_atomic_add_i32(R.c->st.counts + ((size_t)g * F + f) * S + x, 1);
-            sb_atomic_add_i32(R.c->st.H + ((size_t)(pat * 2 + z) * F + f) * C + c, 1);
+            if (g >= 0) sb_atomic_add_i32(acc_counts + ((size_t)g * F + f) * S + x, 1);
+            sb_atomic_add_i32(acc_H + ((size_t)(pat * 2 + z) * F + f) * C + c, 1);
         }
-        if (sb_lane() == 0 && k >= 0) sb_atomic_add_i32(R.c->st.sizes + k, 1);
+        if (sb_lane() == 0 && k >= 0) sb_atomic_add_i32(acc_sizes + k, 1);
     }
     team_sync(R);
+    if (R.xworld > 1) {
+        // all-reduce of the partial blocks through peer memory (reduce-scatter + all-gather in one sweep):
+        // the team's threads split the bins; a thread sums its bins over the ranks' partial blocks and stores
+        // the totals into every rank's copy of the reduced block
+        const size_t n_stat = nG + (size_t)P.K + (size_t)nH;
+        const size_t stride = (size_t)R.tsize * sb_nthr();
+        for (size_t i = (size_t)R.rank * sb_nthr() + sb_tid(); i < n_stat; i += stride) {
+            int32_t v = 0;
+            for (int p = 0; p < R.xworld; p++) v += R.c->lstatp[p][i];
+            for (int p = 0; p < R.xworld; p++) R.c->gstatp[p][i] = v;
+        }
+        team_sync(R);
+    }
     // every CTA fills its replica
-    for (size_t i = sb_tid(); i < nG; i += sb_nthr()) { R.c->rp.counts[i] = R.c->st.counts[i]; R.c->rp.dcnt[i] = 0; }
-    for (int i = sb_tid(); i < nH; i += sb_nthr()) R.c->rp.H[0][i] = R.c->st.H[i];
+    for (size_t i = sb_tid(); i < nG; i += sb_nthr()) { R.c->rp.counts[i] = fin_counts[i]; R.c->rp.dcnt[i] = 0; }
+    for (int i = sb_tid(); i < nH; i += sb_nthr()) R.c->rp.H[0][i] = fin_H[i];
     for (int i = sb_tid(); i < F * C; i += sb_nthr()) R.c->rp.W[i] = R.c->st.W[i];
-    for (int k = sb_tid(); k < P.K; k += sb_nthr()) { R.c->rp.sizes[k] = R.c->st.sizes[k]; R.c->rp.ssz[k] = R.c->st.sizes[k]; }
+    for (int k = sb_tid(); k < P.K; k += sb_nthr()) { R.c->rp.sizes[k] = fin_sizes[k]; R.c->rp.ssz[k] = fin_sizes[k]; }
     for (int g = sb_tid(); g < P.G_tot; g += sb_nthr()) R.c->rp.dirty[g] = 0;
     R.hcur = 0; R.chg_mode = CHG_NONE; R.nd = 0;
     sb_cta_sync();
@@ -2296,12 +2381,21 @@ SB_DEV void mcmc_step(Run &R, sb_step_record *rec) {
         if (pr.need_sync && accept) team_sync(R);     // a fast CTA's commit must not overtake a slow CTA's reads
         if (accept) {
             // object-indexed state in HBM: every CTA writes the same values
+            // (objects sharded over GPUs: the master copy in rank 0's memory is written once, by the first CTA
+            // of the team; every GPU keeps its own replica for the passes)
+            const bool master = R.xworld == 1 || R.rank == 0;
             for (int m = sb_tid(); m < pr.M; m += sb_nthr()) {
                 int o = pr.S[m];
                 int nc = cl_of(R, o, 1);
-                if (pr.src_changed) { R.c->st.osel[o] = R.c->rp.selbuf[m]; if (R.c->mosel) R.c->mosel[o] = R.c->rp.selbuf[m]; }
-                R.c->st.cluster_of[o] = nc;
+                if (pr.src_changed) {
+                    const uint8_t sel = R.c->rp.selbuf[m];
+                    if (master) R.c->st.osel[o] = sel;
+                    if (R.c->mosel) R.c->mosel[o] = sel;
+                    if (R.c->losel) R.c->losel[o] = sel;
+                }
+                if (master) R.c->st.cluster_of[o] = nc;
                 if (R.c->mcl) R.c->mcl[o] = (int16_t)nc;
+                if (R.c->lcl) R.c->lcl[o] = nc;
             }
             for (int k = sb_tid(); k < P.K; k += sb_nthr()) R.c->rp.sizes[k] = R.c->rp.ssz[k];
             if (pr.src_changed) R.hcur ^= 1;
@@ -2393,13 +2487,25 @@ SB_DEV void setup_replica(Run &R, const SbLaunch &L, char *smem, char *glob) {
 SB_KERNEL_BIG sb_run_kernel(const SB_GRID_CONSTANT SbLaunch L) {
     Run R;
     R.P = &L.P;
-    R.tsize = L.team; R.rank = sb_cta() % L.team; R.par = 0; R.vpar = 0; R.spar = 0; R.epoch = 0; R.use_cluster = L.use_cluster;
+    // CTAs of this launch: [cta_base, cta_base + lgrid) of the grid (the whole grid except in emulated multi-rank launches)
+    const int lcta = sb_cta() - L.cta_base, lncta = L.lgrid > 0 ? L.lgrid : sb_ncta();
+    R.xworld = L.xworld > 1 ? L.xworld : 1; R.xrank = R.xworld > 1 ? L.xrank : 0; R.xbase = L.xepoch_base;
+    R.lsize = L.team; R.lrank = lcta % L.team;
+    R.tsize = L.team * R.xworld; R.rank = R.xrank * L.team + R.lrank;
+    R.par = 0; R.vpar = 0; R.spar = 0; R.epoch = 0; R.use_cluster = L.use_cluster;
     R.hcur = 0; R.nd = 0; R.pt = 0; R.cur_op = 0;
-    const int team_id = sb_cta() / L.team, n_teams = sb_ncta() / L.team;
-    setup_replica(R, L, sb_smem(), L.rep_base + (size_t)sb_cta() * L.rep_stride);
+    const int team_id = lcta / L.team, n_teams = lncta / L.team;
+    setup_replica(R, L, sb_smem(), L.rep_base + (size_t)lcta * L.rep_stride);
     if (sb_tid() == 0) {
+        const size_t tred_off = (size_t)team_id * 2 * L.team * SB_MAX_RANKS * SB_REDW;
         R.c->bar = L.bars + team_id;
-        R.c->tred = L.tred + (size_t)team_id * 2 * L.team * SB_REDW;
+        R.c->tred = L.tred + tred_off;
+        R.c->lcl = nullptr; R.c->losel = nullptr; R.c->xabort = L.xabort; R.c->lrel = L.lrelease ? L.lrelease + team_id : nullptr;
+        for (int p = 0; p < SB_MAX_RANKS; p++) {
+            R.c->tredp[p] = p < R.xworld && L.tred_peer[p] ? L.tred_peer[p] + tred_off : nullptr;
+            R.c->xflagp[p] = p < R.xworld && L.xflag_peer[p] ? L.xflag_peer[p] + (size_t)team_id * SB_MAX_RANKS : nullptr;
+            R.c->lstatp[p] = nullptr; R.c->gstatp[p] = nullptr;
+        }
     }
     for (int s = team_id; s < L.n_slots; s += n_teams) {
         SbSlot *slot = L.slots + s;
@@ -2409,10 +2515,22 @@ SB_KERNEL_BIG sb_run_kernel(const SB_GRID_CONSTANT SbLaunch L) {
             R.c->slot = slot;
             R.c->st = L.states[slot->state];
             for (int i = 0; i < SB_N_OPS; i++) R.c->opw[i] = slot->cfg.op_weights[i];
+            if (R.xworld > 1) {
+                R.c->lcl = L.lcl + (size_t)slot->state * L.P.N; R.c->losel = L.losel + (size_t)slot->state * L.P.N;
+                for (int p = 0; p < R.xworld; p++) {
+                    R.c->lstatp[p] = L.lstat_peer[p] + (size_t)slot->state * L.stats_stride;
+                    R.c->gstatp[p] = L.gstat_peer[p] + (size_t)slot->state * L.stats_stride;
+                }
+            }
         }
         sb_cta_sync();
         if (R.c->mcl) for (int o = sb_tid(); o < L.P.N; o += sb_nthr()) R.c->mcl[o] = (int16_t)R.c->st.cluster_of[o];
         if (R.c->mosel) for (int o = sb_tid(); o < L.P.N; o += sb_nthr()) R.c->mosel[o] = R.c->st.osel[o];
+        if (R.c->lcl) {
+            // this GPU's replica of the membership / committed-copy selector (read from the master in rank 0's
+            // memory by the CTAs of this GPU, each its share; the first team barrier of rebuild_state publishes it)
+            for (int o = R.lrank * sb_nthr() + sb_tid(); o < L.P.N; o += R.lsize * sb_nthr()) { R.c->lcl[o] = R.c->st.cluster_of[o]; R.c->losel[o] = R.c->st.osel[o]; }
+        }
         sb_cta_sync();
         const sb_chain_cfg &cfg = slot->cfg;
         R.T = cfg.temperature; R.Tp = cfg.prior_temperature; R.invT = 1.0 / R.T; R.invTp = 1.0 / R.Tp;

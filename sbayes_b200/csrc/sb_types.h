@@ -8,6 +8,7 @@
 #define SB_MAXC SB_MAX_COMPONENTS
 #endif
 #define SB_MAXK 1024         // clusters (sizes are staged in shared memory)
+#define SB_MAX_RANKS 8       // GPUs one chain's objects can be sharded over
 #define SB_REDW 8            // doubles per CTA in a team reduction
 #define SB_NA_U8 255
 
@@ -169,4 +170,22 @@ struct SbLaunch {
     sb_step_record *records;     // [n_slots, n_steps] or null
     int smem_members;            // capacity of the shared-memory member list (geo prior)
     int use_cluster;             // team == thread-block cluster: hardware cluster barrier
+    int cta_base, lgrid;         // first CTA and number of CTAs of this launch (cta_base != 0 only in emulated multi-rank launches)
+    // ---- objects of a chain sharded over the GPUs of one box (sb_shard_attach; xworld == 1: off) ----
+    // A chain is advanced by xworld * team CTAs: `team` on every GPU.  The object-indexed state of the chain
+    // (states[]) lives in rank 0's memory and is reached by the other ranks through peer mappings (NVLink);
+    // the reduction buffer is replicated (every CTA stores its slot into every rank's copy), the team barrier
+    // is hierarchical (L2 ticket per GPU, then one flag per rank pair in peer memory), the bulk statistics
+    // are reduced rank-local first and exchanged through peer memory.
+    int xrank, xworld;
+    unsigned long long xepoch_base;                 // flag values of this launch start above it (flags are never reset)
+    double *tred_peer[SB_MAX_RANKS];                // every rank's copy of tred
+    unsigned long long *xflag_peer[SB_MAX_RANKS];   // every rank's flag words [n_teams][SB_MAX_RANKS]
+    unsigned long long *lrelease;                   // [n_teams] release word of the local barrier phase
+    int32_t *lstat_peer[SB_MAX_RANKS];              // every rank's partial statistics [n_chains][stats_stride]
+    int32_t *gstat_peer[SB_MAX_RANKS];              // every rank's copy of the reduced statistics
+    size_t stats_stride;
+    int32_t *lcl;                                   // [n_chains][N] rank-local replica of cluster_of
+    uint8_t *losel;                                 // [n_chains][N] rank-local replica of osel
+    int *xabort;                                    // set when a cross-GPU wait timed out: every later barrier falls through
 };

@@ -167,3 +167,71 @@ class ShardedEvaluator:
 
     def close(self):
         self.ctx.close()
+
+
+class ShardedChains:
+    """`n_chains` chains whose OBJECTS are sharded over the `world` GPUs of one box: every MCMC step is taken
+    by all GPUs together, each walking its block of the objects in the proposal passes, with the team barriers,
+    the reductions and the bulk statistics crossing GPUs inside the persistent step kernel through NVLink peer
+    memory (include/sbayes_b200.h: sb_shard_attach) -- no host collective per step.
+
+    One process per GPU: `torch.distributed` is used once, to exchange the 128-byte arena handles, and as a host
+    barrier around state uploads.  Every rank constructs this object with the SAME whole problem (the packed
+    observations are replicated: 200 MB at 200 000 x 1 000); the chains' state lives on rank 0.  `run` is
+    collective.  Replaces, for matrices too large for one GPU's pass, the per-step sums over objects of
+    sbayes/sampling/operators.py:1035-1073 (candidate posterior), :496-552 (source Gibbs) and
+    sbayes/model/prior.py:596-611 (source prior)."""
+
+    def __init__(self, prob: Problem, n_chains: int, rank: int = 0, world: int = 1, device: int = 0, team: int = 0, _lib=None):
+        self.rank, self.world, self.n_chains = rank, world, n_chains
+        self.ctx = DeviceContext(prob, n_chains, device=device, team=team, _lib=_lib)
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            h = self.ctx.shard_handle()
+            dev = torch.device("cuda", device) if dist.get_backend() == "nccl" else torch.device("cpu")
+            mine = torch.from_numpy(h.copy()).to(dev)
+            out = torch.empty(world * 128, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(out, mine)
+            self.ctx.shard_attach(rank, world, out.cpu().numpy())
+            dist.barrier()
+
+    def _barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+
+    def configure(self, chain: int, cfg: ChainConfig):
+        self.ctx.configure(chain, cfg)          # the same configuration on every rank
+
+    def set_state(self, chain: int, st: Optional[ChainState], i_step: int = 0):
+        """collective; `st` is needed on rank 0 only"""
+        if self.rank == 0:
+            self.ctx.set_state(chain, st, i_step)
+            self.ctx.sync()
+        else:
+            self.ctx.mark_active(chain)
+        self._barrier()
+
+    def run(self, n_steps: int, records: bool = False):
+        """collective: the kernels of all ranks meet on the device"""
+        self._barrier()
+        rec = self.ctx.run(n_steps, records=records)
+        self._barrier()
+        return rec if self.rank == 0 else None
+
+    def run_async(self, n_steps: int):
+        self.ctx.run_async(n_steps)
+
+    def sync(self):
+        self.ctx.sync()
+
+    def get_state(self, chain: int) -> Optional[ChainState]:
+        return self.ctx.get_state(chain) if self.rank == 0 else None
+
+    def posterior(self, chain: int) -> Optional[dict]:
+        return self.ctx.posterior(chain) if self.rank == 0 else None
+
+    def close(self):
+        self._barrier()
+        self.ctx.close()

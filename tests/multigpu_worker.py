@@ -10,6 +10,7 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 from oracle import model as M  # noqa: E402
 from sbayes_b200 import synth  # noqa: E402
 from sbayes_b200.backend import DeviceContext  # noqa: E402
@@ -69,6 +70,38 @@ def main():
         g = l * world + rank
         assert np.array_equal(post[l], post1[g])
         assert np.array_equal(fin[l].cluster_of, fin1[g].cluster_of) and np.array_equal(fin[l].src, fin1[g].src)
+    dist.barrier()
+    # ---- (c) ONE chain advanced by all ranks, objects sharded (in-kernel exchange over peer memory) -----
+    from sbayes_b200.shard import ShardedChains
+    import parity
+    prob, _ = synth.make_problem(N=3000, F=150, S=6, K=6, n_fam=12, seed=5)
+    cfgs = [ChainConfig(seed=910), ChainConfig(temperature=1.2, prior_temperature=1.1, seed=911)]
+    st0 = [synth.initial_state(prob, seed=45 + c) for c in range(2)]
+    team_local, n_steps = 8, 60
+    sc = ShardedChains(prob, 2, rank=rank, world=world, device=local, team=team_local)
+    for ch in range(2):
+        sc.configure(ch, cfgs[ch])
+        sc.set_state(ch, st0[ch] if rank == 0 else None)
+    recs = [sc.run(n_steps, records=True) for _ in range(2)]
+    if rank == 0:
+        rs = np.concatenate(recs, axis=1)
+        single = DeviceContext(prob, 2, device=local, team=team_local * world)
+        for ch in range(2):
+            single.configure(ch, cfgs[ch]); single.set_state(ch, st0[ch])
+        r1 = np.concatenate([single.run(n_steps, records=True) for _ in range(2)], axis=1)
+        for f in ("op", "accept", "changed", "n_changed"):
+            assert np.array_equal(rs[f], r1[f]), f
+        for f in ("log_q", "log_q_back", "ll_new", "prior_new"):
+            assert np.array_equal(rs[f], r1[f], equal_nan=True), f"{f}: sharded chain != single-GPU chain"
+        for ch in range(2):
+            a, b = sc.get_state(ch), single.get_state(ch)
+            assert np.array_equal(a.cluster_of, b.cluster_of) and np.array_equal(a.src, b.src) and np.array_equal(a.counts, b.counts)
+            assert sc.posterior(ch) == single.posterior(ch)
+        trajs = parity.oracle_trajectories([(prob, cfgs[ch], st0[ch], 2 * n_steps) for ch in range(2)], procs=2)
+        parity.compare_with_trajectories(sc.ctx, rs, trajs)
+        single.close()
+        print(f"SHARDED STEPPING OK world={world}: {2 * n_steps} steps x 2 chains identical to the single-GPU chain and the oracle")
+    sc.close()
     dist.barrier()
     if rank == 0:
         print(f"MULTIGPU OK world={world} swaps={sum(len(a) for a in acc)}")
