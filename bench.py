@@ -494,6 +494,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # (NCCL prints its version banner to stdout otherwise: the line must be the JSON)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     name, w = args.config, CONFIGS[args.config]
     peaks = {}

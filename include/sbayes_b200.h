@@ -35,6 +35,7 @@
  *   sb_posteriors / sb_set_temperatures   the scalars swap_chains reads and the temperatures it exchanges,
  *                        for all chains of the ctx in one call (sbayes/mcmc_setup.py:263-269,389-403)
  *   sb_gibbs_sweep       GibbsSampleSource._propose with ObjectSelector.ALL (sbayes/sampling/operators.py:496-574)
+ *   sb_init_em           SbayesInitializer.generate_clusters_em (sbayes/sampling/initializers.py:93-169)
  *   sb_op_stats          Operator.accepts / rejects / step_times (sbayes/sampling/operators.py:278-293)
  *   sb_shard_handle / sb_shard_attach / sb_run_group   one chain advanced by several GPUs, objects sharded
  *                        (the sums over objects of the proposals cross GPUs inside the step kernel)
@@ -166,6 +167,10 @@ int sb_obs_loglik(sb_ctx *ctx, float *lh_out, double *obj_ll_out, double *sums_o
  * mode 1: log_q_out = sum log q[previous sources] under the current counts (log_q_back after a mode-0 sweep);
  * mode 2: the same for the committed sources.  Outputs may be NULL. */
 int sb_gibbs_sweep(sb_ctx *ctx, uint64_t step, int mode, double *log_q_out, int64_t *n_changed_out, float *ms);
+/* EM-style cluster initializer (SbayesInitializer.generate_clusters_em, sbayes/sampling/initializers.py:93-169):
+ * n_steps EM steps on the soft assignment z0 [G_tot, N] float32 (rows: clusters, then every confounder's groups);
+ * z_out [G_tot, N] receives the final assignment.  Uniform geo prior only. */
+int sb_init_em(sb_ctx *ctx, int32_t n_steps, const float *z0, float *z_out, float *ms);
 int sb_stats_buffer(sb_ctx *ctx, uint64_t *dev_ptr, int64_t *n_int32, int64_t *stride, int64_t *layout3);
 int sb_run(sb_ctx *ctx, int64_t n_steps, const sb_tape *tape, sb_step_record *records);
 int sb_run_async(sb_ctx *ctx, int64_t n_steps);                     /* enqueue only; sb_sync waits */

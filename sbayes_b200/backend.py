@@ -68,7 +68,7 @@ EXPORTS = ["sb_create", "sb_destroy", "sb_last_error", "sb_chain_config", "sb_se
            "sb_set_slots", "sb_counts_rebuild_mma", "sb_counts_rebuild_hist", "sb_info", "sb_stream",
            "sb_eval_batch", "sb_eval_stats", "sb_eval_terms", "sb_stats_buffer", "sb_eval_set_mode", "sb_obs_loglik",
            "sb_swap_scalars", "sb_clock_khz", "sb_posteriors", "sb_set_temperatures", "sb_gibbs_sweep",
-           "sb_export_samples", "sb_shard_handle", "sb_shard_attach", "sb_run_group"]
+           "sb_export_samples", "sb_shard_handle", "sb_shard_attach", "sb_run_group", "sb_init_em"]
 
 
 def _bind(lib):
@@ -88,6 +88,7 @@ def _bind(lib):
     lib.sb_shard_handle.argtypes = [vp, vp]
     lib.sb_shard_attach.argtypes = [vp, i32, i32, vp]
     lib.sb_run_group.argtypes = [vp, i32, i64, vp]
+    lib.sb_init_em.argtypes = [vp, i32, vp, vp, vp]
     lib.sb_posteriors.argtypes = [vp, vp]
     lib.sb_set_temperatures.argtypes = [vp, vp, vp]
     lib.sb_run.argtypes = [vp, i64, C.POINTER(_Tape), vp]
@@ -386,6 +387,15 @@ class DeviceContext:
         st = int(step) + (int(seed) if seed is not None else 0)
         self._ck(self.lib.sb_gibbs_sweep(self.h, st, {"draw": 0, "score_previous": 1, "score": 2}[mode], _ptr(lq), _ptr(ch), _ptr(ms)))
         return (lq, ch, float(ms[0])) if full else float(ms[0])
+
+    def init_em(self, z0: np.ndarray, n_steps: int, timing: bool = False):
+        """EM-style cluster initializer (SbayesInitializer.generate_clusters_em): z0 float32 [G_tot, N] ->
+        final soft assignment float32 [G_tot, N]."""
+        z0 = np.ascontiguousarray(z0, np.float32)
+        assert z0.shape == (self.prob.G_tot, self.prob.N)
+        out, ms = np.empty_like(z0), np.zeros(1, np.float32)
+        self._ck(self.lib.sb_init_em(self.h, int(n_steps), _ptr(z0), _ptr(out), _ptr(ms)))
+        return (out, float(ms[0])) if timing else out
 
     def stats_buffer(self):
         """(device address, int32 elements, per-state stride, (n_counts, n_hist, n_sizes))."""

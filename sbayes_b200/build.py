@@ -23,12 +23,33 @@ def sources():
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(s) for s in sources()):
         return OUT
-    cmd = [NVCC] + FLAGS + os.environ.get("SB_CFLAGS", "").split() + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, "sb_api.cu"), "-lcudart", "-o", OUT]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    # two translation units (sb_api.cu with the 4-component step kernel, sb_uc8.cu with the 8-component one),
+    # compiled in parallel, then linked into one shared library
+    common = [NVCC] + [f for f in FLAGS if f != "-shared"] + os.environ.get("SB_CFLAGS", "").split() + (["-Xptxas", "-v"] if verbose else [])
+    objs, procs = [], []
+    tag = os.path.splitext(os.path.basename(OUT))[0]
+    for src in ("sb_api.cu", "sb_uc8.cu"):
+        obj = os.path.join(CSRC, f"{tag}.{src[:-3]}.o")
+        objs.append(obj)
+        cmd = common + ["-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode:
+            sys.stderr.write(out)
+        if p.returncode:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    link = [NVCC, "-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-lcudart", "-o", OUT]
+    r = subprocess.run(link, capture_output=True, text=True)
     if verbose or r.returncode:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode:
-        raise RuntimeError("nvcc failed: " + " ".join(cmd))
+        raise RuntimeError("nvcc link failed: " + " ".join(link))
+    for o in objs:
+        try:
+            os.remove(o)
+        except OSError:
+            pass
     return OUT
 
 

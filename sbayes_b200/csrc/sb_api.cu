@@ -22,13 +22,13 @@
 #include "sb_core.cuh"
 #undef SB_UC
 #undef SB_NS
-#define SB_UC 8
-#define SB_NS uc8
-#include "sb_core.cuh"
-#undef SB_UC
-#undef SB_NS
+// (the instantiation for 5..8 components is its own translation unit, sb_uc8.cu: the two compile in parallel)
+const void *sb_uc8_run_kernel_ptr();
+void sb_uc8_run_kernel_host(const SbLaunch &L);        // emulator builds: the kernel body as a host function
+long sb_uc8_tiled_calls(int kind);
 #include "sb_counts.cuh"
 #include "sb_eval.cuh"
+#include "sb_init.cuh"
 using uc4::FixedSmem; using uc4::sb_fixed_smem; using uc4::Draws; using uc4::Philox4; using uc4::philox4x32_10; using uc4::u01_double;
 using uc4::sb_export_kernel; using uc4::sb_export_samples_kernel;
 
@@ -458,7 +458,7 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
     int capacity = 64;
 #else
     c->block = SB_BLOCK;
-    c->kernel = C <= 4 ? (const void *)uc4::sb_run_kernel : (const void *)uc8::sb_run_kernel;
+    c->kernel = C <= 4 ? (const void *)uc4::sb_run_kernel : sb_uc8_run_kernel_ptr();
     CK(cudaFuncSetAttribute(c->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
     CK(cudaFuncSetAttribute(c->kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     int per_sm = 0;
@@ -677,6 +677,7 @@ static int prepare_launch(sb_ctx *c, long long n_steps, const sb_tape *tape_dev,
         L.use_cluster = 0;
         L.xepoch_base = (++c->xlaunches) << 32;
         for (int p = 0; p < c->xworld; p++) {
+            L.arena_peer[p] = c->peer_arena[p];
             L.tred_peer[p] = peer_ptr(c, p, c->d_tred); L.xflag_peer[p] = peer_ptr(c, p, c->d_xflag);
             L.lstat_peer[p] = peer_ptr(c, p, c->d_lstat); L.gstat_peer[p] = peer_ptr(c, p, c->d_gstat);
         }
@@ -696,7 +697,7 @@ static int launch(sb_ctx *c, long long n_steps, const sb_tape *tape_dev, sb_step
 #ifdef SB_HOSTSIM
     if (c->xworld > 1) return fail(c, "emulator: chains sharded over ranks are launched together (sb_run_group)");
     if (c->P.C <= 4) hostsim::launch([&]() { uc4::sb_run_kernel(L); }, c->grid, c->block, c->smem);
-    else hostsim::launch([&]() { uc8::sb_run_kernel(L); }, c->grid, c->block, c->smem);
+    else hostsim::launch([&]() { sb_uc8_run_kernel_host(L); }, c->grid, c->block, c->smem);
 #else
     if (c->use_cluster && c->xworld == 1) {
         cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
@@ -820,7 +821,7 @@ SB_API int sb_run_group(sb_ctx **ctxs, int n, int64_t n_steps, sb_step_record *r
             const int cta = hostsim::cta();
             int i = 0;
             while (i + 1 < n && cta >= L[i + 1].cta_base) i++;
-            if (ctxs[i]->P.C <= 4) uc4::sb_run_kernel(L[i]); else uc8::sb_run_kernel(L[i]);
+            if (ctxs[i]->P.C <= 4) uc4::sb_run_kernel(L[i]); else sb_uc8_run_kernel_host(L[i]);
         }, total, c0->block, smem);
     }
 #else
@@ -1365,6 +1366,63 @@ SB_API int sb_obs_loglik(sb_ctx *c, float *lh_out, double *obj_ll_out, double *s
     return 0;
 }
 
+// EM-style cluster initializer (SbayesInitializer.generate_clusters_em, sbayes/sampling/initializers.py:93-169):
+// `n_steps` EM steps from the soft assignment z0 [G_tot, N] (float32; rows = clusters, then every confounder's
+// groups -- the reference's order); z_out receives the final assignment.  Uniform geo prior only (the reference
+// adds a geo term for cost-based priors).  ms = device time of all steps.
+SB_API int sb_init_em(sb_ctx *c, int32_t n_steps, const float *z0, float *z_out, float *ms) {
+    TRY(check_chain(c, 0));
+    if (!z0 || !z_out || n_steps < 1) return fail(c, "bad arguments");
+    if (c->P.geo) return fail(c, "sb_init_em: the geo term of the cost-based prior is not implemented (use the reference's initializer)");
+    const SbProblem &P = c->P;
+    const size_t G = P.G_tot, N = P.N, FS = (size_t)P.F * P.S;
+    const int n_ft = (P.F + SB_EM_FT - 1) / SB_EM_FT, n_gb = (int)((G + SB_EM_GB - 1) / SB_EM_GB);
+    int n_oblk = std::max(1, (8 * c->n_sm + n_ft * n_gb - 1) / (n_ft * n_gb));
+    n_oblk = (int)std::min<size_t>((size_t)n_oblk, std::max<size_t>(1, N / 64));
+    const int rows = (int)((N + n_oblk - 1) / n_oblk);
+    n_oblk = (int)((N + rows - 1) / rows);
+    const size_t keep = c->allocs.size();
+    struct Guard { sb_ctx *c; size_t keep; ~Guard() { while (c->allocs.size() > keep) {
+#ifdef SB_HOSTSIM
+        free(c->allocs.back());
+#else
+        cudaFree(c->allocs.back());
+#endif
+        c->allocs.pop_back(); } } } guard{c, keep};
+    SbEmArgs A; memset(&A, 0, sizeof A);
+    A.P = P; A.n_oblk = n_oblk; A.rows_per_blk = rows;
+    TRY(mk(c, &A.z, G * N)); TRY(mk(c, &A.partial, (size_t)n_oblk * G * FS)); TRY(mk(c, &A.logp, G * FS));
+    TRY(h2d(c, A.z, z0, sizeof(float) * G * N));
+    const size_t smem_counts = (size_t)(SB_EM_BLOCK / 32) * SB_EM_GB * P.S * 32 * 8, smem_assign = (size_t)(SB_EM_BLOCK / 32) * G * 8;
+#ifndef SB_HOSTSIM
+    if (smem_counts > 200 * 1024 || smem_assign > 200 * 1024) return fail(c, "sb_init_em: too many states / groups for the shared-memory bins");
+    CK(cudaFuncSetAttribute((const void *)sb_em_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_counts));
+    CK(cudaFuncSetAttribute((const void *)sb_em_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_assign));
+    EvTimer t(c->stream, ms);
+#else
+    if (ms) *ms = 0.f;
+#endif
+    for (int i = 0; i < n_steps; i++) {
+        const double temperature = pow((double)n_steps / (1.0 + (double)i), 3.0);
+        A.inv_temperature = 1.0 / temperature;
+#ifdef SB_HOSTSIM
+        hostsim::launch([&]() { sb_em_counts_kernel(A); }, n_ft * n_gb * n_oblk, 64, smem_counts);
+        hostsim::launch([&]() { sb_em_tables_kernel(A); }, (int)((G * P.F + 63) / 64), 64, 0);
+        hostsim::launch([&]() { sb_em_assign_kernel(A); }, 2, 64, smem_assign);
+#else
+        sb_em_counts_kernel<<<n_ft * n_gb * n_oblk, SB_EM_BLOCK, smem_counts, c->stream>>>(A);
+        sb_em_tables_kernel<<<(unsigned)((G * P.F + SB_EM_BLOCK - 1) / SB_EM_BLOCK), SB_EM_BLOCK, 0, c->stream>>>(A);
+        sb_em_assign_kernel<<<c->n_sm * 8, SB_EM_BLOCK, smem_assign, c->stream>>>(A);
+        CK(cudaGetLastError());
+#endif
+        c->launches += 3;
+    }
+#ifndef SB_HOSTSIM
+    t.stop();
+#endif
+    return d2h(c, z_out, A.z, sizeof(float) * G * N);
+}
+
 // device address and length (int32 elements) of the statistics block of all states, laid out
 // [state][counts G_tot*F*S | sizes K | H n_pat*2*F*C | pad]; layout3 = {n_counts, n_hist, n_sizes}.
 // A sharded run all-reduces the leading counts | sizes part (the histogram is shard-local)
@@ -1436,7 +1494,7 @@ SB_API int sb_counts_rebuild_mma(sb_ctx *c, int chain, int32_t *counts_out, floa
 
 #ifdef SB_HOSTSIM
 // emulator builds only (not part of the ABI): calls of the tiled passes per kind {alter, wide, jump, alter on feature pairs}
-SB_API long sb_hostsim_tiled_calls(int kind) { return kind >= 0 && kind < 4 ? uc4::g_tiled_calls[kind] + uc8::g_tiled_calls[kind] : -1; }
+SB_API long sb_hostsim_tiled_calls(int kind) { return kind >= 0 && kind < 4 ? uc4::g_tiled_calls[kind] + sb_uc8_tiled_calls(kind) : -1; }
 #endif
 
 #if defined(SB_PHASE_PROF) && !defined(SB_HOSTSIM)

@@ -246,6 +246,9 @@ struct RunC {
     int32_t *lcl;                              // rank-local replica of cluster_of of the current chain (or null)
     uint8_t *losel;                            // ... of osel
     int32_t *lstatp[SB_MAX_RANKS], *gstatp[SB_MAX_RANKS];   // statistics blocks of the current chain in every rank's memory
+    double *valp[2][SB_MAX_RANKS];             // the chain's val arrays in every rank's memory: an object's value lives on the rank
+                                               // that owns the object's block (written there, picked from there)
+    int32_t *llist;                            // this rank's own copy of list_a: CTA-private compaction lists stay local
     int *xabort;
 };
 
@@ -316,7 +319,7 @@ SB_DEV void xteam_wait(Run &R) {
                 if (sb_clock() - t0 > t_lim || sb_ld_volatile_i32(R.c->xabort)) { *R.c->xabort = 1; break; }
             }
         }
-        sb_threadfence_system();
+        // (the acquire loads above order everything that follows; the release store publishes the arrival of all ranks)
         sb_st_release_sys_u64(R.c->lrel, ev);
     } else {
         const long long t0 = sb_clock();
@@ -325,7 +328,6 @@ SB_DEV void xteam_wait(Run &R) {
             if (sb_clock() - t0 > 2 * t_lim || sb_ld_volatile_i32(R.c->xabort)) { *R.c->xabort = 1; break; }
         }
     }
-    sb_threadfence_system();
 }
 
 // a CTA's slot of the team reduction buffer (thread 0): with the objects sharded over GPUs the buffer is
@@ -438,7 +440,8 @@ SB_DEV void team_range(const Run &R, int n, int &lo, int &hi) {
 // Generator.choice(p=...), oracle/draws.py:cdf_pick).  val must be fully written by its
 // owners; contains one team barrier.  Returns the index (or -1 if total is not > 0).
 // extra[0..1] are summed over the team on the way (free ride on the same barrier).
-SB_DEV int team_pick(Run &R, const double *val, int n, double u, double &total, double *extra = nullptr) {
+SB_DEV int team_pick(Run &R, const double *val, int n, double u, double &total, double *extra = nullptr, double *const *val_peers = nullptr) {
+    // val_peers (objects sharded over GPUs): val of block r lives on rank r / lsize; `val` is this rank's copy
     int lo, hi; team_range(R, n, lo, hi);
     const int nthr = sb_nthr(), tid = sb_tid();
     // every thread owns a contiguous chunk of the CTA's block
@@ -470,6 +473,7 @@ SB_DEV int team_pick(Run &R, const double *val, int n, double u, double &total, 
         if (rb != R.rank) {       // the block that holds the target: every CTA scans it (no second barrier)
             const int B = (n + R.tsize - 1) / R.tsize;
             lo = rb * B; hi = lo + B; if (hi > n) hi = n;
+            if (val_peers) val = val_peers[rb / R.lsize];
             ch = (hi - lo + nthr - 1) / nthr;
             a = lo + tid * ch; b = a + ch; if (a > hi) a = hi; if (b > hi) b = hi;
             cs = 0.0;
@@ -605,6 +609,17 @@ SB_DEV int m_cl(const Run &R, int o) { return R.c->mcl ? (int)R.c->mcl[o] : (R.c
 SB_DEV int m_osel(const Run &R, int o) { return R.c->mosel ? (int)R.c->mosel[o] : (R.c->losel ? (int)R.c->losel[o] : (int)R.c->st.osel[o]); }
 SB_DEV int m_combo(const Run &R, int o) { return R.c->mcombo ? (int)R.c->mcombo[o] : sb_ldg(R.P->combo_id + o); }
 SB_DEV int m_pat(const Run &R, int o) { return R.c->combo_pat[m_combo(R, o)]; }
+// proposal values of objects (val[o]): with the objects sharded over GPUs the value of object o lives in the memory
+// of the rank that owns o's block of the team split -- written there by whoever computes it, summed and scanned
+// there by the pick
+SB_DEV double *val_slot(const Run &R, int b, int o) {
+    if (R.xworld == 1) return R.c->st.val[b] + o;
+    const int B = (R.P->N + R.tsize - 1) / R.tsize;
+    return R.c->valp[b][(o / B) / R.lsize] + o;
+}
+SB_DEV double *val_mine(const Run &R, int b) { return R.xworld == 1 ? R.c->st.val[b] : R.c->valp[b][R.xrank]; }
+SB_DEV int32_t *list_mine(const Run &R) { return R.c->llist ? R.c->llist : R.c->st.list_a; }
+
 SB_DEV int cl_of(const Run &R, int o, int view) {
     int c = m_cl(R, o);
     if (!view || R.chg_mode == CHG_NONE) return c;
@@ -1684,7 +1699,7 @@ SB_DEV void posterior_pass(Run &R, int k, int view, bool flat, bool use_geo, int
     if (!flat && hi - lo >= 8 * sb_nwarps()) {
         // few selected objects among many (the members of one cluster): compact them first, then a warp per
         // selected object; the others get their zero in the compaction sweep
-        int32_t *list = R.c->st.list_a + lo;
+        int32_t *list = list_mine(R) + lo;
         const int n = cta_compact(R, lo, hi, list, [&](int o) { return (bool)sel(o); }, [&](int o) { lane_out(o, false, 0.0); });
         batch_items<Marg>(0, n,
             [&](int i) {
@@ -1725,7 +1740,9 @@ SB_DEV Prop op_alter_cluster(Run &R, bool gibbsish, bool use_geo, int nb) {
     else if (size == P.max_size) { grow = false; extra = -log(2.0); }
     else grow = draw_uniform(R.D, SITE_GROW) < R.p_grow;
     const bool flat = R.sfp || !gibbsish;
-    double *val = R.c->st.val[R.vpar];
+    double *val = val_mine(R, R.vpar);
+    double *const *vpeers = R.xworld > 1 ? R.c->valp[R.vpar] : nullptr;
+    const int vb = R.vpar;
     const int free_now = n_free(R);
 
     if (grow) {
@@ -1733,15 +1750,15 @@ SB_DEV Prop op_alter_cluster(Run &R, bool gibbsish, bool use_geo, int nb) {
         PH(R, 2);
         double ex[2] = {0.0, 0.0};
         posterior_pass(R, k, 0, flat, use_geo, size, free_now, [&](int o) { return nb == NB_EVERYWHERE ? m_cl(R, o) < 0 : R.c->st.flag_b[o] != 0; },
-                       [&](int o, bool on, double post) { val[o] = on ? heat(R, post) : 0.0; if (on) ex[0] += 1.0;
+                       [&](int o, bool on, double post) { *val_slot(R, vb, o) = on ? heat(R, post) : 0.0; if (on) ex[0] += 1.0;
                        });
         double total;
-        int o = team_pick(R, val, P.N, draw_uniform(R.D, SITE_OBJECT), total, ex);
+        int o = team_pick(R, val, P.N, draw_uniform(R.D, SITE_OBJECT), total, ex, vpeers);
         PH(R, 4);
         R.vpar ^= 1;
         if (ex[0] == 0.0 || size == P.max_size) return pr;
         if (o < 0) return pr;
-        double lq_obj = log(val[o] / total);
+        double lq_obj = log(*val_slot(R, vb, o) / total);
         pr.changed = 1; pr.M = 1;
         R.chg_mode = CHG_ONE; R.chg_o = o; R.chg_new = k;
         if (sb_tid() == 0) R.c->slist[0] = o;
@@ -1761,13 +1778,13 @@ SB_DEV Prop op_alter_cluster(Run &R, bool gibbsish, bool use_geo, int nb) {
     } else {
         if (size == P.min_size) return pr;
         posterior_pass(R, k, 0, flat, use_geo, size, size, [&](int o) { return m_cl(R, o) == k; },
-                       [&](int o, bool on, double post) { val[o] = on ? 1.0 - heat(R, post) : 0.0; });
+                       [&](int o, bool on, double post) { *val_slot(R, vb, o) = on ? 1.0 - heat(R, post) : 0.0; });
         double total;
-        int o = team_pick(R, val, P.N, draw_uniform(R.D, SITE_OBJECT), total);
+        int o = team_pick(R, val, P.N, draw_uniform(R.D, SITE_OBJECT), total, nullptr, vpeers);
         PH(R, 4);
         R.vpar ^= 1;
         if (o < 0) return pr;
-        double lq_obj = log(val[o] / total);
+        double lq_obj = log(*val_slot(R, vb, o) / total);
         pr.changed = 1; pr.M = 1;
         R.chg_mode = CHG_ONE; R.chg_o = o; R.chg_new = -1;
         if (sb_tid() == 0) R.c->slist[0] = o;
@@ -1879,7 +1896,7 @@ SB_DEV Prop op_alter_cluster_wide(Run &R, bool use_geo) {
     int k = draw_index(R.D, SITE_CLUSTER, 0, P.K);
     int size = R.c->rp.sizes[k];
     int n_av = team_compact(R, P.N, R.c->st.list_b, [&](int o) { int c = m_cl(R, o); return c < 0 || c == k; });
-    double *p = R.c->st.val[R.vpar];
+    double *p = val_mine(R, R.vpar);      // indexed by position in the list of available objects; every CTA touches its own range only
     wide_probs(R, p, k, n_av, 0, use_geo, size);
     int lo, hi; team_range(R, n_av, lo, hi);
     // redraw until the membership changes (operators.py:1515-1517)
@@ -1947,13 +1964,15 @@ SB_DEV Prop op_cluster_jump(Run &R) {
     draw_pair(R.D, SITE_JUMP, P.K, k_src, k_tgt);
     if (R.c->rp.sizes[k_src] <= P.min_size || R.c->rp.sizes[k_tgt] >= P.max_size) return pr;
     int lo, hi; team_range(R, P.N, lo, hi);
-    double *val = R.c->st.val[R.vpar];
+    double *val = val_mine(R, R.vpar);
+    double *const *vpeers = R.xworld > 1 ? R.c->valp[R.vpar] : nullptr;
+    const int vb = R.vpar;
     if (R.c->tile && pass_uses_tables(R, R.c->rp.sizes[k_src])) {
         tiled_pass<TK_JUMP>(R, k_src, k_tgt, [&](int o) { return m_cl(R, o) == k_src; },
-            [&](int o, bool on, const Prod &a, const Prod &b) { val[o] = on ? jump_tail(R, a, b) : 0.0; });
+            [&](int o, bool on, const Prod &a, const Prod &b) { *val_slot(R, vb, o) = on ? jump_tail(R, a, b) : 0.0; });
         if (R.tsize > 1) team_sync(R);
     } else {
-        int32_t *list = R.c->st.list_a + lo;
+        int32_t *list = list_mine(R) + lo;
         const int n = cta_compact(R, lo, hi, list, [&](int o) { return m_cl(R, o) == k_src; }, [&](int o) { val[o] = 0.0; });
         batch_items<JumpAcc>(0, n,
             [&](int i) { JumpAcc a; a.on = 1; jump_marginals(R, list[i], k_src, k_tgt, a.ps, a.pj); return a; },
@@ -1962,11 +1981,11 @@ SB_DEV Prop op_cluster_jump(Run &R) {
     sb_cta_sync();
     PH(R, 18);
     double total;
-    int o = team_pick(R, val, P.N, draw_uniform(R.D, SITE_OBJECT), total);
+    int o = team_pick(R, val, P.N, draw_uniform(R.D, SITE_OBJECT), total, nullptr, vpeers);
     PH(R, 4);
     R.vpar ^= 1;
     if (o < 0) return pr;
-    double lq_obj = log(val[o] / total);
+    double lq_obj = log(*val_slot(R, vb, o) / total);
     pr.changed = 1; pr.M = 1;
     R.chg_mode = CHG_ONE; R.chg_o = o; R.chg_new = k_tgt;
     if (sb_tid() == 0) R.c->slist[0] = o;
@@ -1979,7 +1998,7 @@ SB_DEV Prop op_cluster_jump(Run &R) {
         tiled_pass<TK_JUMP>(R, k_tgt, k_src, [&](int j) { return cl_of(R, j, 1) == k_tgt; },
             [&](int j, bool on, const Prod &a, const Prod &b) { if (on) { double v = jump_tail(R, a, b); s[0] += v; if (j == o) s[1] = v; } });
     } else {
-        int32_t *list = R.c->st.list_a + lo;
+        int32_t *list = list_mine(R) + lo;
         const int n = cta_compact(R, lo, hi, list, [&](int j) { return cl_of(R, j, 1) == k_tgt; }, [&](int) {});
         batch_items<JumpAcc>(0, n,
             [&](int i) { JumpAcc a; a.on = 1; jump_marginals(R, list[i], k_tgt, k_src, a.ps, a.pj); return a; },
@@ -2500,7 +2519,7 @@ SB_KERNEL_BIG sb_run_kernel(const SB_GRID_CONSTANT SbLaunch L) {
         const size_t tred_off = (size_t)team_id * 2 * L.team * SB_MAX_RANKS * SB_REDW;
         R.c->bar = L.bars + team_id;
         R.c->tred = L.tred + tred_off;
-        R.c->lcl = nullptr; R.c->losel = nullptr; R.c->xabort = L.xabort; R.c->lrel = L.lrelease ? L.lrelease + team_id : nullptr;
+        R.c->lcl = nullptr; R.c->losel = nullptr; R.c->llist = nullptr; R.c->xabort = L.xabort; R.c->lrel = L.lrelease ? L.lrelease + team_id : nullptr;
         for (int p = 0; p < SB_MAX_RANKS; p++) {
             R.c->tredp[p] = p < R.xworld && L.tred_peer[p] ? L.tred_peer[p] + tred_off : nullptr;
             R.c->xflagp[p] = p < R.xworld && L.xflag_peer[p] ? L.xflag_peer[p] + (size_t)team_id * SB_MAX_RANKS : nullptr;
@@ -2520,7 +2539,9 @@ SB_KERNEL_BIG sb_run_kernel(const SB_GRID_CONSTANT SbLaunch L) {
                 for (int p = 0; p < R.xworld; p++) {
                     R.c->lstatp[p] = L.lstat_peer[p] + (size_t)slot->state * L.stats_stride;
                     R.c->gstatp[p] = L.gstat_peer[p] + (size_t)slot->state * L.stats_stride;
+                    for (int b = 0; b < 2; b++) R.c->valp[b][p] = (double *)(L.arena_peer[p] + ((char *)R.c->st.val[b] - L.arena_peer[0]));
                 }
+                R.c->llist = (int32_t *)(L.arena_peer[R.xrank] + ((char *)R.c->st.list_a - L.arena_peer[0]));
             }
         }
         sb_cta_sync();

@@ -182,6 +182,7 @@ struct SbLaunch {
     double *tred_peer[SB_MAX_RANKS];                // every rank's copy of tred
     unsigned long long *xflag_peer[SB_MAX_RANKS];   // every rank's flag words [n_teams][SB_MAX_RANKS]
     unsigned long long *lrelease;                   // [n_teams] release word of the local barrier phase
+    char *arena_peer[SB_MAX_RANKS];                 // every rank's arena (same layout everywhere: an array is found at the same offset)
     int32_t *lstat_peer[SB_MAX_RANKS];              // every rank's partial statistics [n_chains][stats_stride]
     int32_t *gstat_peer[SB_MAX_RANKS];              // every rank's copy of the reduced statistics
     size_t stats_stride;
