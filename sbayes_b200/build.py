@@ -15,23 +15,49 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "-shared", "-I" + os.path.join(ROOT, "include")]
 
 
+# translation units and the headers each one sees: an object file is rebuilt only when one of them changed, so an
+# edit of the stand-alone kernels (seconds) does not recompile the step kernel (minutes)
+COMMON = ["sb_platform.cuh", "sb_types.h", "sb_plans.h", "sb_philox.cuh"]
+UNITS = {
+    "sb_api.cu": COMMON + ["sb_ctx.h", "sb_core.cuh"],                     # the 4-component step kernel + the C ABI
+    "sb_uc8.cu": COMMON + ["sb_core.cuh"],                                  # the 8-component step kernel
+    "sb_api_eval.cu": COMMON + ["sb_ctx.h", "sb_eval.cuh", "sb_counts.cuh", "sb_init.cuh"],   # the streaming kernels
+}
+
+
 def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))) + \
         [os.path.join(ROOT, "include", "sbayes_b200.h")]
 
 
+def _newer(target, deps):
+    return os.path.exists(target) and all(os.path.getmtime(target) >= os.path.getmtime(d) for d in deps)
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(s) for s in sources()):
+    import fcntl
+    with open(os.path.join(CSRC, ".build.lock"), "w") as lock:      # one build at a time (tests and tools may race)
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        return _build(force, verbose)
+
+
+def _build(force: bool, verbose: bool) -> str:
+    if not force and _newer(OUT, sources()):
         return OUT
-    # two translation units (sb_api.cu with the 4-component step kernel, sb_uc8.cu with the 8-component one),
-    # compiled in parallel, then linked into one shared library
-    common = [NVCC] + [f for f in FLAGS if f != "-shared"] + os.environ.get("SB_CFLAGS", "").split() + (["-Xptxas", "-v"] if verbose else [])
+    extra = os.environ.get("SB_CFLAGS", "").split()
+    common = [NVCC] + [f for f in FLAGS if f != "-shared"] + extra
     objs, procs = [], []
     tag = os.path.splitext(os.path.basename(OUT))[0]
-    for src in ("sb_api.cu", "sb_uc8.cu"):
+    flagfile = os.path.join(CSRC, f"{tag}.flags")
+    flags_now = " ".join(common)
+    same_flags = os.path.exists(flagfile) and open(flagfile).read() == flags_now
+    for src, hdrs in UNITS.items():
         obj = os.path.join(CSRC, f"{tag}.{src[:-3]}.o")
         objs.append(obj)
-        cmd = common + ["-c", os.path.join(CSRC, src), "-o", obj]
+        deps = [os.path.join(CSRC, src), os.path.join(ROOT, "include", "sbayes_b200.h")] + [os.path.join(CSRC, h) for h in hdrs]
+        if not force and same_flags and _newer(obj, deps):
+            continue
+        cmd = common + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:
         out, _ = p.communicate()
@@ -39,17 +65,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    with open(flagfile, "w") as f:
+        f.write(flags_now)
     link = [NVCC, "-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-lcudart", "-o", OUT]
     r = subprocess.run(link, capture_output=True, text=True)
     if verbose or r.returncode:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode:
         raise RuntimeError("nvcc link failed: " + " ".join(link))
-    for o in objs:
-        try:
-            os.remove(o)
-        except OSError:
-            pass
     return OUT
 
 

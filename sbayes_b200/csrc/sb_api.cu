@@ -3,18 +3,7 @@
 //
 // Product build: nvcc -gencode arch=compute_100a,code=sm_100a.  With -DSB_HOSTSIM (tests
 // only) the device memory is host memory and launches go to the fibre emulator.
-#include <string>
-#include <vector>
-#include <cstring>
-#include <cstdio>
-#include <cstdlib>
-#include <cmath>
-#include <algorithm>
-#include <map>
-#include <functional>
-#include <cstddef>
-#include <unistd.h>
-
+#include "sb_ctx.h"
 // the step kernel, instantiated for up to 4 and up to 8 mixture components (the loops over
 // components are unrolled to that width; the narrow one is what the reference's configs need)
 #define SB_UC 4
@@ -26,132 +15,10 @@
 const void *sb_uc8_run_kernel_ptr();
 void sb_uc8_run_kernel_host(const SbLaunch &L);        // emulator builds: the kernel body as a host function
 long sb_uc8_tiled_calls(int kind);
-#include "sb_counts.cuh"
-#include "sb_eval.cuh"
-#include "sb_init.cuh"
 using uc4::FixedSmem; using uc4::sb_fixed_smem; using uc4::Draws; using uc4::Philox4; using uc4::philox4x32_10; using uc4::u01_double;
 using uc4::sb_export_kernel; using uc4::sb_export_samples_kernel;
 
-#ifdef SB_HOSTSIM
-#define SB_API extern "C" __attribute__((visibility("default")))
-typedef void *sb_stream_t;
-#else
-#define SB_API extern "C" __attribute__((visibility("default")))
-typedef cudaStream_t sb_stream_t;
-#endif
-
-static std::string g_create_error;
-
-struct sb_ctx {
-    int device = 0, n_chains = 0, team = 1, n_teams = 1, grid = 1, block = 256, n_sm = 1, smem_members = 0, clock_khz = 1000000;
-    size_t smem = 0;
-    long long launches = 0;
-    SbProblem P;
-    std::vector<SbShared> h_states;
-    SbShared *d_states = nullptr;
-    SbPlace place;
-    char *d_rep = nullptr;
-    int use_cluster = 0, req_team = 0;
-    size_t rep_alloc = 0;
-    const void *kernel = nullptr;
-    std::function<int(int, int)> place_fn;
-    std::vector<sb_chain_cfg> h_cfg;
-    std::vector<int32_t> cg_ptr, cg_idx;
-    SbSlot *d_slots = nullptr;
-    unsigned long long *d_bars = nullptr;
-    double *d_tred = nullptr;
-    // everything another GPU may have to reach when the objects of a chain are sharded over GPUs (per-chain
-    // state, reduction buffer, flags, statistics blocks) is carved from ONE allocation, the arena: a peer maps
-    // it once (CUDA IPC) and finds every array at the same offset as in its own arena
-    char *arena = nullptr; size_t arena_size = 0, arena_used = 0; bool arena_dry = false;
-    int xrank = 0, xworld = 1;
-    char *peer_arena[SB_MAX_RANKS] = {nullptr};
-    bool peer_opened[SB_MAX_RANKS] = {false};
-    unsigned long long xlaunches = 0;
-    unsigned long long *d_xflag = nullptr, *d_lrelease = nullptr;
-    int32_t *d_lstat = nullptr, *d_gstat = nullptr, *d_lcl = nullptr;
-    uint8_t *d_losel = nullptr;
-    int *d_xabort = nullptr;
-    double *d_glh_all = nullptr, *d_geo_all = nullptr;   // [n_chains, G_tot], [n_chains, K] export copies, one allocation each
-    SbExport exp_;                       // staging buffers of sb_export_samples (allocated on first use)
-    int exp_ok = 0;
-    int32_t *d_exp_idx = nullptr;
-    double *d_post_all = nullptr;        // [n_chains, 8] the post blocks of all states, one allocation
-    std::vector<int> h_slot_state;       // host mirror of SbSlot::state (changed only by sb_swap / sb_set_slots)
-    uint8_t *d_src_tmp = nullptr;
-    int32_t *d_counts_tmp = nullptr;
-    // stand-alone evaluation (sb_eval.cuh): the int32 statistics of all states are one block
-    int32_t *d_stats = nullptr;
-    size_t stats_stride = 0;          // int32 per state: counts | sizes | H, padded to 16 B
-    SbEvalPlan eplan;
-    int eplan_ok = 0;
-    SbMmaPlan mplan;                  // tcgen05 statistics pass over all states
-    int mplan_ok = 0, stats_mode = 0; // 0 = shared-memory histogram, 1 = int8 tensor-core contraction
-    double *d_epartial = nullptr, *d_egeo = nullptr, *d_epost = nullptr;
-    unsigned *d_eticket = nullptr;
-    int *d_eerr = nullptr;
-    // observation likelihood (allocated by the first sb_obs_loglik)
-    SbObsPlan oplan;
-    float *d_obs_out = nullptr;
-    double *d_obs_part = nullptr, *d_obs_ll = nullptr, *d_obs_sums = nullptr;
-    unsigned long long *d_gibbs_changed = nullptr;
-    std::vector<void *> allocs;
-    sb_stream_t stream = 0;
-    std::string err;
-};
-
-// ---------------------------------------------------------------------------------------
-// device memory shim
-// ---------------------------------------------------------------------------------------
-#ifdef SB_HOSTSIM
-static int dev_alloc(sb_ctx *c, void **p, size_t n) { *p = calloc(1, n ? n : 1); c->allocs.push_back(*p); return *p ? 0 : -1; }
-static void dev_free_all(sb_ctx *c) { for (void *p : c->allocs) free(p); c->allocs.clear(); }
-static int h2d(sb_ctx *, void *d, const void *h, size_t n) { memcpy(d, h, n); return 0; }
-static int d2h(sb_ctx *, void *h, const void *d, size_t n) { memcpy(h, d, n); return 0; }
-static int dev_zero(sb_ctx *, void *d, size_t n) { memset(d, 0, n); return 0; }
-static int dev_sync(sb_ctx *) { return 0; }
-#else
-#define CK(call)                                                                                   \
-    do {                                                                                           \
-        cudaError_t e_ = (call);                                                                   \
-        if (e_ != cudaSuccess) {                                                                   \
-            c->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
-            return -2;                                                                             \
-        }                                                                                          \
-    } while (0)
-static int dev_alloc(sb_ctx *c, void **p, size_t n) {
-    CK(cudaMalloc(p, n ? n : 1));
-    c->allocs.push_back(*p);
-    CK(cudaMemsetAsync(*p, 0, n ? n : 1, c->stream));
-    return 0;
-}
-static void dev_free_all(sb_ctx *c) { for (void *p : c->allocs) cudaFree(p); c->allocs.clear(); }
-static int h2d(sb_ctx *c, void *d, const void *h, size_t n) { CK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream)); return 0; }
-static int d2h(sb_ctx *c, void *h, const void *d, size_t n) { CK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); return 0; }
-static int dev_zero(sb_ctx *c, void *d, size_t n) { CK(cudaMemsetAsync(d, 0, n, c->stream)); return 0; }
-static int dev_sync(sb_ctx *c) { CK(cudaStreamSynchronize(c->stream)); return 0; }
-#endif
-
-#define TRY(x) do { int r_ = (x); if (r_) return r_; } while (0)
-template <class T> static int up(sb_ctx *c, const T **dst, const std::vector<T> &v) {
-    void *p; TRY(dev_alloc(c, &p, v.size() * sizeof(T)));
-    if (!v.empty()) TRY(h2d(c, p, v.data(), v.size() * sizeof(T)));
-    *dst = (const T *)p; return 0;
-}
-template <class T> static int mk(sb_ctx *c, T **dst, size_t n) { void *p; TRY(dev_alloc(c, &p, n * sizeof(T))); *dst = (T *)p; return 0; }
-
-// carve n elements from the arena (256-byte aligned); in the dry pass only the size is accumulated
-template <class T> static int amk(sb_ctx *c, T **dst, size_t n) {
-    const size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
-    if (!c->arena_dry) {
-        if (c->arena_used + bytes > c->arena_size) { c->err = "internal: arena overflow"; return -1; }
-        *dst = (T *)(c->arena + c->arena_used);
-    } else *dst = nullptr;
-    c->arena_used += bytes;
-    return 0;
-}
-
-static int fail(sb_ctx *c, const char *msg) { if (c) c->err = msg; else g_create_error = msg; return -1; }
+std::string g_create_error;
 
 // ---------------------------------------------------------------------------------------
 SB_API const char *sb_last_error(const sb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -558,36 +425,7 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
     TRY(mk(c, &c->d_slots, n_chains)); TRY(h2d(c, c->d_slots, slots.data(), sizeof(SbSlot) * n_chains));
     TRY(mk(c, &c->d_bars, c->n_teams + 1));
     TRY(mk(c, &c->d_src_tmp, nS)); TRY(mk(c, &c->d_counts_tmp, nG));
-    // stand-alone evaluation kernels
-    {
-        size_t budget = 56 * 1024;       // measured best (profiles/r1k_eval_smem_sweep.txt): three CTAs per SM by registers
-#ifdef SB_HOSTSIM
-        if (getenv("SB_HOSTSIM_EVAL_SMEM")) budget = (size_t)atol(getenv("SB_HOSTSIM_EVAL_SMEM"));
-#else
-        if (getenv("SB_EVAL_SMEM_KB")) budget = (size_t)atol(getenv("SB_EVAL_SMEM_KB")) * 1024;   // tuning knob
-#endif
-        c->eplan_ok = sb_eval_make_plan(P, n_chains, c->n_sm, budget, &c->eplan) == 0;
-        if (!c->eplan_ok) c->eplan_ok = sb_eval_make_plan(P, n_chains, c->n_sm, 220 * 1024, &c->eplan) == 0;
-#ifdef SB_HOSTSIM
-        if (c->eplan_ok && getenv("SB_HOSTSIM_EVAL_OBLK")) {     // tests: force several object blocks
-            int nb = atoi(getenv("SB_HOSTSIM_EVAL_OBLK"));
-            c->eplan.rows_per_blk = (N + nb - 1) / nb; c->eplan.n_oblk = (N + c->eplan.rows_per_blk - 1) / c->eplan.rows_per_blk;
-        }
-#else
-        if (c->eplan_ok) {
-            CK(cudaFuncSetAttribute((const void *)sb_eval_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->eplan.smem));
-            if (P.geo) CK(cudaFuncSetAttribute((const void *)sb_eval_geo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->smem_members * 12 + 64)));
-        }
-#endif
-        c->mplan_ok = sb_mma_make_plan(P, n_chains, c->n_sm, &c->mplan) == 0;
-#ifndef SB_HOSTSIM
-        if (c->mplan_ok) CK(cudaFuncSetAttribute((const void *)sb_counts_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->mplan.smem));
-#else
-        c->mplan_ok = 0;
-#endif
-        TRY(mk(c, &c->d_epartial, (size_t)n_chains * SB_EVAL_MAXPARTS * 4)); TRY(mk(c, &c->d_eticket, (size_t)n_chains));
-        TRY(mk(c, &c->d_egeo, (size_t)n_chains * K)); TRY(mk(c, &c->d_epost, (size_t)n_chains * 8)); TRY(mk(c, &c->d_eerr, 1));
-    }
+    TRY(sb_eval_setup(c));        // plans and scratch buffers of the stand-alone kernels (sb_api_eval.cu)
     return dev_sync(c);
 }
 
@@ -599,16 +437,6 @@ SB_API int sb_create(const sb_problem_desc *desc, int device, int n_chains, int 
     *out = c;
     return 0;
 }
-
-static int check_chain(sb_ctx *c, int chain) {
-    if (!c) return -1;
-    if (chain < 0 || chain >= c->n_chains) return fail(c, "chain index out of range");
-#ifndef SB_HOSTSIM
-    CK(cudaSetDevice(c->device));
-#endif
-    return 0;
-}
-static int get_slot(sb_ctx *c, int chain, SbSlot *s) { return d2h(c, s, c->d_slots + chain, sizeof(SbSlot)); }
 
 SB_API int sb_chain_config(sb_ctx *c, int chain, const sb_chain_cfg *cfg) {
     TRY(check_chain(c, chain));
@@ -1149,280 +977,6 @@ SB_API int sb_swap(sb_ctx *c, int attempts, int only_neighbours, uint64_t seed, 
     return 0;
 }
 
-// ---------------------------------------------------------------------------------------
-// stand-alone full evaluation of every chain (sb_eval.cuh)
-// ---------------------------------------------------------------------------------------
-static SbEvalArgs eval_args(sb_ctx *c, long long n_global) {
-    SbEvalArgs A; memset(&A, 0, sizeof A);
-    A.P = c->P; A.states = c->d_states; A.slots = c->d_slots; A.n_states = c->n_chains; A.plan = c->eplan;
-    A.partial = c->d_epartial; A.ticket = c->d_eticket; A.geo_val = c->d_egeo; A.post = c->d_epost; A.err = c->d_eerr;
-    A.n_global = n_global > 0 ? n_global : c->P.N; A.geo_cap = c->smem_members;
-    return A;
-}
-#ifndef SB_HOSTSIM
-struct EvTimer {
-    cudaEvent_t e0 = nullptr, e1 = nullptr; cudaStream_t s; float *out;
-    EvTimer(cudaStream_t st, float *o) : s(st), out(o) { if (out) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); } }
-    void stop() { if (out) { cudaEventRecord(e1, s); cudaEventSynchronize(e1); cudaEventElapsedTime(out, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1); out = nullptr; } }
-};
-#endif
-
-// statistics pass: counts, source histogram and cluster sizes of every state (zeroed first)
-SB_API int sb_eval_stats(sb_ctx *c, float *ms) {
-    TRY(check_chain(c, 0));
-    if (!c->eplan_ok && c->stats_mode == 0) return fail(c, "evaluation histogram does not fit in shared memory (too many groups x states)");
-    SbEvalArgs A = eval_args(c, 0);
-    const int grid = c->n_chains * c->eplan.n_ftiles * c->eplan.n_oblk;
-#ifdef SB_HOSTSIM
-    if (ms) *ms = 0.f;
-    TRY(dev_zero(c, c->d_stats, sizeof(int32_t) * c->stats_stride * c->n_chains));
-    hostsim::launch([&]() { sb_eval_hist_kernel(A); }, grid, 64, c->eplan.smem);
-#else
-    EvTimer t(c->stream, ms);
-    TRY(dev_zero(c, c->d_stats, sizeof(int32_t) * c->stats_stride * c->n_chains));
-    if (c->stats_mode == 1) {
-        if (!c->mplan_ok) return fail(c, "the tensor-core statistics pass does not fit this problem (more than 256 group columns)");
-        sb_counts_mma_kernel<<<c->n_chains * c->mplan.n_ftiles * c->mplan.n_oblk, SB_MMA_BLOCK, c->mplan.smem, c->stream>>>(A, c->mplan);
-    } else {
-        sb_eval_hist_kernel<<<grid, SB_EVAL_BLOCK, c->eplan.smem, c->stream>>>(A);
-    }
-    CK(cudaGetLastError());
-    t.stop();
-#endif
-    c->launches++;
-    return 0;
-}
-
-// posterior terms of every chain from the statistics currently in the ctx; `n_global` = number
-// of objects of the whole problem when this ctx holds a shard of the objects (0: not sharded)
-SB_API int sb_eval_terms(sb_ctx *c, int64_t n_global, sb_posterior_t *out, float *ms) {
-    TRY(check_chain(c, 0));
-    if (!c->eplan_ok) return fail(c, "evaluation plan unavailable (the histogram bins of one 16-feature tile do not fit in shared memory)");
-    SbEvalArgs A = eval_args(c, (long long)n_global);
-    if (c->P.geo && n_global > 0 && n_global != c->P.N) return fail(c, "the geo prior is not supported with sharded objects");
-    TRY(dev_zero(c, c->d_eticket, sizeof(unsigned) * c->n_chains));
-    TRY(dev_zero(c, c->d_eerr, sizeof(int)));
-#ifdef SB_HOSTSIM
-    if (ms) *ms = 0.f;
-    if (c->P.geo) hostsim::launch([&]() { sb_eval_geo_kernel(A); }, c->n_chains * c->P.K, 64, (size_t)c->smem_members * 12 + 64);
-    hostsim::launch([&]() { sb_eval_terms_kernel(A); }, c->n_chains * c->eplan.n_parts, 64, 1024);
-#else
-    EvTimer t(c->stream, ms);
-    if (c->P.geo) {
-        sb_eval_geo_kernel<<<c->n_chains * c->P.K, 128, (size_t)c->smem_members * 12 + 64, c->stream>>>(A);
-        CK(cudaGetLastError());
-        c->launches++;
-    }
-    sb_eval_terms_kernel<<<c->n_chains * c->eplan.n_parts, SB_EVAL_BLOCK, 1024, c->stream>>>(A);
-    CK(cudaGetLastError());
-    t.stop();
-#endif
-    c->launches++;
-    if (out) {
-        std::vector<double> post((size_t)c->n_chains * 8);
-        TRY(d2h(c, post.data(), c->d_epost, sizeof(double) * post.size()));
-        int err = 0; TRY(d2h(c, &err, c->d_eerr, sizeof(int)));
-        if (err == 2) return fail(c, "source component out of range in state");
-        if (err == 3) return fail(c, "cluster larger than the geo-prior member list");
-        std::vector<SbSlot> slots(c->n_chains);
-        TRY(d2h(c, slots.data(), c->d_slots, sizeof(SbSlot) * c->n_chains));
-        for (int i = 0; i < c->n_chains; i++) {
-            const double *p = &post[(size_t)slots[i].state * 8];
-            out[i].ll = p[0]; out[i].size_prior = p[1]; out[i].geo_prior = p[2]; out[i].weights_prior = p[3]; out[i].source_prior = p[4];
-            out[i].prior = p[1] + p[2] + p[3] + p[4];
-        }
-    }
-    return 0;
-}
-
-// which statistics pass sb_eval_stats / sb_eval_batch run: 0 = shared-memory histogram,
-// 1 = int8 tcgen05 contraction (sb_counts.cuh)
-SB_API int sb_eval_set_mode(sb_ctx *c, int mode) {
-    if (!c) return -1;
-    if (mode != 0 && mode != 1) return fail(c, "unknown statistics mode");
-#ifdef SB_HOSTSIM
-    if (mode == 1) return fail(c, "the tensor-core statistics pass needs a GPU");
-#endif
-    if (mode == 1 && !c->mplan_ok) return fail(c, "the tensor-core statistics pass does not fit this problem (more than 256 group columns)");
-    c->stats_mode = mode;
-    return 0;
-}
-
-// uncached likelihood + prior of every chain: out[n_chains]; ms (may be NULL) receives the
-// device time of {statistics pass, terms}
-SB_API int sb_eval_batch(sb_ctx *c, sb_posterior_t *out, float *ms2) {
-    TRY(sb_eval_stats(c, ms2 ? ms2 : nullptr));
-    return sb_eval_terms(c, 0, out, ms2 ? ms2 + 1 : nullptr);
-}
-
-// per-object partial sums / per-chain sums shared by the observation-likelihood and the Gibbs-sweep kernels
-static int ensure_obs_buffers(sb_ctx *c) {
-    if (c->d_obs_part) return 0;
-    const SbProblem &P = c->P;
-    if (sb_obs_make_plan(P, c->n_chains, c->n_sm, &c->oplan)) return fail(c, "per-tile tables (groups x states x 16 features) do not fit in shared memory");
-    TRY(mk(c, &c->d_obs_part, (size_t)c->n_chains * c->oplan.n_ftiles * P.N));
-    TRY(mk(c, &c->d_obs_ll, (size_t)c->n_chains * P.N)); TRY(mk(c, &c->d_obs_sums, (size_t)c->n_chains));
-    TRY(mk(c, &c->d_gibbs_changed, (size_t)c->n_chains));
-#ifndef SB_HOSTSIM
-    CK(cudaFuncSetAttribute((const void *)sb_obs_lik_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->oplan.smem));
-    CK(cudaFuncSetAttribute((const void *)sb_gibbs_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->oplan.smem));
-#endif
-    return 0;
-}
-
-// Full-sweep source Gibbs of every chain (GibbsSampleSource with ObjectSelector.ALL,
-// sbayes/sampling/operators.py:496-574; the initializer's use, sbayes/sampling/initializers.py:285-310).
-//   mode 0  resample the source of EVERY observation of every chain from its conditional given the current
-//           counts and weights (draws: Philox (chain seed, step, SITE_GIBBS, o * F + f)); commits the new
-//           sources; log_q_out[chain] = sum log q[new], n_changed_out[chain] = reassigned observations
-//   mode 1  log_q_out = sum log q[previous sources] under the CURRENT counts (the log_q_back of the proposal,
-//           to be called after a mode-0 sweep); mode 2: the same for the committed sources
-// The statistics pass runs first (the tables need the committed counts).  The cached posterior of the chains
-// (sb_posterior) is stale after a mode-0 sweep until the next sb_run / sb_eval.  Outputs may be NULL; ms
-// receives the device time of the sweep kernel + reduction.
-SB_API int sb_gibbs_sweep(sb_ctx *c, uint64_t step, int mode, double *log_q_out, int64_t *n_changed_out, float *ms) {
-    TRY(check_chain(c, 0));
-    if (mode < 0 || mode > 2) return fail(c, "unknown sweep mode");
-    const SbProblem &P = c->P;
-    TRY(ensure_obs_buffers(c));
-    TRY(sb_eval_stats(c, nullptr));
-    SbGibbsArgs G; memset(&G, 0, sizeof G);
-    G.P = P; G.states = c->d_states; G.slots = c->d_slots; G.n_states = c->n_chains; G.plan = c->oplan;
-    G.obj_part = c->d_obs_part; G.n_changed = c->d_gibbs_changed; G.step = step; G.mode = mode;
-    SbObsArgs A; memset(&A, 0, sizeof A);
-    A.P = P; A.states = c->d_states; A.n_states = c->n_chains; A.plan = c->oplan;
-    A.obj_part = c->d_obs_part; A.obj_ll = c->d_obs_ll; A.sums = c->d_obs_sums;
-    const int grid = c->n_chains * c->oplan.n_ftiles * c->oplan.n_oblk;
-    TRY(dev_zero(c, c->d_gibbs_changed, sizeof(unsigned long long) * c->n_chains));
-    TRY(dev_zero(c, c->d_eticket, sizeof(unsigned) * c->n_chains));
-#ifdef SB_HOSTSIM
-    if (ms) *ms = 0.f;
-    hostsim::launch([&]() { sb_gibbs_sweep_kernel(G); }, grid, 64, c->oplan.smem);
-    hostsim::launch([&]() { sb_obs_reduce_kernel(A, c->d_epartial, c->d_eticket); }, c->n_chains * SB_OBS_RPARTS, 64, 1024);
-    if (mode == 0) hostsim::launch([&]() { sb_flip_osel_kernel(c->d_states, c->n_chains, P.N); }, 2, 64, 0);
-#else
-    EvTimer t(c->stream, ms);
-    sb_gibbs_sweep_kernel<<<grid, SB_EVAL_BLOCK, c->oplan.smem, c->stream>>>(G);
-    CK(cudaGetLastError());
-    sb_obs_reduce_kernel<<<c->n_chains * SB_OBS_RPARTS, SB_EVAL_BLOCK, 1024, c->stream>>>(A, c->d_epartial, c->d_eticket);
-    CK(cudaGetLastError());
-    t.stop();
-    if (mode == 0) { sb_flip_osel_kernel<<<c->n_sm * 2, 256, 0, c->stream>>>(c->d_states, c->n_chains, P.N); CK(cudaGetLastError()); }
-#endif
-    c->launches += mode == 0 ? 3 : 2;
-    std::vector<double> sums(c->n_chains);
-    std::vector<unsigned long long> ch(c->n_chains);
-    TRY(d2h(c, sums.data(), c->d_obs_sums, sizeof(double) * c->n_chains));
-    TRY(d2h(c, ch.data(), c->d_gibbs_changed, sizeof(unsigned long long) * c->n_chains));
-    for (int i = 0; i < c->n_chains; i++) {
-        const int s = c->h_slot_state[i];
-        if (log_q_out) log_q_out[i] = sums[s];
-        if (n_changed_out) n_changed_out[i] = (int64_t)ch[s];
-    }
-    return 0;
-}
-
-// Observation likelihood of every chain (LikelihoodLogger._write_sample, sbayes/sampling/
-// loggers.py:354-359; likelihood_per_component_exact, sbayes/sampling/conditionals.py:300-367).
-// Runs the statistics pass first (the tables need the committed counts), then one streaming
-// kernel.  lh_out [n_chains, N, F] float32, obj_ll_out [n_chains, N] and sums_out [n_chains]
-// (sum of log lh per object / per chain) may each be NULL; ms receives the device time of the
-// likelihood kernel + reduction.
-SB_API int sb_obs_loglik(sb_ctx *c, float *lh_out, double *obj_ll_out, double *sums_out, float *ms) {
-    TRY(check_chain(c, 0));
-    const SbProblem &P = c->P;
-    const size_t nNF = (size_t)P.N * P.F;
-    TRY(ensure_obs_buffers(c));
-    if (!c->d_obs_out) TRY(mk(c, &c->d_obs_out, nNF * c->n_chains));
-    TRY(sb_eval_stats(c, nullptr));
-    SbObsArgs A; memset(&A, 0, sizeof A);
-    A.P = P; A.states = c->d_states; A.n_states = c->n_chains; A.plan = c->oplan;
-    A.out = c->d_obs_out; A.obj_part = c->d_obs_part; A.obj_ll = c->d_obs_ll; A.sums = c->d_obs_sums;
-    const int grid = c->n_chains * c->oplan.n_ftiles * c->oplan.n_oblk;
-#ifdef SB_HOSTSIM
-    if (ms) *ms = 0.f;
-    hostsim::launch([&]() { sb_obs_lik_kernel(A); }, grid, 64, c->oplan.smem);
-    TRY(dev_zero(c, c->d_eticket, sizeof(unsigned) * c->n_chains));
-    hostsim::launch([&]() { sb_obs_reduce_kernel(A, c->d_epartial, c->d_eticket); }, c->n_chains * SB_OBS_RPARTS, 64, 1024);
-#else
-    EvTimer t(c->stream, ms);
-    sb_obs_lik_kernel<<<grid, SB_EVAL_BLOCK, c->oplan.smem, c->stream>>>(A);
-    CK(cudaGetLastError());
-    TRY(dev_zero(c, c->d_eticket, sizeof(unsigned) * c->n_chains));
-    sb_obs_reduce_kernel<<<c->n_chains * SB_OBS_RPARTS, SB_EVAL_BLOCK, 1024, c->stream>>>(A, c->d_epartial, c->d_eticket);
-    CK(cudaGetLastError());
-    t.stop();
-#endif
-    c->launches += 2;
-    std::vector<SbSlot> slots(c->n_chains);
-    TRY(d2h(c, slots.data(), c->d_slots, sizeof(SbSlot) * c->n_chains));
-    for (int i = 0; i < c->n_chains; i++) {
-        const int s = slots[i].state;
-        if (lh_out) TRY(d2h(c, lh_out + (size_t)i * nNF, c->d_obs_out + (size_t)s * nNF, sizeof(float) * nNF));
-        if (obj_ll_out) TRY(d2h(c, obj_ll_out + (size_t)i * P.N, c->d_obs_ll + (size_t)s * P.N, sizeof(double) * P.N));
-        if (sums_out) TRY(d2h(c, sums_out + i, c->d_obs_sums + s, sizeof(double)));
-    }
-    if (!lh_out && !obj_ll_out && !sums_out) TRY(dev_sync(c));
-    return 0;
-}
-
-// EM-style cluster initializer (SbayesInitializer.generate_clusters_em, sbayes/sampling/initializers.py:93-169):
-// `n_steps` EM steps from the soft assignment z0 [G_tot, N] (float32; rows = clusters, then every confounder's
-// groups -- the reference's order); z_out receives the final assignment.  Uniform geo prior only (the reference
-// adds a geo term for cost-based priors).  ms = device time of all steps.
-SB_API int sb_init_em(sb_ctx *c, int32_t n_steps, const float *z0, float *z_out, float *ms) {
-    TRY(check_chain(c, 0));
-    if (!z0 || !z_out || n_steps < 1) return fail(c, "bad arguments");
-    if (c->P.geo) return fail(c, "sb_init_em: the geo term of the cost-based prior is not implemented (use the reference's initializer)");
-    const SbProblem &P = c->P;
-    const size_t G = P.G_tot, N = P.N, FS = (size_t)P.F * P.S;
-    const int n_ft = (P.F + SB_EM_FT - 1) / SB_EM_FT, n_gb = (int)((G + SB_EM_GB - 1) / SB_EM_GB);
-    int n_oblk = std::max(1, (8 * c->n_sm + n_ft * n_gb - 1) / (n_ft * n_gb));
-    n_oblk = (int)std::min<size_t>((size_t)n_oblk, std::max<size_t>(1, N / 64));
-    const int rows = (int)((N + n_oblk - 1) / n_oblk);
-    n_oblk = (int)((N + rows - 1) / rows);
-    const size_t keep = c->allocs.size();
-    struct Guard { sb_ctx *c; size_t keep; ~Guard() { while (c->allocs.size() > keep) {
-#ifdef SB_HOSTSIM
-        free(c->allocs.back());
-#else
-        cudaFree(c->allocs.back());
-#endif
-        c->allocs.pop_back(); } } } guard{c, keep};
-    SbEmArgs A; memset(&A, 0, sizeof A);
-    A.P = P; A.n_oblk = n_oblk; A.rows_per_blk = rows;
-    TRY(mk(c, &A.z, G * N)); TRY(mk(c, &A.partial, (size_t)n_oblk * G * FS)); TRY(mk(c, &A.logp, G * FS));
-    TRY(h2d(c, A.z, z0, sizeof(float) * G * N));
-    const size_t smem_counts = (size_t)(SB_EM_BLOCK / 32) * SB_EM_GB * P.S * 32 * 8, smem_assign = (size_t)(SB_EM_BLOCK / 32) * G * 8;
-#ifndef SB_HOSTSIM
-    if (smem_counts > 200 * 1024 || smem_assign > 200 * 1024) return fail(c, "sb_init_em: too many states / groups for the shared-memory bins");
-    CK(cudaFuncSetAttribute((const void *)sb_em_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_counts));
-    CK(cudaFuncSetAttribute((const void *)sb_em_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_assign));
-    EvTimer t(c->stream, ms);
-#else
-    if (ms) *ms = 0.f;
-#endif
-    for (int i = 0; i < n_steps; i++) {
-        const double temperature = pow((double)n_steps / (1.0 + (double)i), 3.0);
-        A.inv_temperature = 1.0 / temperature;
-#ifdef SB_HOSTSIM
-        hostsim::launch([&]() { sb_em_counts_kernel(A); }, n_ft * n_gb * n_oblk, 64, smem_counts);
-        hostsim::launch([&]() { sb_em_tables_kernel(A); }, (int)((G * P.F + 63) / 64), 64, 0);
-        hostsim::launch([&]() { sb_em_assign_kernel(A); }, 2, 64, smem_assign);
-#else
-        sb_em_counts_kernel<<<n_ft * n_gb * n_oblk, SB_EM_BLOCK, smem_counts, c->stream>>>(A);
-        sb_em_tables_kernel<<<(unsigned)((G * P.F + SB_EM_BLOCK - 1) / SB_EM_BLOCK), SB_EM_BLOCK, 0, c->stream>>>(A);
-        sb_em_assign_kernel<<<c->n_sm * 8, SB_EM_BLOCK, smem_assign, c->stream>>>(A);
-        CK(cudaGetLastError());
-#endif
-        c->launches += 3;
-    }
-#ifndef SB_HOSTSIM
-    t.stop();
-#endif
-    return d2h(c, z_out, A.z, sizeof(float) * G * N);
-}
-
 // device address and length (int32 elements) of the statistics block of all states, laid out
 // [state][counts G_tot*F*S | sizes K | H n_pat*2*F*C | pad]; layout3 = {n_counts, n_hist, n_sizes}.
 // A sharded run all-reduces the leading counts | sizes part (the histogram is shard-local)
@@ -1445,52 +999,6 @@ SB_API int sb_info(const sb_ctx *c, int32_t *out8) {
 SB_API uint64_t sb_stream(const sb_ctx *c) { return c ? (uint64_t)(uintptr_t)c->stream : 0; }
 SB_API int64_t sb_clock_khz(const sb_ctx *c) { return c ? (int64_t)c->clock_khz : 0; }
 
-// bulk count rebuild as stand-alone kernels (sb_counts.cuh): shared-memory histogram and the
-// int8 tensor-core contraction.  Both read the committed state of `chain` and return the
-// stacked counts; `ms` receives the device time of the kernel.
-static int counts_common(sb_ctx *c, int chain, int32_t *counts_out, float *ms, bool mma) {
-    TRY(check_chain(c, chain));
-    const SbProblem &P = c->P;
-    SbSlot slot; TRY(get_slot(c, chain, &slot));
-    SbShared &s = c->h_states[slot.state];
-    const size_t nG = (size_t)P.G_tot * P.F * P.S;
-    TRY(dev_zero(c, c->d_counts_tmp, sizeof(int32_t) * nG));
-    float t = 0.f;
-#ifdef SB_HOSTSIM
-    const int32_t *result = c->d_counts_tmp;
-    if (mma) return fail(c, "the tensor-core rebuild needs a GPU");
-    hostsim::launch([&]() { sb_counts_hist_kernel(P, s, c->d_counts_tmp); }, 2, 64, sb_counts_hist_smem(P));
-#else
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    CK(cudaEventRecord(e0, c->stream));
-    const int32_t *result = c->d_counts_tmp;
-    if (mma) {
-        // single state: the tensor-core pass writes the state's own statistics block
-        SbMmaPlan mp;
-        if (sb_mma_make_plan(P, 1, c->n_sm, &mp)) return fail(c, "the tensor-core statistics pass does not fit this problem (more than 256 group columns)");
-        SbEvalArgs A = eval_args(c, 0);
-        A.states = c->d_states + slot.state; A.n_states = 1;
-        CK(cudaFuncSetAttribute((const void *)sb_counts_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mp.smem));
-        CK(cudaMemsetAsync(s.counts, 0, sizeof(int32_t) * c->stats_stride, c->stream));
-        sb_counts_mma_kernel<<<mp.n_ftiles * mp.n_oblk, SB_MMA_BLOCK, mp.smem, c->stream>>>(A, mp);
-        result = s.counts;
-    } else {
-        if (sb_counts_hist_launch(P, s, c->d_counts_tmp, c->n_sm, c->stream)) return fail(c, "count rebuild launch failed");
-    }
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(e1, c->stream));
-    CK(cudaEventSynchronize(e1));
-    CK(cudaEventElapsedTime(&t, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-#endif
-    c->launches++;
-    if (ms) *ms = t;
-    if (counts_out) TRY(d2h(c, counts_out, result, sizeof(int32_t) * nG));
-    return 0;
-}
-SB_API int sb_counts_rebuild_hist(sb_ctx *c, int chain, int32_t *counts_out, float *ms) { return counts_common(c, chain, counts_out, ms, false); }
-SB_API int sb_counts_rebuild_mma(sb_ctx *c, int chain, int32_t *counts_out, float *ms) { return counts_common(c, chain, counts_out, ms, true); }
 
 #ifdef SB_HOSTSIM
 // emulator builds only (not part of the ABI): calls of the tiled passes per kind {alter, wide, jump, alter on feature pairs}

@@ -36,6 +36,7 @@
 // SB_NS (the namespace the instantiation lives in); see sb_api.cu.
 #include "sb_platform.cuh"
 #include "sb_types.h"
+#include "sb_philox.cuh"
 #ifndef SB_UC
 #error "define SB_UC and SB_NS before including sb_core.cuh"
 #endif
@@ -84,28 +85,7 @@ __device__ long long g_phase_n[SB_N_OPS];
 #define PH(R, id) do { } while (0)
 #endif
 
-// -----------------------------------------------------------------------------------------
-// Philox4x32-10 (Salmon et al. 2011); stream addressing identical to oracle/philox.py
-// -----------------------------------------------------------------------------------------
-struct Philox4 { uint32_t w[4]; };
-
-SB_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
-    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
-#pragma unroll
-    for (int r = 0; r < 10; r++) {
-        uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
-        uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
-        uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
-        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    Philox4 o; o.w[0] = c0; o.w[1] = c1; o.w[2] = c2; o.w[3] = c3; return o;
-}
-SB_HD double u01_double(uint32_t w0, uint32_t w1) {
-    return ((double)(w0 >> 5) * 67108864.0 + (double)(w1 >> 6)) / 9007199254740992.0;
-}
-SB_DEV double u01_float(uint32_t w0) { return (double)(w0 >> 8) / 16777216.0; }
+using sbp::Philox4; using sbp::philox4x32_10; using sbp::u01_double; using sbp::u01_float;     // sb_philox.cuh
 
 struct Draws {
     uint32_t k0, k1;
@@ -305,29 +285,33 @@ SB_HD FixedSmem sb_fixed_smem(int G, int K, int F, int C, int cap, unsigned base
 SB_DEV void xteam_wait(Run &R) {
     if (sb_ld_volatile_i32(R.c->xabort)) return;
     const long long t_lim = 8000000000LL;
-    sb_threadfence_system();
+    sb_threadfence_system();                     // this CTA's stores (peer memory included) before its arrival
     const unsigned long long arrived = sb_atomic_add_u64(R.c->bar, 1ull) + 1ull;
     const unsigned long long ev = R.xbase + R.epoch;
     if (arrived == R.epoch * (unsigned long long)R.lsize) {
+        // the fence makes everything this thread has observed (the other CTAs' arrivals and, through their fences, their
+        // stores) visible system-wide before the flags; the polls are plain volatile loads, ordered by the fence after them
+        sb_threadfence_system();
         for (int p = 0; p < R.xworld; p++)
-            if (p != R.xrank) sb_st_release_sys_u64(R.c->xflagp[p] + R.xrank, ev);
+            if (p != R.xrank) sb_st_volatile_u64(R.c->xflagp[p] + R.xrank, ev);
         for (int p = 0; p < R.xworld; p++) {
             if (p == R.xrank) continue;
             const long long t0 = sb_clock();
-            while (sb_ld_acquire_sys_u64(R.c->xflagp[R.xrank] + p) < ev) {
+            while (sb_ld_volatile_u64(R.c->xflagp[R.xrank] + p) < ev) {
                 sb_spin();
                 if (sb_clock() - t0 > t_lim || sb_ld_volatile_i32(R.c->xabort)) { *R.c->xabort = 1; break; }
             }
         }
-        // (the acquire loads above order everything that follows; the release store publishes the arrival of all ranks)
-        sb_st_release_sys_u64(R.c->lrel, ev);
+        sb_threadfence_system();
+        sb_st_volatile_u64(R.c->lrel, ev);
     } else {
         const long long t0 = sb_clock();
-        while (sb_ld_acquire_sys_u64(R.c->lrel) < ev) {
+        while (sb_ld_volatile_u64(R.c->lrel) < ev) {
             sb_spin();
             if (sb_clock() - t0 > 2 * t_lim || sb_ld_volatile_i32(R.c->xabort)) { *R.c->xabort = 1; break; }
         }
     }
+    sb_threadfence_system();                     // what the other ranks stored before their arrival, before this CTA reads on
 }
 
 // a CTA's slot of the team reduction buffer (thread 0): with the objects sharded over GPUs the buffer is
@@ -457,17 +441,28 @@ SB_DEV int team_pick(Run &R, const double *val, int n, double u, double &total, 
         if (tid == 0) tred_put(R, R.par, s, 3);
         R.par ^= 1;
         team_sync(R);
-        total = 0.0;
-        double e0 = 0.0, e1 = 0.0;
-        for (int r = 0; r < R.tsize; r++) { total += buf[r * SB_REDW]; e0 += buf[r * SB_REDW + 1]; e1 += buf[r * SB_REDW + 2]; }
+        // every warp on its own, lanes over the team's slots (a team can have more than a thousand CTAs when the
+        // objects are sharded over GPUs): totals by lane-strided sums + butterfly, the block that holds the target by a
+        // chunked warp scan -- the same result in every warp of every CTA
+        const int lane = sb_lane();
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+        for (int r = lane; r < R.tsize; r += 32) { t0 += buf[r * SB_REDW]; t1 += buf[r * SB_REDW + 1]; t2 += buf[r * SB_REDW + 2]; }
+        total = warp_sum(t0);
+        const double e0 = warp_sum(t1), e1 = warp_sum(t2);
         if (extra) { extra[0] = e0; extra[1] = e1; }
         if (!(total > 0.0)) return -1;
         const double target = u * total;
-        rb = -1; double prefix = 0.0, acc = 0.0;
-        for (int r = 0; r < R.tsize; r++) {
-            double sr = buf[r * SB_REDW];
-            if (sr > 0.0) { rb = r; prefix = acc; if (acc + sr > target) break; }
-            acc += sr;
+        rb = -1; double prefix = 0.0, carry = 0.0;
+        for (int r0 = 0; r0 < R.tsize; r0 += 32) {
+            const int r = r0 + lane;
+            const double sr = r < R.tsize ? buf[r * SB_REDW] : 0.0;
+            double incl = sr;
+            for (int off = 1; off < 32; off <<= 1) { const double t = sb_shfl_f64(incl, lane - off); if (lane >= off) incl += t; }
+            const double excl = carry + (incl - sr);
+            const unsigned pos = sb_ballot(sr > 0.0), hit = sb_ballot(sr > 0.0 && excl + sr > target);
+            if (hit) { const int l = sb_ffs(hit) - 1; rb = r0 + l; prefix = sb_shfl_f64(excl, l); break; }
+            if (pos) { const int l = 31 - sb_clz(pos); rb = r0 + l; prefix = sb_shfl_f64(excl, l); }     // last positive block so far
+            carry += sb_shfl_f64(incl, 31);
         }
         tloc = target - prefix;
         if (rb != R.rank) {       // the block that holds the target: every CTA scans it (no second barrier)
@@ -534,7 +529,11 @@ SB_DEV int team_compact(Run &R, int n, int32_t *list, Pred pred) {
     R.par ^= 1;
     team_sync(R);
     int base = 0, total = 0;
-    for (int r = 0; r < R.tsize; r++) { int v = (int)buf[r * SB_REDW]; if (r < R.rank) base += v; total += v; }
+    {
+        double tb = 0.0, tt = 0.0;      // (integers: exact in any order)
+        for (int r = sb_lane(); r < R.tsize; r += 32) { const double v = buf[r * SB_REDW]; if (r < R.rank) tb += v; tt += v; }
+        base = (int)warp_sum(tb); total = (int)warp_sum(tt);
+    }
     int running = base, nw = sb_nwarps();
     for (int c0 = lo; c0 < hi; c0 += sb_nthr()) {
         int i = c0 + sb_tid();
@@ -1440,6 +1439,14 @@ SB_DEV void proposal_rows(Run &R) {
     for (int idx = sb_tid(); idx < R.nd * F; idx += sb_nthr()) {
         const int g = R.c->rp.dlist[idx / F], f = idx % F;
         const size_t gf = (size_t)g * F + f, b = gf * S;
+        // most (group, feature) rows of a dirty group saw no change: find that out with all loads of the row in
+        // flight at once (the replicas of the large shapes live in the HBM slice: a dependent load is an L2 round trip)
+        int touched = 0;
+#ifndef SB_HOSTSIM
+#pragma unroll 8
+#endif
+        for (int s = 0; s < S; s++) touched |= R.c->rp.dcnt[b + s];
+        if (!touched) continue;
         int D = 0; bool any = false; double delta = 0.0;
         for (int s = 0; s < S; s++) {
             int d = R.c->rp.dcnt[b + s];
@@ -1470,6 +1477,12 @@ SB_DEV void proposal_close(Run &R, bool accept) {
     for (int idx = sb_tid(); idx < R.nd * F; idx += sb_nthr()) {
         const int g = R.c->rp.dlist[idx / F], f = idx % F;
         const size_t gf = (size_t)g * F + f, b = gf * S;
+        int touched = 0;
+#ifndef SB_HOSTSIM
+#pragma unroll 8
+#endif
+        for (int s = 0; s < S; s++) touched |= R.c->rp.dcnt[b + s];
+        if (!touched) continue;            // (a row whose changes cancelled keeps its terms: nothing to undo either)
         int D = 0;
         for (int s = 0; s < S; s++) {
             int d = R.c->rp.dcnt[b + s];

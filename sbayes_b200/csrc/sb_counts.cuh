@@ -8,6 +8,7 @@
 #pragma once
 #include "sb_platform.cuh"
 #include "sb_types.h"
+#include "sb_plans.h"
 #include "sb_eval.cuh"
 
 SB_HD size_t sb_counts_hist_smem(const SbProblem &) { return 0; }
@@ -61,15 +62,6 @@ static int sb_counts_hist_launch(const SbProblem &P, const SbShared &st, int32_t
 #define SB_MMA_KC 64          /* objects per stage (two K = 32 MMAs per M tile) */
 #define SB_MMA_BLOCK 512
 
-struct SbMmaPlan {
-    int cs;            // C * S rows of A per feature
-    int npad;          // columns of D: G_tot + n_pat*2, padded to 16
-    int ftw;           // bytes (features) of a packed row per CTA, multiple of 16, <= 128
-    int n_ftiles, n_oblk, rows_per_blk;   // rows_per_blk is a multiple of SB_MMA_KC
-    int tiles;         // M tiles of 128 rows per CTA
-    int tmem_cols;     // power of two >= tiles * npad
-    unsigned a_bytes, b_bytes, smem;
-};
 
 static inline int sb_mma_make_plan(const SbProblem &P, int n_states, int n_sm, SbMmaPlan *mp) {
     const int cs = P.C * P.S, ncol = P.G_tot + P.n_pat * 2, npad = (ncol + 15) / 16 * 16;

@@ -19,19 +19,13 @@
 #pragma once
 #include "sb_platform.cuh"
 #include "sb_types.h"
+#include "sb_plans.h"
+#include "sb_philox.cuh"
 #include <stdlib.h>
 
 #define SB_EVAL_BLOCK 256
 #define SB_EVAL_MAXPARTS 512
 
-struct SbEvalPlan {
-    int ft;            // features per tile (multiple of 16 bytes of a packed row)
-    int n_ftiles;      // tiles per row
-    int n_oblk;        // object blocks per (state, tile)
-    int rows_per_blk;  // objects per block
-    int n_parts;       // CTAs per state of the terms kernel
-    unsigned smem;     // dynamic shared memory of the histogram kernel
-};
 
 struct SbEvalArgs {
     SbProblem P;
@@ -466,7 +460,6 @@ SB_KERNEL sb_eval_terms_kernel(const SB_GRID_CONSTANT SbEvalArgs A) {
 // memory in fp64; log(lh) is taken of products of four.  Per-object sums over the tile go to
 // obj_part[state][tile][o]; sb_obs_reduce_kernel adds tiles and objects in a fixed order.
 // -----------------------------------------------------------------------------------------
-struct SbObsPlan { int ft, n_ftiles, n_oblk, rows_per_blk; unsigned smem; };
 
 struct SbObsArgs {
     SbProblem P;
@@ -810,14 +803,14 @@ SB_DEV void ev_gibbs_body(const SbGibbsArgs &A) {
             const uint8_t *xr = P.x + off, *sr = (sel ? src1 : src0) + off;
             uint8_t *so = (sel ? src0 : src1) + off;
             double prod = 1.0;
-            uc4::Philox4 ph; ph.w[0] = ph.w[1] = ph.w[2] = ph.w[3] = 0;
+            sbp::Philox4 ph; ph.w[0] = ph.w[1] = ph.w[2] = ph.w[3] = 0;
 #ifndef SB_HOSTSIM
 #pragma unroll
 #endif
             for (int j = 0; j < 4; j++) {
                 const int fl = fls[j];
                 if (A.mode == 0 && !(j & 1) && fl < fv)      // the pair's draw: (chain seed, step, SITE_GIBBS, o * ceil(F/2) + f / 2)
-                    ph = uc4::philox4x32_10((uint32_t)((size_t)o * hF + ((f0 + fl) >> 1)), (uint32_t)SITE_GIBBS, st_lo, st_hi, k0, k1);
+                    ph = sbp::philox4x32_10((uint32_t)((size_t)o * hF + ((f0 + fl) >> 1)), (uint32_t)SITE_GIBBS, st_lo, st_hi, k0, k1);
                 if (fl >= fv) continue;
                 const int x = (int)sb_ldg(xr + fl), c_old = (int)sr[fl];
                 if (x == SB_NA_U8) { if (A.mode == 0) so[fl] = SB_NA_U8; continue; }
@@ -839,7 +832,7 @@ SB_DEV void ev_gibbs_body(const SbGibbsArgs &A) {
                 for (int u = 0; u < UC; u++) if (u < C) q[u] *= inv;
                 int pick;
                 if (A.mode == 0) {
-                    const double uu = (j & 1) ? uc4::u01_double(ph.w[2], ph.w[3]) : uc4::u01_double(ph.w[0], ph.w[1]);
+                    const double uu = (j & 1) ? sbp::u01_double(ph.w[2], ph.w[3]) : sbp::u01_double(ph.w[0], ph.w[1]);
                     double last = 0.0, cum = 0.0;
 #ifndef SB_HOSTSIM
 #pragma unroll

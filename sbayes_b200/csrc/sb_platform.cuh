@@ -44,6 +44,8 @@ SB_DEV void sb_threadfence_system() {}
 SB_DEV unsigned long long sb_ld_acquire_sys_u64(const unsigned long long *p) { return *(volatile const unsigned long long *)p; }
 SB_DEV void sb_st_release_sys_u64(unsigned long long *p, unsigned long long v) { *(volatile unsigned long long *)p = v; }
 SB_DEV int sb_ld_volatile_i32(const int *p) { return *(volatile const int *)p; }
+SB_DEV unsigned long long sb_ld_volatile_u64(const unsigned long long *p) { return *(volatile const unsigned long long *)p; }
+SB_DEV void sb_st_volatile_u64(unsigned long long *p, unsigned long long v) { *(volatile unsigned long long *)p = v; }
 SB_DEV void sb_spin() { hostsim::yield(); }
 SB_DEV long long sb_clock() { return 0; }
 SB_DEV uint32_t sb_mulhi_u32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
@@ -91,6 +93,8 @@ SB_DEV void sb_st_release_sys_u64(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 SB_DEV int sb_ld_volatile_i32(const int *p) { return *(volatile const int *)p; }
+SB_DEV unsigned long long sb_ld_volatile_u64(const unsigned long long *p) { return *(volatile const unsigned long long *)p; }
+SB_DEV void sb_st_volatile_u64(unsigned long long *p, unsigned long long v) { *(volatile unsigned long long *)p = v; }
 SB_DEV void sb_spin() {}
 SB_DEV long long sb_clock() { return clock64(); }
 SB_DEV uint32_t sb_mulhi_u32(uint32_t a, uint32_t b) { return __umulhi(a, b); }

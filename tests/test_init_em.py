@@ -55,10 +55,10 @@ def test_em_matches_numpy_restatement(backend, shape):
     z0 = INI.initial_soft_assignment(prob, np.random.default_rng(5))
     ctx = DeviceContext(prob, 1, _lib=_lib(backend))
     try:
-        z = ctx.init_em(z0, 12)
+        z = ctx.init_em(z0, 8)
     finally:
         ctx.close()
-    ref = em_numpy(prob, z0, 12)
+    ref = em_numpy(prob, z0, 8)
     assert np.all(z[~INI.groups_available(prob)] == 0)
     assert np.allclose(z.sum(axis=0), 1.0, atol=1e-5)
     assert np.abs(z - ref).max() < 2e-5

@@ -84,7 +84,7 @@ def test_emulated_sharded_chain(lib, env, world, team_local, tiled):
     prob, _ = synth.make_problem(N=90, F=18, S=4, K=3, n_fam=4, seed=29, max_size=35, jagged_states=True)
     cfgs = [ChainConfig(seed=900), _ClusterHeavy(temperature=1.2, prior_temperature=1.1, seed=901)]
     st0 = [synth.initial_state(prob, seed=35 + i, objects_per_cluster=7) for i in range(2)]
-    sharded_vs_single(prob, st0, cfgs, 60, world, team_local, lib=lib)
+    sharded_vs_single(prob, st0, cfgs, 45, world, team_local, lib=lib)
 
 
 @pytest.mark.gpu
