@@ -171,6 +171,15 @@ int sb_gibbs_sweep(sb_ctx *ctx, uint64_t step, int mode, double *log_q_out, int6
  * n_steps EM steps on the soft assignment z0 [G_tot, N] float32 (rows: clusters, then every confounder's groups);
  * z_out [G_tot, N] receives the final assignment.  Uniform geo prior only. */
 int sb_init_em(sb_ctx *ctx, int32_t n_steps, const float *z0, float *z_out, float *ms);
+/* Which statistics pass sb_eval_stats runs and its launch geometry: out8 = {pass (0 two-increment histogram, 1 int8
+ * tcgen05 contraction, 2 fine-row histogram), feature-tile width, feature tiles, object blocks, dynamic shared memory,
+ * fine rows, CTAs, block size}. */
+int sb_eval_info(sb_ctx *ctx, int32_t *out8);
+/* Effect draws at log time (conditional_effect_sample, sbayes/sampling/conditionals.py:125-149, as called by
+ * ParametersCSVLogger._write_sample, sbayes/sampling/loggers.py:160-224): for each listed chain
+ * out[i, g, f, :] ~ Dirichlet(counts[g, f, :] + concentration[g, f, :]) over the applicable states (zero elsewhere), counts =
+ * the chain's committed count tensors; Philox draws (chain seed, step).  out: float64 [n, G_tot, F, S]. */
+int sb_effect_sample(sb_ctx *ctx, int32_t n, const int32_t *chains, uint64_t step, double *out, float *ms);
 int sb_stats_buffer(sb_ctx *ctx, uint64_t *dev_ptr, int64_t *n_int32, int64_t *stride, int64_t *layout3);
 int sb_run(sb_ctx *ctx, int64_t n_steps, const sb_tape *tape, sb_step_record *records);
 int sb_run_async(sb_ctx *ctx, int64_t n_steps);                     /* enqueue only; sb_sync waits */

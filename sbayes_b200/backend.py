@@ -68,7 +68,8 @@ EXPORTS = ["sb_create", "sb_destroy", "sb_last_error", "sb_chain_config", "sb_se
            "sb_set_slots", "sb_counts_rebuild_mma", "sb_counts_rebuild_hist", "sb_info", "sb_stream",
            "sb_eval_batch", "sb_eval_stats", "sb_eval_terms", "sb_stats_buffer", "sb_eval_set_mode", "sb_obs_loglik",
            "sb_swap_scalars", "sb_clock_khz", "sb_posteriors", "sb_set_temperatures", "sb_gibbs_sweep",
-           "sb_export_samples", "sb_shard_handle", "sb_shard_attach", "sb_run_group", "sb_init_em"]
+           "sb_export_samples", "sb_shard_handle", "sb_shard_attach", "sb_run_group", "sb_init_em", "sb_eval_info",
+           "sb_effect_sample"]
 
 
 def _bind(lib):
@@ -89,6 +90,8 @@ def _bind(lib):
     lib.sb_shard_attach.argtypes = [vp, i32, i32, vp]
     lib.sb_run_group.argtypes = [vp, i32, i64, vp]
     lib.sb_init_em.argtypes = [vp, i32, vp, vp, vp]
+    lib.sb_eval_info.argtypes = [vp, vp]
+    lib.sb_effect_sample.argtypes = [vp, i32, vp, u64, vp, vp]
     lib.sb_posteriors.argtypes = [vp, vp]
     lib.sb_set_temperatures.argtypes = [vp, vp, vp]
     lib.sb_run.argtypes = [vp, i64, C.POINTER(_Tape), vp]
@@ -395,6 +398,23 @@ class DeviceContext:
         assert z0.shape == (self.prob.G_tot, self.prob.N)
         out, ms = np.empty_like(z0), np.zeros(1, np.float32)
         self._ck(self.lib.sb_init_em(self.h, int(n_steps), _ptr(z0), _ptr(out), _ptr(ms)))
+        return (out, float(ms[0])) if timing else out
+
+    def eval_info(self) -> dict:
+        """which statistics pass `eval_stats` runs ("hist", "mma", "fine") and its launch geometry"""
+        o = np.zeros(8, np.int32)
+        self._ck(self.lib.sb_eval_info(self.h, _ptr(o)))
+        return {"pass": ("hist", "mma", "fine")[int(o[0])], "ft": int(o[1]), "n_ftiles": int(o[2]), "n_oblk": int(o[3]),
+                "smem": int(o[4]), "fine_rows": int(o[5]), "grid": int(o[6]), "block": int(o[7])}
+
+    def effect_sample(self, chains=None, step: int = 0, timing: bool = False):
+        """conditional_effect_sample of the reference's parameter logger for the listed chains: float64
+        [n, G_tot, F, S] Dirichlet draws from (committed counts + prior concentration), rows = clusters, then every
+        confounder's groups."""
+        chains = np.arange(self.n_chains, dtype=np.int32) if chains is None else np.ascontiguousarray(chains, np.int32)
+        out = np.empty((len(chains), self.prob.G_tot, self.prob.F, self.prob.S), np.float64)
+        ms = np.zeros(1, np.float32)
+        self._ck(self.lib.sb_effect_sample(self.h, len(chains), _ptr(chains), int(step), _ptr(out), _ptr(ms)))
         return (out, float(ms[0])) if timing else out
 
     def stats_buffer(self):

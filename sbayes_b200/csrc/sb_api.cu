@@ -31,6 +31,7 @@ SB_API void sb_destroy(sb_ctx *c) {
     for (int p = 0; p < SB_MAX_RANKS; p++) if (c->peer_opened[p]) cudaIpcCloseMemHandle(c->peer_arena[p]);
 #endif
     dev_free_all(c);
+    if (c->eval_ext && c->eval_ext_free) c->eval_ext_free(c->eval_ext);
 #ifndef SB_HOSTSIM
     if (c->stream) cudaStreamDestroy(c->stream);
 #endif

@@ -7,6 +7,142 @@
 #include "sb_eval.cuh"
 #include "sb_init.cuh"
 
+// ---------------------------------------------------------------------------------------
+// fine-row statistics pass (sb_eval.cuh: ev_hist_fine): row tables, the NA-mapped copy of the state bytes, launch plan
+// ---------------------------------------------------------------------------------------
+struct FineState {
+    SbFineArgs fa; int ok = 0; const void *kernel = nullptr;
+    double *d_eff = nullptr; size_t eff_cap = 0; int32_t *d_eff_chains = nullptr;    // staging of sb_effect_sample
+};
+static void fine_free(void *p) { delete (FineState *)p; }
+static FineState *fine_of(sb_ctx *c) { return (FineState *)c->eval_ext; }
+
+#ifndef SB_HOSTSIM
+static const void *fine_kernel_ptr(int S1) {
+    switch (S1) {
+    case 2: return (const void *)sb_eval_fine_kernel<2>; case 3: return (const void *)sb_eval_fine_kernel<3>;
+    case 4: return (const void *)sb_eval_fine_kernel<4>; case 5: return (const void *)sb_eval_fine_kernel<5>;
+    case 6: return (const void *)sb_eval_fine_kernel<6>; case 7: return (const void *)sb_eval_fine_kernel<7>;
+    case 8: return (const void *)sb_eval_fine_kernel<8>; case 9: return (const void *)sb_eval_fine_kernel<9>;
+    }
+    return nullptr;
+}
+#else
+static void fine_kernel_host(int S1, const SbEvalArgs &A, const SbFineArgs &FA) {
+    switch (S1) {
+    case 2: sb_eval_fine_kernel<2>(A, FA); break; case 3: sb_eval_fine_kernel<3>(A, FA); break;
+    case 4: sb_eval_fine_kernel<4>(A, FA); break; case 5: sb_eval_fine_kernel<5>(A, FA); break;
+    case 6: sb_eval_fine_kernel<6>(A, FA); break; case 7: sb_eval_fine_kernel<7>(A, FA); break;
+    case 8: sb_eval_fine_kernel<8>(A, FA); break; case 9: sb_eval_fine_kernel<9>(A, FA); break;
+    }
+}
+#endif
+
+static int fine_setup(sb_ctx *c) {
+    const SbProblem &P = c->P;
+    FineState *fs = new FineState();
+    memset(&fs->fa, 0, sizeof fs->fa);
+    c->eval_ext = fs; c->eval_ext_free = fine_free;
+    const int N = P.N, C = P.C, K = P.K, np = P.n_pat, S1 = P.S + 1;
+    if (!P.obj_pack || S1 < 2 || S1 > 9 || getenv("SB_EVAL_NO_FINE")) return 0;
+    std::vector<uint32_t> pack(N);
+    std::vector<int32_t> pat_bits(np);
+    TRY(d2h(c, pack.data(), P.obj_pack, sizeof(uint32_t) * N));
+    TRY(d2h(c, pat_bits.data(), P.pat_bits, sizeof(int32_t) * np));
+    // fine rows: [0, K*np) (cluster, pattern); [K*np, (K+1)*np) (free, pattern); then one pair (not in a cluster, in a
+    // cluster) per distinct (component, group or none, pattern); last the trash pair (components the problem does not have)
+    std::map<uint32_t, int> pair_of;
+    int next = (K + 1) * np;
+    auto key_of = [](int u, uint32_t g, uint32_t pat) { return ((uint32_t)u << 24) | (g << 8) | pat; };
+    for (int pat = 0; pat < np; pat++)                 // a component the pattern lacks: counts nowhere, but H sees it
+        for (int u = 1; u < C; u++) if (!((pat_bits[pat] >> u) & 1)) { pair_of[key_of(u, 255u, (uint32_t)pat)] = next; next += 2; }
+    for (int o = 0; o < N; o++) {
+        const uint32_t pat = pack[o] & 255u;
+        for (int u = 1; u < C && u < 4; u++) {
+            const uint32_t k = key_of(u, (pack[o] >> (8 * u)) & 255u, pat);
+            if (!pair_of.count(k)) { pair_of[k] = next; next += 2; }
+        }
+    }
+    const int trash = next, R = next + 2;
+    if (trash + 1 > 255) return 0;                     // row ids travel as bytes: the two-increment pass serves
+    std::vector<uint32_t> fine(N);
+    for (int o = 0; o < N; o++) {
+        const uint32_t pat = pack[o] & 255u;
+        uint32_t w = pat;
+        for (int u = 1; u < 4; u++) {
+            int row = trash;
+            if (u < C) row = pair_of[key_of(u, (pack[o] >> (8 * u)) & 255u, pat)];
+            w |= (uint32_t)row << (8 * u);
+        }
+        fine[o] = w;
+    }
+    std::vector<std::vector<int32_t>> cl(P.G_tot), hl((size_t)np * 2 * C);
+    for (int k = 0; k < K; k++)
+        for (int p = 0; p < np; p++) { cl[k].push_back(k * np + p); hl[(size_t)(p * 2 + 1) * C].push_back(k * np + p); }
+    for (int p = 0; p < np; p++) hl[(size_t)(p * 2) * C].push_back(K * np + p);
+    for (auto &kv : pair_of) {
+        const int u = (int)(kv.first >> 24), g = (int)((kv.first >> 8) & 255u), pat = (int)(kv.first & 255u);
+        for (int in = 0; in < 2; in++) {
+            if (g != 255) cl[g].push_back(kv.second + in);
+            hl[(size_t)(pat * 2 + in) * C + u].push_back(kv.second + in);
+        }
+    }
+    auto csr = [](const std::vector<std::vector<int32_t>> &l, std::vector<int32_t> &ptr, std::vector<int32_t> &idx) {
+        ptr.assign(1, 0);
+        for (auto &v : l) { idx.insert(idx.end(), v.begin(), v.end()); ptr.push_back((int32_t)idx.size()); }
+    };
+    std::vector<int32_t> cp, ci, hp, hi;
+    csr(cl, cp, ci); csr(hl, hp, hi);
+    // launch plan: the widest feature tile whose bins fit the budget, balanced tiles, object blocks by the cost model of the
+    // two-increment pass (one block per (state, tile) lets the CTA own its slice of the statistics)
+    const size_t per_f = (size_t)R * S1 * 4, fixed = (size_t)K * 4 + (size_t)R * 4 + 64;
+    size_t budget = 56 * 1024;
+#ifdef SB_HOSTSIM
+    if (getenv("SB_HOSTSIM_EVAL_SMEM")) budget = (size_t)atol(getenv("SB_HOSTSIM_EVAL_SMEM"));
+#else
+    if (getenv("SB_FINE_SMEM_KB")) budget = (size_t)atol(getenv("SB_FINE_SMEM_KB")) * 1024;
+#endif
+    if (budget < fixed + 16 * per_f) budget = 110 * 1024;
+    if (budget < fixed + 16 * per_f) budget = 220 * 1024;
+    if (budget < fixed + 16 * per_f) return 0;
+    int ft_max = (int)((budget - fixed) / per_f) / 16 * 16;
+#ifdef SB_HOSTSIM
+    if (getenv("SB_HOSTSIM_FINE_FT")) ft_max = atoi(getenv("SB_HOSTSIM_FINE_FT"));      // tests: several feature tiles
+#endif
+    int n_ftiles = (P.ldx + ft_max - 1) / ft_max;
+    const int ft = ((P.ldx + n_ftiles - 1) / n_ftiles + 15) / 16 * 16;
+    n_ftiles = (P.ldx + ft - 1) / ft;
+    const size_t smem = fixed + (size_t)ft * per_f;
+    long long per_sm = (long long)((227 * 1024) / (smem + 1024)); if (per_sm > 4) per_sm = 4; if (per_sm < 1) per_sm = 1;
+    const long long slots = per_sm * c->n_sm, base = (long long)c->n_chains * n_ftiles;
+    long long max_blk = N / 128; if (max_blk < 1) max_blk = 1; if (max_blk > 4096) max_blk = 4096;
+    long long n_oblk = 1; double best = -1.0;
+    for (long long n = 1; n <= max_blk; n++) {
+        const long long waves = (base * n + slots - 1) / slots;
+        const double cost = (double)waves * ((double)((N + n - 1) / n) * ft + 3.0 * (double)ft * R * S1);
+        if (best < 0.0 || cost < best) { best = cost; n_oblk = n; }
+    }
+#ifdef SB_HOSTSIM
+    if (getenv("SB_HOSTSIM_EVAL_OBLK")) n_oblk = atoi(getenv("SB_HOSTSIM_EVAL_OBLK"));
+#endif
+    int rows = (int)((N + n_oblk - 1) / n_oblk);
+    n_oblk = (N + rows - 1) / rows;
+    // device copies
+    std::vector<uint8_t> xs((size_t)N * P.ldx);
+    TRY(d2h(c, xs.data(), P.x, xs.size()));
+    for (auto &v : xs) if (v >= (uint8_t)P.S) v = (uint8_t)P.S;
+    SbFineArgs &fa = fs->fa;
+    TRY(up(c, &fa.xs, xs)); TRY(up(c, &fa.obj_fine, fine));
+    TRY(up(c, &fa.cnt_ptr, cp)); TRY(up(c, &fa.cnt_idx, ci)); TRY(up(c, &fa.h_ptr, hp)); TRY(up(c, &fa.h_idx, hi));
+    fa.n_rows = R; fa.ft = ft; fa.n_ftiles = n_ftiles; fa.n_oblk = (int)n_oblk; fa.rows_per_blk = rows; fa.smem = (unsigned)smem;
+#ifndef SB_HOSTSIM
+    fs->kernel = fine_kernel_ptr(S1);
+    CK(cudaFuncSetAttribute(fs->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+    fs->ok = 1;
+    return 0;
+}
+
 int sb_eval_setup(sb_ctx *c) {
     const SbProblem &P = c->P;
     const int n_chains = c->n_chains, K = P.K, N = P.N; (void)N;
@@ -40,6 +176,7 @@ int sb_eval_setup(sb_ctx *c) {
         TRY(mk(c, &c->d_epartial, (size_t)n_chains * SB_EVAL_MAXPARTS * 4)); TRY(mk(c, &c->d_eticket, (size_t)n_chains));
         TRY(mk(c, &c->d_egeo, (size_t)n_chains * K)); TRY(mk(c, &c->d_epost, (size_t)n_chains * 8)); TRY(mk(c, &c->d_eerr, 1));
     }
+    TRY(fine_setup(c));
     return 0;
 }
 
@@ -64,19 +201,27 @@ struct EvTimer {
 // statistics pass: counts, source histogram and cluster sizes of every state (zeroed first)
 SB_API int sb_eval_stats(sb_ctx *c, float *ms) {
     TRY(check_chain(c, 0));
-    if (!c->eplan_ok && c->stats_mode == 0) return fail(c, "evaluation histogram does not fit in shared memory (too many groups x states)");
+    FineState *fs = fine_of(c);
+    const bool fine = fs && fs->ok && c->stats_mode == 0;
+    if (!fine && !c->eplan_ok && c->stats_mode == 0) return fail(c, "evaluation histogram does not fit in shared memory (too many groups x states)");
     SbEvalArgs A = eval_args(c, 0);
-    const int grid = c->n_chains * c->eplan.n_ftiles * c->eplan.n_oblk;
+    const int grid = fine ? c->n_chains * fs->fa.n_ftiles * fs->fa.n_oblk : c->n_chains * c->eplan.n_ftiles * c->eplan.n_oblk;
+    // (the fine-row pass with one object block per (state, tile) stores every word of the statistics itself)
+    const bool zero = !(fine && fs->fa.n_oblk == 1);
 #ifdef SB_HOSTSIM
     if (ms) *ms = 0.f;
-    TRY(dev_zero(c, c->d_stats, sizeof(int32_t) * c->stats_stride * c->n_chains));
-    hostsim::launch([&]() { sb_eval_hist_kernel(A); }, grid, 64, c->eplan.smem);
+    if (zero) TRY(dev_zero(c, c->d_stats, sizeof(int32_t) * c->stats_stride * c->n_chains));
+    if (fine) hostsim::launch([&]() { fine_kernel_host(c->P.S + 1, A, fs->fa); }, grid, 64, fs->fa.smem);
+    else hostsim::launch([&]() { sb_eval_hist_kernel(A); }, grid, 64, c->eplan.smem);
 #else
     EvTimer t(c->stream, ms);
-    TRY(dev_zero(c, c->d_stats, sizeof(int32_t) * c->stats_stride * c->n_chains));
+    if (zero) TRY(dev_zero(c, c->d_stats, sizeof(int32_t) * c->stats_stride * c->n_chains));
     if (c->stats_mode == 1) {
         if (!c->mplan_ok) return fail(c, "the tensor-core statistics pass does not fit this problem (more than 256 group columns)");
         sb_counts_mma_kernel<<<c->n_chains * c->mplan.n_ftiles * c->mplan.n_oblk, SB_MMA_BLOCK, c->mplan.smem, c->stream>>>(A, c->mplan);
+    } else if (fine) {
+        void *args[2] = {(void *)&A, (void *)&fs->fa};
+        CK(cudaLaunchKernel(fs->kernel, dim3(grid), dim3(SB_EVAL_BLOCK), args, fs->fa.smem, c->stream));
     } else {
         sb_eval_hist_kernel<<<grid, SB_EVAL_BLOCK, c->eplan.smem, c->stream>>>(A);
     }
@@ -85,6 +230,58 @@ SB_API int sb_eval_stats(sb_ctx *c, float *ms) {
 #endif
     c->launches++;
     return 0;
+}
+
+// which statistics pass sb_eval_stats runs and its launch geometry:
+// out8 = {pass (0 two-increment histogram, 1 int8 tensor-core contraction, 2 fine-row histogram), feature-tile width,
+//         feature tiles, object blocks, dynamic shared memory, fine rows, CTAs, block size}
+SB_API int sb_eval_info(sb_ctx *c, int32_t *out8) {
+    if (!c || !out8) return -1;
+    FineState *fs = fine_of(c);
+    memset(out8, 0, sizeof(int32_t) * 8);
+    if (c->stats_mode == 1) {
+        out8[0] = 1; out8[1] = c->mplan.ftw; out8[2] = c->mplan.n_ftiles; out8[3] = c->mplan.n_oblk; out8[4] = (int)c->mplan.smem;
+        out8[6] = c->n_chains * c->mplan.n_ftiles * c->mplan.n_oblk; out8[7] = SB_MMA_BLOCK;
+    } else if (fs && fs->ok) {
+        out8[0] = 2; out8[1] = fs->fa.ft; out8[2] = fs->fa.n_ftiles; out8[3] = fs->fa.n_oblk; out8[4] = (int)fs->fa.smem; out8[5] = fs->fa.n_rows;
+        out8[6] = c->n_chains * fs->fa.n_ftiles * fs->fa.n_oblk; out8[7] = SB_EVAL_BLOCK;
+    } else {
+        out8[1] = c->eplan.ft; out8[2] = c->eplan.n_ftiles; out8[3] = c->eplan.n_oblk; out8[4] = (int)c->eplan.smem;
+        out8[6] = c->n_chains * c->eplan.n_ftiles * c->eplan.n_oblk; out8[7] = SB_EVAL_BLOCK;
+    }
+    return 0;
+}
+
+// effect draws of the listed chains at log time (sb_eval.cuh: sb_effect_sample_kernel): out [n, G_tot, F, S] float64
+SB_API int sb_effect_sample(sb_ctx *c, int32_t n, const int32_t *chains, uint64_t step, double *out, float *ms) {
+    TRY(check_chain(c, 0));
+    if (n <= 0 || !chains || !out) return fail(c, "sb_effect_sample: nothing to do");
+    for (int i = 0; i < n; i++) if (chains[i] < 0 || chains[i] >= c->n_chains) return fail(c, "chain index out of range");
+    FineState *fs = fine_of(c);
+    const SbProblem &P = c->P;
+    const size_t per = (size_t)P.G_tot * P.F * P.S, need = per * (size_t)n;
+    if (fs->eff_cap < need) {
+        void *p; TRY(dev_alloc(c, &p, need * sizeof(double))); fs->d_eff = (double *)p; fs->eff_cap = need;     // (earlier buffers go with the ctx)
+    }
+    if (!fs->d_eff_chains) TRY(mk(c, &fs->d_eff_chains, (size_t)c->n_chains));
+    if (n > c->n_chains) return fail(c, "sb_effect_sample: more entries than chains");
+    TRY(sb_eval_stats(c, nullptr));        // the count tensors of the committed states (a state set by sb_set_state has none yet)
+    TRY(h2d(c, fs->d_eff_chains, chains, sizeof(int32_t) * n));
+    SbEffectArgs A; memset(&A, 0, sizeof A);
+    A.P = P; A.states = c->d_states; A.slots = c->d_slots; A.chains = fs->d_eff_chains; A.n = n; A.step = step; A.out = fs->d_eff;
+    const long long items = (long long)P.G_tot * P.F * n;
+    int grid = (int)((items + 127) / 128); if (grid > 8 * c->n_sm) grid = 8 * c->n_sm; if (grid < 1) grid = 1;
+#ifdef SB_HOSTSIM
+    if (ms) *ms = 0.f;
+    hostsim::launch([&]() { sb_effect_sample_kernel(A); }, grid > 4 ? 4 : grid, 64, 0);
+#else
+    EvTimer t(c->stream, ms);
+    sb_effect_sample_kernel<<<grid, 128, 0, c->stream>>>(A);
+    CK(cudaGetLastError());
+    t.stop();
+#endif
+    c->launches++;
+    return d2h(c, out, fs->d_eff, need * sizeof(double));
 }
 
 // posterior terms of every chain from the statistics currently in the ctx; `n_global` = number

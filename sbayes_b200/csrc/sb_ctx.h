@@ -81,6 +81,8 @@ struct sb_ctx {
     float *d_obs_out = nullptr;
     double *d_obs_part = nullptr, *d_obs_ll = nullptr, *d_obs_sums = nullptr;
     unsigned long long *d_gibbs_changed = nullptr;
+    void *eval_ext = nullptr;                        // private state of sb_api_eval.cu (tables of the fine-row statistics pass)
+    void (*eval_ext_free)(void *) = nullptr;
     std::vector<void *> allocs;
     sb_stream_t stream = 0;
     std::string err;

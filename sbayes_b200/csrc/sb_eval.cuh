@@ -275,6 +275,150 @@ SB_DEV void ev_hist_fast(const SbEvalArgs &A) {
         for (int k = sb_tid(); k < P.K; k += sb_nthr()) if (sz[k]) sb_atomic_add_i32(st.sizes + k, sz[k]);
 }
 
+// -----------------------------------------------------------------------------------------
+// Fine-row statistics pass (every BASELINE config: at most 4 components, fewer than 255 fine rows).
+// ONE shared-memory increment per observation instead of two: the bins are indexed by a *fine row*
+//   (cluster k, has-pattern)                     for component 0 of a cluster member
+//   (no cluster, has-pattern)                    for component 0 of a free object (counts nowhere, H only)
+//   (confounder group, has-pattern, in-cluster?) for component c >= 1
+// so that both the count tensors (sum of the fine rows of a group) and the source histogram H[pattern,
+// in-cluster, f, c] (sum over the fine rows of (pattern, in-cluster, c) and over the states) are sums of
+// bins, taken once per CTA in the flush.  Missing values go to an extra bin per (row, feature) (`xs`: the
+// state bytes with NA and padding mapped to S), components without a group to a trash row: the inner
+// loop has no predicate and no select.  Per observation: byte extracts of the state and of the
+// (component + 1) selector, a byte permute that picks the fine row from two registers of the object, one
+// multiply-add, one shifted add, one `red.shared` whose feature offset is an immediate.
+// With one object block per (state, tile) -- every BASELINE shape -- a CTA owns its slice of the
+// statistics block and flushes with plain stores: no memset, no global atomics.
+// -----------------------------------------------------------------------------------------
+struct SbFineArgs {
+    const uint8_t *xs;          // [N, ldx] state bytes, NA / padding = S
+    const uint32_t *obj_fine;   // [N] byte 0 = has-pattern, bytes 1..3 = fine row (not-in-cluster flavour) of the object's group
+                                //     in confounder 1..3; the in-cluster flavour is the next row; trash row if none
+    const int32_t *cnt_ptr, *cnt_idx;   // CSR: fine rows of count row g            [G_tot + 1]
+    const int32_t *h_ptr, *h_idx;       // CSR: fine rows of H row (pz * C + c)     [n_pat * 2 * C + 1]
+    int n_rows;                 // fine rows including the two trash rows
+    int ft, n_ftiles, n_oblk, rows_per_blk;
+    unsigned smem;
+};
+
+#ifdef SB_HOSTSIM
+SB_DEV uint32_t ev_prmt(uint32_t a, uint32_t b, uint32_t s) {
+    const uint64_t pool = (uint64_t)a | ((uint64_t)b << 32);
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) r |= (uint32_t)((pool >> (8 * ((s >> (4 * i)) & 7))) & 255u) << (8 * i);
+    return r;
+}
+template <int OFF> SB_DEV void ev_inc_at(ev_bins_t b, uint32_t byte_addr) { b[(byte_addr >> 2) + OFF]++; }
+SB_DEV uint32_t ev_bins_base(ev_bins_t) { return 0u; }
+#else
+SB_DEV uint32_t ev_prmt(uint32_t a, uint32_t b, uint32_t s) {     // (selector nibbles are 0..7 here: no masking, unlike __byte_perm)
+    uint32_t d; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(s)); return d;
+}
+template <int OFF> SB_DEV void ev_inc_at(ev_bins_t, uint32_t byte_addr) {
+    asm volatile("red.shared.add.u32 [%0+%1], 1;" ::"r"(byte_addr), "n"(OFF * 4) : "memory");
+}
+SB_DEV uint32_t ev_bins_base(ev_bins_t b) { return b; }
+#endif
+
+// the four observations of one word; t0 = byte address of the chunk's first feature in row 0
+template <int S1, int J0>
+SB_DEV void ev_fine_word(ev_bins_t bins, uint32_t xw, uint32_t vw, uint32_t lo, uint32_t hi, uint32_t gs4, uint32_t t0) {
+#define SB_FINE_OBS(j)                                                                                   \
+    {                                                                                                    \
+        const uint32_t v = ev_prmt(vw, 0u, 0x4440u | (j)), x = ev_prmt(xw, 0u, 0x4440u | (j));            \
+        const uint32_t g = ev_prmt(lo, hi, v);                                                           \
+        ev_inc_at<(J0 + (j)) * S1>(bins, g * gs4 + t0 + (x << 2));                                        \
+    }
+    SB_FINE_OBS(0) SB_FINE_OBS(1) SB_FINE_OBS(2) SB_FINE_OBS(3)
+#undef SB_FINE_OBS
+}
+
+template <int S1>
+SB_DEV void ev_hist_fine(const SbEvalArgs &A, const SbFineArgs &FA) {
+    const SbProblem &P = A.P;
+    const int F = P.F, S = P.S, C = P.C, K = P.K;
+    int w = sb_cta();
+    const int oblk = w % FA.n_oblk; w /= FA.n_oblk;
+    const int tile = w % FA.n_ftiles; w /= FA.n_ftiles;
+    const SbShared st = A.states[w];
+    const int f0 = tile * FA.ft;
+    const int ftw = (P.ldx - f0 < FA.ft ? P.ldx - f0 : FA.ft);
+    const int gs = ev_odd(FA.ft * S1);
+    const int lo_o = oblk * FA.rows_per_blk, hi_o = lo_o + FA.rows_per_blk < P.N ? lo_o + FA.rows_per_blk : P.N;
+    int32_t *cnt = (int32_t *)sb_smem();
+    const int n_bins = FA.n_rows * gs;
+    int32_t *sz = cnt + n_bins;                                   // [K]
+    for (int i = sb_tid(); i < n_bins + K; i += sb_nthr()) cnt[i] = 0;
+    sb_cta_sync();
+    const int cpr = ftw >> 4;
+    const ev_bins_t bins = ev_bins(cnt);
+    const uint32_t gs4 = (uint32_t)gs * 4u, base = ev_bins_base(bins);
+    const uint8_t *src0 = st.src[0], *src1 = st.src[1];
+    const uint32_t np = (uint32_t)P.n_pat;
+    for (int o0 = lo_o + sb_warp() * 32; o0 < hi_o; o0 += sb_nwarps() * 32) {
+        const int o = o0 + sb_lane();
+        const bool live = o < hi_o;
+        uint32_t glo = 0u, ghi = 0u;
+        const uint8_t *xr = FA.xs, *sr = src0;
+        if (live) {
+            const int k = st.cluster_of[o];
+            const uint32_t fine = sb_ldg(FA.obj_fine + o);
+            const uint32_t in = k >= 0 ? 1u : 0u;
+            const uint32_t rc = (uint32_t)(k >= 0 ? k : K) * np + (fine & 255u);
+            const uint32_t wv = fine + in * 0x01010100u;            // confounder rows: the in-cluster flavour is the next one
+            glo = ((wv << 8) & 0xFFFF0000u) | (rc << 8);             // selector 1 -> cluster row, 2 / 3 -> confounder 1 / 2
+            ghi = wv >> 24;                                          // selector 4 -> confounder 3
+            const size_t off = (size_t)o * P.ldx + f0;
+            xr = FA.xs + off; sr = (st.osel[o] ? src1 : src0) + off;
+            if (tile == 0 && k >= 0) sb_atomic_add_i32(sz + k, 1);
+        }
+        if (!live) continue;                                         // (no warp-wide operation below)
+        sb_u4 xv, sv, xn, sn;
+        xn = ev_load16(xr); sn = ev_load16(sr);
+        for (int ch = 0; ch < cpr; ch++) {
+            xv = xn; sv = sn;
+            if (ch + 1 < cpr) { xn = ev_load16(xr + (ch + 1) * 16); sn = ev_load16(sr + (ch + 1) * 16); }
+            const uint32_t t0 = base + (uint32_t)(ch * 16 * S1 * 4);
+            // component byte c (255 where the value is missing: its state byte then points at the extra bin) -> selector c + 1
+            ev_fine_word<S1, 0>(bins, xv.x, (sv.x & 0x03030303u) + 0x01010101u, glo, ghi, gs4, t0);
+            ev_fine_word<S1, 4>(bins, xv.y, (sv.y & 0x03030303u) + 0x01010101u, glo, ghi, gs4, t0);
+            ev_fine_word<S1, 8>(bins, xv.z, (sv.z & 0x03030303u) + 0x01010101u, glo, ghi, gs4, t0);
+            ev_fine_word<S1, 12>(bins, xv.w, (sv.w & 0x03030303u) + 0x01010101u, glo, ghi, gs4, t0);
+        }
+    }
+    sb_cta_sync();
+    // flush: every element of this tile's slice of the statistics block is a sum of bins
+    const int fv = F - f0 < ftw ? F - f0 : ftw;                    // real features in the tile
+    const bool own = FA.n_oblk == 1;                               // the CTA owns the slice: plain stores, nothing was zeroed
+    if (fv > 0) {
+        const int n_c = P.G_tot * fv * S;
+        for (int i = sb_tid(); i < n_c; i += sb_nthr()) {
+            const int g = i / (fv * S), r = i - g * (fv * S), fl = r / S, s = r - fl * S;
+            int v = 0;
+            for (int q = sb_ldg(FA.cnt_ptr + g); q < sb_ldg(FA.cnt_ptr + g + 1); q++) v += cnt[sb_ldg(FA.cnt_idx + q) * gs + fl * S1 + s];
+            int32_t *dst = st.counts + ((size_t)g * F + f0 + fl) * S + s;
+            if (own) *dst = v; else if (v) sb_atomic_add_i32(dst, v);
+        }
+        const int n_h = P.n_pat * 2 * fv * C;
+        for (int i = sb_tid(); i < n_h; i += sb_nthr()) {
+            const int pz = i / (fv * C), r = i - pz * (fv * C), fl = r / C, c = r - fl * C;
+            int v = 0;
+            for (int q = sb_ldg(FA.h_ptr + pz * C + c); q < sb_ldg(FA.h_ptr + pz * C + c + 1); q++) {
+                const int32_t *b = cnt + sb_ldg(FA.h_idx + q) * gs + fl * S1;
+                for (int s = 0; s < S; s++) v += b[s];
+            }
+            int32_t *dst = st.H + ((size_t)pz * F + f0 + fl) * C + c;
+            if (own) *dst = v; else if (v) sb_atomic_add_i32(dst, v);
+        }
+    }
+    if (tile == 0)
+        for (int k = sb_tid(); k < K; k += sb_nthr()) { if (own) st.sizes[k] = sz[k]; else if (sz[k]) sb_atomic_add_i32(st.sizes + k, sz[k]); }
+}
+
+template <int S1>
+SB_KERNEL sb_eval_fine_kernel(const SB_GRID_CONSTANT SbEvalArgs A, const SB_GRID_CONSTANT SbFineArgs FA) { ev_hist_fine<S1>(A, FA); }
+
 // (forcing 64 registers for a fourth CTA per SM measured slower: profiles/r1l_eval_smem_sweep.txt)
 SB_KERNEL sb_eval_hist_kernel(const SB_GRID_CONSTANT SbEvalArgs A) {
     if (A.P.obj_pack) ev_hist_fast(A);
@@ -875,6 +1019,78 @@ SB_KERNEL sb_flip_osel_kernel(const SbShared *states, int n_states, int N) {
     for (long long i = (long long)sb_cta() * sb_nthr() + sb_tid(); i < total; i += (long long)sb_ncta() * sb_nthr()) {
         const SbShared st = states[i / N];
         st.osel[i % N] ^= 1;
+    }
+}
+
+// -----------------------------------------------------------------------------------------
+// Effect draws at log time: conditional_effect_sample (sbayes/sampling/conditionals.py:125-149), called by
+// ParametersCSVLogger._write_sample for the cluster effect and every confounding effect of a logged sample
+// (sbayes/sampling/loggers.py:160-224): p[g, f, :] ~ Dirichlet(counts[g, f, :] + alpha[g, f, :]) over the
+// applicable states.  The reference first rebuilds the counts as a [groups, objects, features, states]
+// boolean contraction (conditionals.py:68-86) and then loops over (group, feature) in Python; here the
+// counts are the chain's committed statistics and one thread serves one (chain, group, feature).
+// Gamma draws: Marsaglia-Tsang (2000), shapes below one boosted by U^(1/shape); Philox addressed by
+// (chain seed, step, SITE_EFFECT, attempt sub-stream, (g*F + f)*S + s) -- oracle/effects.py draws the same.
+// -----------------------------------------------------------------------------------------
+#define SB_SITE_EFFECT 14
+struct SbEffectArgs {
+    SbProblem P;
+    const SbShared *states;
+    const SbSlot *slots;
+    const int32_t *chains;       // [n] chain (slot) indices
+    int n;
+    unsigned long long step;
+    double *out;                 // [n, G_tot, F, S]
+};
+
+SB_DEV double ev_effect_gamma(uint32_t k0, uint32_t k1, uint32_t st_lo, uint32_t st_hi, double shape, uint32_t idx) {
+    const bool boost = shape < 1.0;
+    const double a = boost ? shape + 1.0 : shape;
+    const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    for (uint32_t t = 0;; t++) {
+        const sbp::Philox4 p = sbp::philox4x32_10(idx, (uint32_t)SB_SITE_EFFECT | ((2u * t) << 8), st_lo, st_hi, k0, k1);
+        const sbp::Philox4 q = sbp::philox4x32_10(idx, (uint32_t)SB_SITE_EFFECT | ((2u * t + 1u) << 8), st_lo, st_hi, k0, k1);
+        const double u1 = sbp::u01_double(p.w[0], p.w[1]), u2 = sbp::u01_double(p.w[2], p.w[3]);
+        const double u3 = sbp::u01_double(q.w[0], q.w[1]), u4 = sbp::u01_double(q.w[2], q.w[3]);
+        const double xn = sqrt(-2.0 * log(1.0 - u1)) * cos(2.0 * 3.141592653589793 * u2);
+        double v = 1.0 + c * xn;
+        if (v <= 0.0) continue;
+        v = v * v * v;
+        if (log(1.0 - u3) < 0.5 * xn * xn + d - d * v + d * log(v)) {
+            double g = d * v;
+            if (boost) g *= exp(log(1.0 - u4) / shape);
+            return g;
+        }
+    }
+}
+
+SB_KERNEL sb_effect_sample_kernel(const SB_GRID_CONSTANT SbEffectArgs A) {
+    const SbProblem &P = A.P;
+    const int F = P.F, S = P.S;
+    const long long per = (long long)P.G_tot * F, total = per * A.n;
+    for (long long it = (long long)sb_cta() * sb_nthr() + sb_tid(); it < total; it += (long long)sb_ncta() * sb_nthr()) {
+        const int ci = (int)(it / per);
+        const long long gf = it - (long long)ci * per;
+        const int g = (int)(gf / F), f = (int)(gf - (long long)g * F);
+        const SbSlot sl = A.slots[A.chains[ci]];
+        const SbShared st = A.states[sl.state];
+        const uint32_t k0 = (uint32_t)(sl.cfg.seed & 0xFFFFFFFFull), k1 = (uint32_t)(sl.cfg.seed >> 32);
+        const uint32_t st_lo = (uint32_t)(A.step & 0xFFFFFFFFull), st_hi = (uint32_t)(A.step >> 32);
+        const double *al = P.alpha + ((size_t)ev_arow(P, g) * F + f) * S;
+        const int32_t *cr = st.counts + (size_t)gf * S;
+        double *out = A.out + (size_t)it * S;
+        double tot = 0.0; int n_app = 0;
+        for (int s = 0; s < S; s++) {
+            const double a = sb_ldg(al + s);
+            double v = 0.0;
+            if (a > 0.0) { v = ev_effect_gamma(k0, k1, st_lo, st_hi, a + (double)cr[s], (uint32_t)(gf * S + s)); n_app++; }
+            out[s] = v; tot += v;
+        }
+        for (int s = 0; s < S; s++) {
+            const bool app = sb_ldg(al + s) > 0.0;
+            // (all draws underflowed -- concentrations far below one: fall back to the uniform vector)
+            out[s] = tot > 0.0 ? out[s] / tot : (app ? 1.0 / (double)n_app : 0.0);
+        }
     }
 }
 

@@ -18,12 +18,17 @@ from sbayes_b200.packed import ChainConfig, SIZE_UNIFORM_SIZE, SIZE_QUADRATIC  #
 TOL = parity.TOL_ORACLE      # 1e-10 relative
 
 
-def check_batch(prob, states, lib=None, cfgs=None):
+def check_batch(prob, states, lib=None, cfgs=None, want_pass=None, geometry=None):
     ctx = DeviceContext(prob, len(states), _lib=lib)
     try:
         for c, st in enumerate(states):
             ctx.configure(c, cfgs[c] if cfgs else ChainConfig(seed=c))
             ctx.set_state(c, st)
+        if want_pass:
+            info = ctx.eval_info()
+            assert info["pass"] == want_pass, info
+            if geometry:
+                assert (info["n_ftiles"], info["n_oblk"]) == geometry, info
         res = ctx.eval_batch()
         for c, st in enumerate(states):
             ref = st.copy()
@@ -65,14 +70,31 @@ def env():
 
 def test_emulated_eval_batch(lib):
     prob, sts = small_problem()
-    check_batch(prob, sts, lib)
+    check_batch(prob, sts, lib, want_pass="fine", geometry=(1, 1))      # one increment per observation, plain-store flush
+
+
+def test_emulated_eval_fine_tiles_and_object_blocks(lib, env):
+    """fine-row pass with several feature tiles (the last one narrower) and several object blocks (atomic flush)"""
+    prob, sts = small_problem(F=70)
+    env["SB_HOSTSIM_FINE_FT"] = "32"
+    check_batch(prob, sts, lib, want_pass="fine", geometry=(3, 1))
+    env["SB_HOSTSIM_EVAL_OBLK"] = "3"
+    check_batch(prob, sts, lib, want_pass="fine", geometry=(3, 3))
+
+
+def test_emulated_eval_two_increment_pass(lib, env):
+    """the two-increment histogram (what problems with more than 254 fine rows fall back to)"""
+    prob, sts = small_problem()
+    env["SB_EVAL_NO_FINE"] = "1"
+    check_batch(prob, sts, lib, want_pass="hist")
 
 
 def test_emulated_eval_feature_tiles_and_object_blocks(lib, env):
     prob, sts = small_problem(F=70)
     env["SB_HOSTSIM_EVAL_SMEM"] = str(16 * (prob.G_tot * prob.S + 2 * 2 * prob.C) * 4 + prob.K * 4 + 64 + 200)   # 16-feature tiles
     env["SB_HOSTSIM_EVAL_OBLK"] = "3"
-    check_batch(prob, sts, lib)
+    env["SB_EVAL_NO_FINE"] = "1"
+    check_batch(prob, sts, lib, want_pass="hist")
 
 
 def test_emulated_eval_priors(lib):

@@ -45,9 +45,12 @@ def main():
             ctx.eval_batch()
             ts = [ctx.eval_batch(timing=True) for _ in range(10)]
             h = min(t[1][0] for t in ts); tm = min(t[1][1] for t in ts)
+            print(f"[{name}] statistics pass: {ctx.eval_info()}", flush=True)
             print(f"[{name}] eval_batch: stats {h*1e3:.1f} us ({fe/h/1e6:.1f} GB/s algorithmic) terms {tm*1e3:.1f} us  -> {w['chains']/((h+tm)*1e-3):.0f} evals/s  "
                   f"ll={ts[0][0][0]['ll']} prior={ts[0][0][0]['prior']}", flush=True)
             try:
+                if "--no-mma" in sys.argv:
+                    raise RuntimeError("skipped")
                 ctx.eval_set_mode("mma")
                 ctx.eval_batch()
                 ts = [ctx.eval_batch(timing=True) for _ in range(10)]
