@@ -95,17 +95,21 @@ static int fine_setup(sb_ctx *c) {
     csr(cl, cp, ci); csr(hl, hp, hi);
     // launch plan: the widest feature tile whose bins fit the budget, balanced tiles, object blocks by the cost model of the
     // two-increment pass (one block per (state, tile) lets the CTA own its slice of the statistics)
-    const size_t per_f = (size_t)R * S1 * 4, fixed = (size_t)K * 4 + (size_t)R * 4 + 64;
-    size_t budget = 56 * 1024;
+    const size_t per_f = (size_t)R * S1 * 4, fixed = (size_t)K * 4 + (size_t)R * 4 + 64 + ((size_t)P.G_tot + (size_t)np * 2 * C + 2 + 2 * (size_t)R) * 4;
+    // measured (profiles/r4e_finesweep.txt): 32-feature tiles in about 55 KB at config 4 (four CTAs per SM) 122 us against 164 us
+    // of the two-increment pass; where 32-feature tiles of fine rows do not fit that budget (config 5: 170 rows x 9 bins) the
+    // two-increment pass with its fewer rows stays faster, so the fine pass is only planned when they fit
+    size_t budget = 60 * 1024;
 #ifdef SB_HOSTSIM
     if (getenv("SB_HOSTSIM_EVAL_SMEM")) budget = (size_t)atol(getenv("SB_HOSTSIM_EVAL_SMEM"));
+    if (budget < fixed + 16 * per_f) budget = fixed + 16 * per_f;         // (the emulator has no capacity limit)
 #else
     if (getenv("SB_FINE_SMEM_KB")) budget = (size_t)atol(getenv("SB_FINE_SMEM_KB")) * 1024;
+    if (budget < fixed + (P.ldx < 32 ? P.ldx : 32) * per_f) return 0;
 #endif
-    if (budget < fixed + 16 * per_f) budget = 110 * 1024;
-    if (budget < fixed + 16 * per_f) budget = 220 * 1024;
-    if (budget < fixed + 16 * per_f) return 0;
     int ft_max = (int)((budget - fixed) / per_f) / 16 * 16;
+    if (ft_max < 16) return 0;
+    if (ft_max > 32 && !getenv("SB_FINE_WIDE")) ft_max = 32;                     // (wider tiles measured slower at config 2 and 4)
 #ifdef SB_HOSTSIM
     if (getenv("SB_HOSTSIM_FINE_FT")) ft_max = atoi(getenv("SB_HOSTSIM_FINE_FT"));      // tests: several feature tiles
 #endif
@@ -122,6 +126,7 @@ static int fine_setup(sb_ctx *c) {
         const double cost = (double)waves * ((double)((N + n - 1) / n) * ft + 3.0 * (double)ft * R * S1);
         if (best < 0.0 || cost < best) { best = cost; n_oblk = n; }
     }
+    if (getenv("SB_FINE_OBLK")) n_oblk = atoi(getenv("SB_FINE_OBLK"));      // tuning knob
 #ifdef SB_HOSTSIM
     if (getenv("SB_HOSTSIM_EVAL_OBLK")) n_oblk = atoi(getenv("SB_HOSTSIM_EVAL_OBLK"));
 #endif

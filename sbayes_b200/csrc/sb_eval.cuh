@@ -349,42 +349,64 @@ SB_DEV void ev_hist_fine(const SbEvalArgs &A, const SbFineArgs &FA) {
     int32_t *cnt = (int32_t *)sb_smem();
     const int n_bins = FA.n_rows * gs;
     int32_t *sz = cnt + n_bins;                                   // [K]
+    // the row lists of the flush, staged once (a flush element would otherwise walk a chain of dependent global loads)
+    const int n_cp = P.G_tot + 1, n_hp = P.n_pat * 2 * C + 1;
+    int32_t *t_cp = sz + K, *t_hp = t_cp + n_cp, *t_ci = t_hp + n_hp, *t_hi = t_ci + FA.n_rows;
     for (int i = sb_tid(); i < n_bins + K; i += sb_nthr()) cnt[i] = 0;
+    for (int i = sb_tid(); i < n_cp; i += sb_nthr()) t_cp[i] = sb_ldg(FA.cnt_ptr + i);
+    for (int i = sb_tid(); i < n_hp; i += sb_nthr()) t_hp[i] = sb_ldg(FA.h_ptr + i);
+    for (int i = sb_tid(); i < FA.n_rows; i += sb_nthr()) {       // (each list has at most n_rows entries)
+        t_ci[i] = i < sb_ldg(FA.cnt_ptr + P.G_tot) ? sb_ldg(FA.cnt_idx + i) : 0;
+        t_hi[i] = i < sb_ldg(FA.h_ptr + n_hp - 1) ? sb_ldg(FA.h_idx + i) : 0;
+    }
     sb_cta_sync();
     const int cpr = ftw >> 4;
     const ev_bins_t bins = ev_bins(cnt);
     const uint32_t gs4 = (uint32_t)gs * 4u, base = ev_bins_base(bins);
     const uint8_t *src0 = st.src[0], *src1 = st.src[1];
     const uint32_t np = (uint32_t)P.n_pat;
-    for (int o0 = lo_o + sb_warp() * 32; o0 < hi_o; o0 += sb_nwarps() * 32) {
-        const int o = o0 + sb_lane();
-        const bool live = o < hi_o;
-        uint32_t glo = 0u, ghi = 0u;
-        const uint8_t *xr = FA.xs, *sr = src0;
-        if (live) {
-            const int k = st.cluster_of[o];
-            const uint32_t fine = sb_ldg(FA.obj_fine + o);
-            const uint32_t in = k >= 0 ? 1u : 0u;
-            const uint32_t rc = (uint32_t)(k >= 0 ? k : K) * np + (fine & 255u);
-            const uint32_t wv = fine + in * 0x01010100u;            // confounder rows: the in-cluster flavour is the next one
-            glo = ((wv << 8) & 0xFFFF0000u) | (rc << 8);             // selector 1 -> cluster row, 2 / 3 -> confounder 1 / 2
-            ghi = wv >> 24;                                          // selector 4 -> confounder 3
-            const size_t off = (size_t)o * P.ldx + f0;
-            xr = FA.xs + off; sr = (st.osel[o] ? src1 : src0) + off;
-            if (tile == 0 && k >= 0) sb_atomic_add_i32(sz + k, 1);
-        }
-        if (!live) continue;                                         // (no warp-wide operation below)
-        sb_u4 xv, sv, xn, sn;
-        xn = ev_load16(xr); sn = ev_load16(sr);
-        for (int ch = 0; ch < cpr; ch++) {
-            xv = xn; sv = sn;
-            if (ch + 1 < cpr) { xn = ev_load16(xr + (ch + 1) * 16); sn = ev_load16(sr + (ch + 1) * 16); }
-            const uint32_t t0 = base + (uint32_t)(ch * 16 * S1 * 4);
-            // component byte c (255 where the value is missing: its state byte then points at the extra bin) -> selector c + 1
-            ev_fine_word<S1, 0>(bins, xv.x, (sv.x & 0x03030303u) + 0x01010101u, glo, ghi, gs4, t0);
-            ev_fine_word<S1, 4>(bins, xv.y, (sv.y & 0x03030303u) + 0x01010101u, glo, ghi, gs4, t0);
-            ev_fine_word<S1, 8>(bins, xv.z, (sv.z & 0x03030303u) + 0x01010101u, glo, ghi, gs4, t0);
-            ev_fine_word<S1, 12>(bins, xv.w, (sv.w & 0x03030303u) + 0x01010101u, glo, ghi, gs4, t0);
+    // software pipeline over the warp's trips (32 objects each): the per-object words (cluster, fine rows, committed
+    // copy) of trip t + 2 and the first chunks of trip t + 1 are in flight while trip t is counted -- the source row's
+    // address depends on the committed-copy byte, two dependent global loads that would otherwise be exposed per trip
+    const int stride = sb_nwarps() * 32;
+    const int o_first = lo_o + sb_warp() * 32 + sb_lane(), o_last = hi_o - 1;
+    auto clampo = [&](int o) { return o < hi_o ? o : o_last; };
+    if (lo_o + sb_warp() * 32 < hi_o) {
+        int kA, kB; uint32_t fineA, fineB; uint8_t selA, selB;
+        { const int o = clampo(o_first); kA = st.cluster_of[o]; fineA = sb_ldg(FA.obj_fine + o); selA = st.osel[o]; }
+        { const int o = clampo(o_first + stride); kB = st.cluster_of[o]; fineB = sb_ldg(FA.obj_fine + o); selB = st.osel[o]; }
+        const uint8_t *xrA, *srA;
+        { const size_t off = (size_t)clampo(o_first) * P.ldx + f0; xrA = FA.xs + off; srA = (selA ? src1 : src0) + off; }
+        sb_u4 xn = ev_load16(xrA), sn = ev_load16(srA);
+        for (int o = o_first; o - sb_lane() < hi_o; o += stride) {
+            // trip t + 1: row pointers from the words requested a trip ago, first chunks requested now; trip t + 2: words requested
+            const uint8_t *xrB, *srB;
+            { const size_t off = (size_t)clampo(o + stride) * P.ldx + f0; xrB = FA.xs + off; srB = (selB ? src1 : src0) + off; }
+            const sb_u4 xB = ev_load16(xrB), sB = ev_load16(srB);
+            int kC; uint32_t fineC; uint8_t selC;
+            { const int oc = clampo(o + 2 * stride); kC = st.cluster_of[oc]; fineC = sb_ldg(FA.obj_fine + oc); selC = st.osel[oc]; }
+            if (o < hi_o) {                                          // (no warp-wide operation below)
+                const int k = kA;
+                const uint32_t in = k >= 0 ? 1u : 0u;
+                const uint32_t rc = (uint32_t)(k >= 0 ? k : K) * np + (fineA & 255u);
+                const uint32_t wv = fineA + in * 0x01010100u;        // confounder rows: the in-cluster flavour is the next one
+                const uint32_t glo = ((wv << 8) & 0xFFFF0000u) | (rc << 8);   // selector 1 -> cluster row, 2 / 3 -> confounder 1 / 2
+                const uint32_t ghi = wv >> 24;                       // selector 4 -> confounder 3
+                if (tile == 0 && k >= 0) sb_atomic_add_i32(sz + k, 1);
+                sb_u4 xv, sv;
+                for (int ch = 0; ch < cpr; ch++) {
+                    xv = xn; sv = sn;
+                    if (ch + 1 < cpr) { xn = ev_load16(xrA + (ch + 1) * 16); sn = ev_load16(srA + (ch + 1) * 16); }
+                    const uint32_t t0 = base + (uint32_t)(ch * 16 * S1 * 4);
+                    // component byte c (255 where the value is missing: its state byte then points at the extra bin) -> selector c + 1
+                    ev_fine_word<S1, 0>(bins, xv.x, (sv.x & 0x03030303u) + 0x01010101u, glo, ghi, gs4, t0);
+                    ev_fine_word<S1, 4>(bins, xv.y, (sv.y & 0x03030303u) + 0x01010101u, glo, ghi, gs4, t0);
+                    ev_fine_word<S1, 8>(bins, xv.z, (sv.z & 0x03030303u) + 0x01010101u, glo, ghi, gs4, t0);
+                    ev_fine_word<S1, 12>(bins, xv.w, (sv.w & 0x03030303u) + 0x01010101u, glo, ghi, gs4, t0);
+                }
+            }
+            kA = kB; fineA = fineB; xrA = xrB; srA = srB; xn = xB; sn = sB;
+            kB = kC; fineB = fineC; selB = selC;
         }
     }
     sb_cta_sync();
@@ -392,20 +414,22 @@ SB_DEV void ev_hist_fine(const SbEvalArgs &A, const SbFineArgs &FA) {
     const int fv = F - f0 < ftw ? F - f0 : ftw;                    // real features in the tile
     const bool own = FA.n_oblk == 1;                               // the CTA owns the slice: plain stores, nothing was zeroed
     if (fv > 0) {
-        const int n_c = P.G_tot * fv * S;
-        for (int i = sb_tid(); i < n_c; i += sb_nthr()) {
-            const int g = i / (fv * S), r = i - g * (fv * S), fl = r / S, s = r - fl * S;
-            int v = 0;
-            for (int q = sb_ldg(FA.cnt_ptr + g); q < sb_ldg(FA.cnt_ptr + g + 1); q++) v += cnt[sb_ldg(FA.cnt_idx + q) * gs + fl * S1 + s];
-            int32_t *dst = st.counts + ((size_t)g * F + f0 + fl) * S + s;
-            if (own) *dst = v; else if (v) sb_atomic_add_i32(dst, v);
+        for (int g = sb_warp(); g < P.G_tot; g += sb_nwarps()) {       // warps over groups, lanes over the (feature, state) row
+            const int q0 = t_cp[g], q1 = t_cp[g + 1];
+            int32_t *drow = st.counts + ((size_t)g * F + f0) * S;
+            for (int r = sb_lane(), fl = sb_lane() / S, s0 = sb_lane() - (sb_lane() / S) * S; r < fv * S; r += 32) {
+                int v = 0;
+                for (int q = q0; q < q1; q++) v += cnt[t_ci[q] * gs + fl * S1 + s0];
+                if (own) drow[r] = v; else if (v) sb_atomic_add_i32(drow + r, v);
+                s0 += 32 % S; fl += 32 / S; if (s0 >= S) { s0 -= S; fl++; }
+            }
         }
         const int n_h = P.n_pat * 2 * fv * C;
         for (int i = sb_tid(); i < n_h; i += sb_nthr()) {
             const int pz = i / (fv * C), r = i - pz * (fv * C), fl = r / C, c = r - fl * C;
             int v = 0;
-            for (int q = sb_ldg(FA.h_ptr + pz * C + c); q < sb_ldg(FA.h_ptr + pz * C + c + 1); q++) {
-                const int32_t *b = cnt + sb_ldg(FA.h_idx + q) * gs + fl * S1;
+            for (int q = t_hp[pz * C + c]; q < t_hp[pz * C + c + 1]; q++) {
+                const int32_t *b = cnt + t_hi[q] * gs + fl * S1;
                 for (int s = 0; s < S; s++) v += b[s];
             }
             int32_t *dst = st.H + ((size_t)pz * F + f0 + fl) * C + c;

@@ -70,7 +70,7 @@ def env():
 
 def test_emulated_eval_batch(lib):
     prob, sts = small_problem()
-    check_batch(prob, sts, lib, want_pass="fine", geometry=(1, 1))      # one increment per observation, plain-store flush
+    check_batch(prob, sts, lib, want_pass="fine", geometry=(2, 1))      # one increment per observation, plain-store flush
 
 
 def test_emulated_eval_fine_tiles_and_object_blocks(lib, env):

@@ -3,7 +3,7 @@ usage: tools_evalprof.py <case> <hist|mma> [chains]"""
 import os as _os, sys as _sys
 _sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # repo root (bench.py, sbayes_b200/, oracle/)
 import sys
-import tools_scale as TS
+from tools import scale as TS
 from sbayes_b200 import synth
 from sbayes_b200.backend import DeviceContext
 from sbayes_b200.packed import ChainConfig

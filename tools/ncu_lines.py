@@ -7,8 +7,12 @@ rep, lib = sys.argv[1], sys.argv[2]
 kern = sys.argv[3] if len(sys.argv) > 3 else "sb_run_kernel"
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
+dis = []
+for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):      # one per translation unit: take the one with the kernel
+    d = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
+    if any(l.startswith("\t.section\t.text.") and kern in l for l in d):
+        dis = d
+        break
 # instructions of the kernel with their line info (innermost line + inline chain)
 ins = []; on = False; cur = None
 for l in dis:
