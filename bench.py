@@ -414,9 +414,10 @@ def full_eval_line(ctx, prob, n_chains, label, tag, flush, peak, reps=7):
                 ts.append(ctx.eval_batch(timing=True)[1])
             st, tm = float(np.median([t[0] for t in ts])), float(np.median([t[1] for t in ts]))
             algo = 2.0 * prob.N * prob.F * n_chains
-            kern = "sb_eval_hist_kernel" if mode == "hist" else "sb_counts_mma_kernel"
+            info = ctx.eval_info()          # which statistics pass the library planned for this shape
+            kern = {"hist": "sb_eval_hist_kernel", "fine": "sb_eval_fine_kernel", "mma": "sb_counts_mma_kernel"}[info["pass"]]
             out[mode] = {"stats_us": st * 1e3, "terms_us": tm * 1e3, "evals_per_sec": n_chains / ((st + tm) * 1e-3),
-                         "roofline": roofline(kern, algo, st * 1e-3, peak, ncu_traffic(kern, tag))}
+                         "pass": info, "roofline": roofline(kern, algo, st * 1e-3, peak, ncu_traffic(kern, tag))}
         except Exception as e:       # the tensor-core pass refuses problems with > 256 group columns
             out[mode] = {"unavailable": str(e)}
     ctx.eval_set_mode("hist")
@@ -447,6 +448,12 @@ def full_eval_line(ctx, prob, n_chains, label, tag, flush, peak, reps=7):
                                                        ncu_traffic("sb_gibbs_sweep_kernel", tag))}
     except Exception as e:
         out["gibbs_sweep"] = {"unavailable": str(e)}
+    try:      # effect draws at log time (conditional_effect_sample of the parameter logger) for every chain
+        ctx.effect_sample(step=1)
+        ts = [ctx.effect_sample(step=2 + i, timing=True)[1] for i in range(3)]
+        out["effect_sample"] = {"us": float(np.median(ts)) * 1e3, "draws": int(prob.G_tot * prob.F * n_chains)}
+    except Exception as e:
+        out["effect_sample"] = {"unavailable": str(e)}
     return out
 
 

@@ -19,6 +19,7 @@ from __future__ import annotations
 import logging
 import os
 import time as _time
+import threading
 import typing as typ
 
 import numpy as np
@@ -167,6 +168,7 @@ class MCMCChain:
         s = refbridge.sample_from_state(self.prob, self.model, self.data, st, type(template), i_step=i_step,
                                         chain=getattr(template, "chain", 0))
         refbridge.fill_cache_from_device(self.prob, s, exp, self.sample_from_prior)
+        _attach_effects(self.ctx, self.prob, s, 0, i_step)
         self._ll = s.last_lh / self.temperature
         self._prior = s.last_prior / self.prior_temperature
         self._uploaded, self._eval = s, post
@@ -281,6 +283,7 @@ class MCMC:
         exp = self.ctx.export_samples([chain])[0]
         s = refbridge.sample_from_state(self.prob, self.model, self.data, exp["state"], type(template), i_step=i_step, chain=chain)
         refbridge.fill_cache_from_device(self.prob, s, exp, self.sample_from_prior)
+        _attach_effects(self.ctx, self.prob, s, chain, i_step)
         self._ll[chain], self._prior[chain] = s.last_lh, s.last_prior
         return s
 
@@ -481,6 +484,50 @@ class _ExplicitWeights(ChainConfig):
         return self._w
 
 
+def _attach_effects(ctx, prob, sample, chain: int, i_step: int):
+    """The effect draws the parameter logger asks for (conditional_effect_sample, sbayes/sampling/conditionals.py:125-149,
+    called at sbayes/sampling/loggers.py:162 and :217) taken on the device from the chain's committed counts: one array per
+    call the logger will make (cluster effect, then every confounder in order).  `install_effect_logging` hands them out."""
+    p = ctx.effect_sample([chain], step=int(i_step))[0]
+    offs = prob.group_offsets()
+    sample._sb_effects = [p[offs[i]:offs[i + 1]] for i in range(len(offs) - 1)]
+
+
+_effect_state = threading.local()
+effect_logging_stats = {"device": 0, "host": 0}       # how many effect arrays the logger took from the device / drew on the host
+
+
+def install_effect_logging():
+    """Rebind `conditional_effect_sample` inside the reference's logger module: while a `ParametersCSVLogger` writes a sample
+    that came from the device chain, its calls return the device's draws (in call order) instead of rebuilding a
+    [groups, objects, features, states] boolean contraction per effect on the host (conditionals.py:68-86); any other
+    sample takes the reference's own path."""
+    import sbayes.sampling.loggers as lg
+    if getattr(lg, "_sb_effects_installed", False):
+        return
+    orig_sample, orig_write = lg.conditional_effect_sample, lg.ParametersCSVLogger._write_sample
+
+    def conditional_effect_sample(features, is_source_group, applicable_states, prior_counts=0.1):
+        queue = getattr(_effect_state, "queue", None)
+        if queue:
+            effect_logging_stats["device"] += 1
+            return queue.pop(0)
+        effect_logging_stats["host"] += 1
+        return orig_sample(features=features, is_source_group=is_source_group, applicable_states=applicable_states, prior_counts=prior_counts)
+
+    def _write_sample(self, sample):
+        eff = getattr(sample, "_sb_effects", None)
+        _effect_state.queue = list(eff) if eff is not None else None
+        try:
+            return orig_write(self, sample)
+        finally:
+            _effect_state.queue = None
+
+    lg.conditional_effect_sample = conditional_effect_sample
+    lg.ParametersCSVLogger._write_sample = _write_sample
+    lg._sb_effects_installed = True
+
+
 def install(*, seed: typ.Optional[int] = None, device: typ.Optional[int] = None, _lib=None):
     """Make the reference use the device chain: `sbayes.sampling.mcmc_chain.MCMCChain` and the
     name imported into `sbayes.mcmc_setup` (sbayes/mcmc_setup.py:25) are rebound; so are
@@ -526,4 +573,5 @@ def install(*, seed: typ.Optional[int] = None, device: typ.Optional[int] = None,
     ms.MCMCChain = InstalledMCMCChain
     mm.MCMC = InstalledMCMC
     ms.MCMC = InstalledMCMC
+    install_effect_logging()
     return InstalledMCMCChain

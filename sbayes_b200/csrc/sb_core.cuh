@@ -1287,16 +1287,28 @@ SB_DEV void tiled_pass(Run &R, int k, int k2, Sel sel, Tail tail) {
         int pb = sb_ldg(P.combo_start + j0), pe = sb_ldg(P.combo_start + j1);
         if (pb < plo) pb = plo;
         if (pe > phi) pe = phi;
+        // one object ahead: position -> object -> (selected?, combo, row pointer) -> first 16 bytes of the row is a chain of
+        // dependent loads (L2 round trips at the large shapes); the next object's chain is in flight while this one's row is walked
+        int p_n = pb + sb_warp() * gpw + sb_lane() / L;
+        int o_n = p_n < pe ? sb_ldg(P.perm + p_n) : 0;
+        bool on_n = p_n < pe && sel(o_n);
+        const double *tc_n = unit; const uint8_t *xr_n = PAIRS ? P.xp : P.x;
+        if (on_n) { tc_n = unit + 2 + (size_t)(m_combo(R, o_n) - j0) * per_combo; xr_n = PAIRS ? P.xp + (size_t)o_n * P.ldp : x_row(R, o_n); }
+        Row16 nx = load_row16(xr_n + (q < nchunks ? q : 0) * 16);
         for (int p0 = pb + sb_warp() * gpw; p0 < pe; p0 += ngroups) {   // warp-uniform trip count
-            const int p = p0 + sb_lane() / L;
-            const bool active = p < pe;
-            const int o = active ? sb_ldg(P.perm + p) : 0;
-            const bool on = active && sel(o);
+            const int p = p_n, o = o_n;
+            const bool active = p < pe, on = on_n;
+            const double *tc = tc_n; const uint8_t *xr = xr_n;
+            Row16 cur0 = nx;
+            p_n = p + ngroups;
+            o_n = p_n < pe ? sb_ldg(P.perm + p_n) : 0;
+            on_n = p_n < pe && sel(o_n);
+            tc_n = unit; xr_n = PAIRS ? P.xp : P.x;
+            if (on_n) { tc_n = unit + 2 + (size_t)(m_combo(R, o_n) - j0) * per_combo; xr_n = PAIRS ? P.xp + (size_t)o_n * P.ldp : x_row(R, o_n); }
+            const Row16 first_n = load_row16(xr_n + (q < nchunks ? q : 0) * 16);
             Prod a = prod_one(), b = prod_one();
             if (on) {
-                const double *tc = unit + 2 + (size_t)(m_combo(R, o) - j0) * per_combo;
-                const uint8_t *xr = PAIRS ? P.xp + (size_t)o * P.ldp : x_row(R, o);
-                Row16 nx = load_row16(xr + (q < nchunks ? q : 0) * 16);
+                nx = cur0;
                 for (int ch = q; ch < nchunks; ch += L) {
                     const Row16 cur = nx;
                     if (ch + L < nchunks) nx = load_row16(xr + (ch + L) * 16);   // requested before the gathers of the current chunk
@@ -1304,6 +1316,7 @@ SB_DEV void tiled_pass(Run &R, int k, int k2, Sel sel, Tail tail) {
                     else chunk_products<W>(unit, tc, S, ch * 16, cur, a, b);
                 }
             }
+            nx = first_n;
             for (int off = L >> 1; off > 0; off >>= 1) {
                 a.m *= sb_shfl_f64(a.m, sb_lane() ^ off); a.e += sb_shfl_i32(a.e, sb_lane() ^ off); prod_renorm(a);
                 if (W == 2) { b.m *= sb_shfl_f64(b.m, sb_lane() ^ off); b.e += sb_shfl_i32(b.e, sb_lane() ^ off); prod_renorm(b); }

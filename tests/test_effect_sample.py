@@ -123,3 +123,36 @@ def test_concentration_is_the_references():
         ctx.close()
     z = (dev.mean(axis=0) - conc / a0) / np.sqrt(np.maximum(var, 1e-300) / 200)
     assert np.abs(z[conc > 0]).max() < 5.0
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_parameter_logger_takes_device_draws(backend, tmp_path):
+    """the reference's own ParametersCSVLogger, fed by the drop-in chain: its effect columns are the device's draws"""
+    from test_dropin_chain import _reference_problem
+    from sbayes_b200 import chain as CHN
+    r = H.ref()
+    import sbayes.sampling.loggers as lg
+    prob0, data, model = _reference_problem()
+    CHN.install_effect_logging()
+    logger = lg.ParametersCSVLogger(str(tmp_path / "stats.txt"), data, model, False, match_clusters=False)
+    opcfg = r.config.OperatorsConfig(clusters=70, weights=10, source=20)
+    ch = CHN.MCMCChain(model, data, opcfg, [logger], temperature=1.0, prior_temperature=1.0, seed=99, team=2, _lib=_lib(backend))
+    prob = ch.prob
+    st0 = synth.initial_state(prob, seed=3, objects_per_cluster=6)
+    st0.counts = M.rebuild_counts(prob, st0)
+    before = dict(CHN.effect_logging_stats)
+    out = ch.run(n_steps=60, logging_interval=30, initial_sample=H.sample_from_state(prob, model, data, st0))
+    logger.close()
+    n_eff = 1 + len(prob.conf_gid)
+    assert CHN.effect_logging_stats["device"] - before["device"] == 2 * n_eff      # two logged samples
+    assert CHN.effect_logging_stats["host"] == before["host"]
+    # the last row's areal columns are the oracle's draws from the final state's counts (same Philox streams)
+    rows = [l.rstrip("\n").split("\t") for l in open(tmp_path / "stats.txt")]
+    head, last = rows[0], rows[-1]
+    st = H.state_from_sample(prob, out)
+    want = E.effect_sample(prob, M.rebuild_counts(prob, st), ch._cfg.seed, 60)
+    for name, k, f, s in (("areal_a0_f0_s0", 0, 0, 0), ("areal_a1_f3_s1", 1, 3, 1)):
+        assert abs(float(last[head.index(name)]) - want[k, f, s]) < 1e-7        # (the logger prints 8 significant digits)
+    off = prob.group_offsets()[2]
+    assert abs(float(last[head.index("family_g1_f2_s0")]) - want[off + 1, 2, 0]) < 1e-7
