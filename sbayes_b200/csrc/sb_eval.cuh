@@ -50,6 +50,13 @@ SB_DEV sb_u4 ev_load16(const uint8_t *p) {      // p is 16-byte aligned
     const uint4 t = *(const uint4 *)p; sb_u4 v; v.x = t.x; v.y = t.y; v.z = t.z; v.w = t.w; return v;
 #endif
 }
+#ifdef SB_HOSTSIM
+SB_DEV void ev_store_f32x4(float *p, float a, float b, float c, float d) { p[0] = a; p[1] = b; p[2] = c; p[3] = d; }
+SB_DEV void ev_store16(uint8_t *p, const sb_u4 &v) { memcpy(p, &v, 16); }
+#else
+SB_DEV void ev_store_f32x4(float *p, float a, float b, float c, float d) { *(float4 *)p = make_float4(a, b, c, d); }   // p is 16-byte aligned
+SB_DEV void ev_store16(uint8_t *p, const sb_u4 &v) { *(uint4 *)p = make_uint4(v.x, v.y, v.z, v.w); }                 // p is 16-byte aligned
+#endif
 SB_DEV int ev_arow(const SbProblem &P, int g) { return g < P.K ? (P.dedup ? 0 : g) : g - P.arow_off; }
 
 // -----------------------------------------------------------------------------------------
@@ -674,10 +681,11 @@ static inline int sb_obs_make_plan(const SbProblem &P, int n_states, int n_sm, S
     return 0;
 }
 
-// Work mapping: a row of the tile (one object, ft features) is shared by ft/4 lanes, lane j of
-// the row takes features j, j + ft/4, j + 2 ft/4, j + 3 ft/4 -- every load, table gather and
-// store of one instruction then touches consecutive features (coalesced bytes in, coalesced
-// floats out, table rows with odd strides); 32 / (ft/4) rows per warp iteration.
+// Work mapping: a lane takes one 16-byte chunk of a row (16 features of one object: one 16-byte load of the states,
+// one of the sources, four 16-byte stores of floats), so the per-object set-up (cluster, group rows, weight row, row
+// pointers) is paid once per 16 observations; ft/16 lanes share a row, 32 / (ft/16) rows per warp iteration.
+// (Round 1 gave a lane 4 features of a row: coalesced single-byte loads, but the set-up -- about 100 instructions --
+// was paid per 4 observations.)
 template <int UC>
 SB_DEV void ev_obs_body(const SbObsArgs &A) {
     const SbProblem &P = A.P;
@@ -720,13 +728,12 @@ SB_DEV void ev_obs_body(const SbObsArgs &A) {
     }
     sb_cta_sync();
     const int lo = oblk * pl.rows_per_blk, hi = lo + pl.rows_per_blk < N ? lo + pl.rows_per_blk : N;
-    const int lpr = ft >> 2, rpw = 32 / lpr;                       // lanes per row, rows per warp iteration
+    const int lpr = ft >> 4, rpw = 32 / lpr;                       // lanes per row (one 16-byte chunk each), rows per warp iteration
     const int fg = sb_lane() % lpr, rw = sb_lane() / lpr;
-    int rot[4];
-#ifndef SB_HOSTSIM
-#pragma unroll
-#endif
-    for (int j = 0; j < 4; j++) rot[j] = (fg + j * lpr) % S;
+    const int fb = fg << 4;                                         // first feature (within the tile) of this lane's chunk
+    const bool has_chunk = f0 + fb < P.ldx;
+    const int r0 = fb % S;
+    const bool vec_out = (F & 3) == 0;                              // rows of the float output are 16-byte aligned
     const uint8_t *src0 = st.src[0], *src1 = st.src[1];
     float *out = A.out + (size_t)s_idx * N * F;
     double *opart = A.obj_part + ((size_t)s_idx * pl.n_ftiles + tile) * N;
@@ -739,7 +746,7 @@ SB_DEV void ev_obs_body(const SbObsArgs &A) {
 #endif
         for (int u = 0; u < UC; u++) { gb[u] = -1; gr[u] = 0; }
         double acc = 0.0;
-        if (live) {
+        if (live && has_chunk) {
             const int k = st.cluster_of[o];
             if (k >= 0) { gb[0] = k * gs; gr[0] = k * rs; }
             int pat;
@@ -761,42 +768,59 @@ SB_DEV void ev_obs_body(const SbObsArgs &A) {
                 pat = sb_ldg(P.combo_pat + combo);
             }
             const double *wrow = wt + (size_t)(pat * 2 + (k >= 0 ? 1 : 0)) * hs;
-            const size_t off = (size_t)o * P.ldx + f0;
-            const uint8_t *xr = P.x + off, *sr = (st.osel[o] ? src1 : src0) + off;
-            float *orow = out + (size_t)o * F + f0;
-            int xs[4], cs[4];
+            const size_t off = (size_t)o * P.ldx + f0 + fb;
+            const sb_u4 xv = ev_load16(P.x + off), sv = ev_load16((st.osel[o] ? src1 : src0) + off);
+            const uint32_t xw4[4] = {xv.x, xv.y, xv.z, xv.w}, sw4[4] = {sv.x, sv.y, sv.z, sv.w};
+            float *orow = out + (size_t)o * F + f0 + fb;
+            int r = r0;                                              // (fb + i) mod S
 #ifndef SB_HOSTSIM
 #pragma unroll
 #endif
-            for (int j = 0; j < 4; j++) { const int fl = fg + j * lpr; xs[j] = fl < fv ? (int)sb_ldg(xr + fl) : SB_NA_U8; cs[j] = fl < fv ? (int)sr[fl] : SB_NA_U8; }
-            double prod = 1.0;
+            for (int half = 0; half < 2; half++) {
+                double prod = 1.0;
 #ifndef SB_HOSTSIM
 #pragma unroll
 #endif
-            for (int j = 0; j < 4; j++) {
-                const int fl = fg + j * lpr;
-                if (fl >= fv) continue;
-                const int x = xs[j];
-                double lh = 1.0;
-                if (x != SB_NA_U8) {
-                    lh = 0.0;
-                    int xr_ = x + rot[j]; xr_ = xr_ >= S ? xr_ - S : xr_;       // (x + fl) mod S
+                for (int w2 = 0; w2 < 2; w2++) {
+                    const int wi = 2 * half + w2;
+                    float o4[4];
 #ifndef SB_HOSTSIM
 #pragma unroll
 #endif
-                    for (int u = 0; u < UC; u++) {
-                        if (u < C && gb[u] >= 0) {
-                            const bool d = cs[j] == u;
-                            const double n = num[gb[u] + fl * S + xr_] - (d ? 1.0 : 0.0);
-                            const double r = d ? rd1[gr[u] + fl] : rd0[gr[u] + fl];
-                            lh += wrow[fl * Cp + u] * (n * r);
+                    for (int j = 0; j < 4; j++) {
+                        const int fl = fb + 4 * wi + j;
+                        const int x = (int)((xw4[wi] >> (8 * j)) & 255u), cj = (int)((sw4[wi] >> (8 * j)) & 255u);
+                        double lh = 1.0;
+                        if (x != SB_NA_U8) {
+                            lh = 0.0;
+                            int xr_ = x + r; xr_ = xr_ >= S ? xr_ - S : xr_;       // (x + fl) mod S
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+                            for (int u = 0; u < UC; u++) {
+                                if (u < C && gb[u] >= 0) {
+                                    const bool d = cj == u;
+                                    const double n = num[gb[u] + fl * S + xr_] - (d ? 1.0 : 0.0);
+                                    const double rr = d ? rd1[gr[u] + fl] : rd0[gr[u] + fl];
+                                    lh += wrow[fl * Cp + u] * (n * rr);
+                                }
+                            }
                         }
+                        o4[j] = (float)lh;
+                        if (fl < fv) prod *= lh;                     // (padding bytes are missing values: lh = 1)
+                        r = r + 1 == S ? 0 : r + 1;
+                    }
+                    const int flw = fb + 4 * wi;
+                    if (vec_out && flw + 3 < fv) ev_store_f32x4(orow + 4 * wi, o4[0], o4[1], o4[2], o4[3]);
+                    else {
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+                        for (int j = 0; j < 4; j++) if (flw + j < fv) orow[4 * wi + j] = o4[j];
                     }
                 }
-                orow[fl] = (float)lh;
-                prod *= lh;
+                acc += log(prod);
             }
-            acc = log(prod);
         }
         // sum over the lanes of the row (segments of lpr lanes, lpr a power of two)
         for (int d = lpr >> 1; d > 0; d >>= 1) acc += sb_shfl_f64(acc, sb_lane() ^ d);
@@ -920,15 +944,14 @@ SB_DEV void ev_gibbs_body(const SbGibbsArgs &A) {
     }
     sb_cta_sync();
     const int lo = oblk * pl.rows_per_blk, hi = lo + pl.rows_per_blk < N ? lo + pl.rows_per_blk : N;
-    // a row of the tile is shared by ft/4 lanes; a lane takes two pairs of ADJACENT features (2 fg, 2 fg + 1) and
-    // (ft/2 + 2 fg, ft/2 + 2 fg + 1): one Philox call serves a pair (words 0,1 -> even feature, words 2,3 -> odd)
-    const int lpr = ft >> 2, rpw = 32 / lpr;
+    // a lane takes one 16-byte chunk of a row (16 features of one object; see ev_obs_body): the per-object set-up is paid
+    // once per 16 observations, states / old sources arrive in two 16-byte loads, the new sources leave in one 16-byte
+    // store; one Philox call serves a PAIR of adjacent features (words 0,1 -> even feature, words 2,3 -> odd)
+    const int lpr = ft >> 4, rpw = 32 / lpr;
     const int fg = sb_lane() % lpr, rw = sb_lane() / lpr;
-    int fls[4], rot[4];
-#ifndef SB_HOSTSIM
-#pragma unroll
-#endif
-    for (int j = 0; j < 4; j++) { fls[j] = (j >> 1) * (ft >> 1) + 2 * fg + (j & 1); rot[j] = fls[j] % S; }
+    const int fb = fg << 4;
+    const bool has_chunk = f0 + fb < P.ldx;
+    const int r0 = fb % S;
     const int hF = (F + 1) >> 1;                                     // Philox calls per row
     uint8_t *src0 = st.src[0], *src1 = st.src[1];
     double *opart = A.obj_part + ((size_t)s_idx * pl.n_ftiles + tile) * N;
@@ -944,7 +967,7 @@ SB_DEV void ev_gibbs_body(const SbGibbsArgs &A) {
 #endif
         for (int u = 0; u < UC; u++) gb[u] = -1;
         double acc = 0.0;
-        if (live) {
+        if (live && has_chunk) {
             const int k = st.cluster_of[o];
             if (k >= 0) gb[0] = k * gs;
             int pat;
@@ -966,63 +989,84 @@ SB_DEV void ev_gibbs_body(const SbGibbsArgs &A) {
                 pat = sb_ldg(P.combo_pat + combo);
             }
             const double *wrow = wt + (size_t)(pat * 2 + (k >= 0 ? 1 : 0)) * hs;
-            const size_t off = (size_t)o * P.ldx + f0;
+            const size_t off = (size_t)o * P.ldx + f0 + fb;
             const int sel = st.osel[o];
-            const uint8_t *xr = P.x + off, *sr = (sel ? src1 : src0) + off;
             uint8_t *so = (sel ? src0 : src1) + off;
-            double prod = 1.0;
-            sbp::Philox4 ph; ph.w[0] = ph.w[1] = ph.w[2] = ph.w[3] = 0;
+            const sb_u4 xv = ev_load16(P.x + off), sv = ev_load16((sel ? src1 : src0) + off);
+            sb_u4 ov = sv;                                           // (padding bytes keep what the committed copy holds)
+            if (A.mode == 1) ov = ev_load16(so);
+            const uint32_t xw4[4] = {xv.x, xv.y, xv.z, xv.w}, sw4[4] = {sv.x, sv.y, sv.z, sv.w};
+            uint32_t ow4[4] = {ov.x, ov.y, ov.z, ov.w};
+            int r = r0;                                              // (fb + i) mod S
 #ifndef SB_HOSTSIM
 #pragma unroll
 #endif
-            for (int j = 0; j < 4; j++) {
-                const int fl = fls[j];
-                if (A.mode == 0 && !(j & 1) && fl < fv)      // the pair's draw: (chain seed, step, SITE_GIBBS, o * ceil(F/2) + f / 2)
-                    ph = sbp::philox4x32_10((uint32_t)((size_t)o * hF + ((f0 + fl) >> 1)), (uint32_t)SITE_GIBBS, st_lo, st_hi, k0, k1);
-                if (fl >= fv) continue;
-                const int x = (int)sb_ldg(xr + fl), c_old = (int)sr[fl];
-                if (x == SB_NA_U8) { if (A.mode == 0) so[fl] = SB_NA_U8; continue; }
-                int xr_ = x + rot[j]; xr_ = xr_ >= S ? xr_ - S : xr_;
-                double q[UC], tot = 0.0;
+            for (int half = 0; half < 2; half++) {
+                double prod = 1.0;
 #ifndef SB_HOSTSIM
 #pragma unroll
 #endif
-                for (int u = 0; u < UC; u++) {
-                    q[u] = 0.0;
-                    if (u < C) { const double l = gb[u] >= 0 ? lik[gb[u] + fl * S + xr_] : 0.0; q[u] = l * wrow[fl * Cp + u]; tot += q[u]; }
+                for (int w2 = 0; w2 < 2; w2++) {
+                    const int wi = 2 * half + w2;
+                    sbp::Philox4 ph; ph.w[0] = ph.w[1] = ph.w[2] = ph.w[3] = 0;
+                    uint32_t neww = ow4[wi];
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+                    for (int j = 0; j < 4; j++) {
+                        const int fl = fb + 4 * wi + j;
+                        if (A.mode == 0 && !(j & 1) && fl < fv)      // the pair's draw: (chain seed, step, SITE_GIBBS, o * ceil(F/2) + f / 2)
+                            ph = sbp::philox4x32_10((uint32_t)((size_t)o * hF + ((f0 + fl) >> 1)), (uint32_t)SITE_GIBBS, st_lo, st_hi, k0, k1);
+                        const int x = (int)((xw4[wi] >> (8 * j)) & 255u), c_old = (int)((sw4[wi] >> (8 * j)) & 255u);
+                        const int rr = r;
+                        r = r + 1 == S ? 0 : r + 1;
+                        if (fl >= fv) continue;
+                        if (x == SB_NA_U8) { neww |= 255u << (8 * j); continue; }
+                        int xr_ = x + rr; xr_ = xr_ >= S ? xr_ - S : xr_;
+                        double q[UC], tot = 0.0;
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+                        for (int u = 0; u < UC; u++) {
+                            q[u] = 0.0;
+                            if (u < C) { const double l = gb[u] >= 0 ? lik[gb[u] + fl * S + xr_] : 0.0; q[u] = l * wrow[fl * Cp + u]; tot += q[u]; }
+                        }
+                        // one division per observation: q = raw * (1 / total); the inverse-CDF test u < cum / last is taken
+                        // as u * last < cum (the same decision except within an ulp of a boundary)
+                        const double inv = 1.0 / tot;
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+                        for (int u = 0; u < UC; u++) if (u < C) q[u] *= inv;
+                        int pick;
+                        if (A.mode == 0) {
+                            const double uu = (j & 1) ? sbp::u01_double(ph.w[2], ph.w[3]) : sbp::u01_double(ph.w[0], ph.w[1]);
+                            double last = 0.0, cum = 0.0;
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+                            for (int u = 0; u < UC; u++) if (u < C) last += q[u];
+                            const double ul = uu * last;
+                            pick = 0; bool got = false;
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+                            for (int u = 0; u < UC; u++) if (u < C) { cum += q[u]; if (!got && ul < cum) { pick = u; got = true; } }
+                            neww = (neww & ~(255u << (8 * j))) | ((uint32_t)pick << (8 * j));
+                            changed += pick != c_old ? 1u : 0u;
+                        } else pick = A.mode == 1 ? (int)((ow4[wi] >> (8 * j)) & 255u) : c_old;
+                        double qp = 0.0;
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+                        for (int u = 0; u < UC; u++) if (u == pick) qp = q[u];
+                        prod *= qp;
+                    }
+                    ow4[wi] = neww;
                 }
-                // one division per observation: q = raw * (1 / total); the inverse-CDF test u < cum / last is taken
-                // as u * last < cum (the same decision except within an ulp of a boundary)
-                const double inv = 1.0 / tot;
-#ifndef SB_HOSTSIM
-#pragma unroll
-#endif
-                for (int u = 0; u < UC; u++) if (u < C) q[u] *= inv;
-                int pick;
-                if (A.mode == 0) {
-                    const double uu = (j & 1) ? sbp::u01_double(ph.w[2], ph.w[3]) : sbp::u01_double(ph.w[0], ph.w[1]);
-                    double last = 0.0, cum = 0.0;
-#ifndef SB_HOSTSIM
-#pragma unroll
-#endif
-                    for (int u = 0; u < UC; u++) if (u < C) last += q[u];
-                    const double ul = uu * last;
-                    pick = 0; bool got = false;
-#ifndef SB_HOSTSIM
-#pragma unroll
-#endif
-                    for (int u = 0; u < UC; u++) if (u < C) { cum += q[u]; if (!got && ul < cum) { pick = u; got = true; } }
-                    so[fl] = (uint8_t)pick;
-                    changed += pick != c_old ? 1u : 0u;
-                } else pick = A.mode == 1 ? (int)so[fl] : c_old;
-                double qp = 0.0;
-#ifndef SB_HOSTSIM
-#pragma unroll
-#endif
-                for (int u = 0; u < UC; u++) if (u == pick) qp = q[u];
-                prod *= qp;
+                acc += log(prod);
             }
-            acc = log(prod);
+            if (A.mode == 0) { sb_u4 nv; nv.x = ow4[0]; nv.y = ow4[1]; nv.z = ow4[2]; nv.w = ow4[3]; ev_store16(so, nv); }
         }
         for (int d = lpr >> 1; d > 0; d >>= 1) acc += sb_shfl_f64(acc, sb_lane() ^ d);
         if (live && fg == 0) opart[o] = acc;

@@ -67,6 +67,13 @@ def main():
                 print(f"[{name}] obs_loglik: {t*1e3:.1f} us  ({6*prob.N*prob.F*w['chains']/t/1e6:.1f} GB/s algorithmic at 6 B/obs, {prob.N*prob.F*w['chains']/t/1e6:.1f} G obs/s)", flush=True)
             except Exception as e:
                 print(f"[{name}] obs_loglik failed: {e}", flush=True)
+            try:
+                ctx.gibbs_sweep(seed=1)
+                tms = [ctx.gibbs_sweep(seed=2 + i) for i in range(6)]
+                t = min(tms)
+                print(f"[{name}] gibbs_sweep: {t*1e3:.1f} us  ({3*prob.N*prob.F*w['chains']/t/1e6:.1f} GB/s algorithmic at 3 B/obs)", flush=True)
+            except Exception as e:
+                print(f"[{name}] gibbs_sweep failed: {e}", flush=True)
             if "--no-steps" in sys.argv: ctx.close(); continue
             ctx.run(10)
             torch.cuda.synchronize(); t = time.perf_counter()
