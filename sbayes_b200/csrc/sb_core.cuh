@@ -397,6 +397,22 @@ SB_DEV void block_sum(Run &R, double (&v)[K]) {
     }
 }
 
+// Large teams (objects sharded over GPUs: more than a thousand slots): if every warp walked all slots of the reduction
+// buffer, 148 CTAs x 16 warps would read it from L2 for each reduction (tens of MB and a dependent chain of L2 round trips
+// per step); above this team size the warps of a CTA split the slots and combine their partials through shared memory.
+// The combination order depends only on the team size and the CTA size, so the bits are the same in every CTA and in
+// a single-GPU run with the same team.
+#ifdef SB_HOSTSIM
+SB_DEV int split_min() { const char *e = getenv("SB_HOSTSIM_SPLIT_MIN"); return e ? atoi(e) : 64; }
+#else
+SB_DEV int split_min() { return 64; }
+#endif
+SB_DEV void split_range(const Run &R, int &r_lo, int &r_hi, int &per) {
+    per = (R.tsize + sb_nwarps() - 1) / sb_nwarps();
+    r_lo = sb_warp() * per; if (r_lo > R.tsize) r_lo = R.tsize;
+    r_hi = r_lo + per; if (r_hi > R.tsize) r_hi = R.tsize;
+}
+
 // team-wide sum (one team barrier); result identical in every thread of the team.
 template <int K, bool PROD = false>
 SB_DEV void team_sum(Run &R, double (&v)[K]) {
@@ -406,6 +422,17 @@ SB_DEV void team_sum(Run &R, double (&v)[K]) {
     if (sb_tid() == 0) tred_put(R, R.par, v, K);
     R.par ^= 1;
     team_sync(R);
+    if (R.tsize > split_min()) {
+        int r_lo, r_hi, per; split_range(R, r_lo, r_hi, per);
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            double t = PROD ? 1.0 : 0.0;
+            for (int r = r_lo + sb_lane(); r < r_hi; r += 32) { if (PROD) t *= buf[r * SB_REDW + k]; else t += buf[r * SB_REDW + k]; }
+            v[k] = t;
+        }
+        block_sum<K, PROD>(R, v);
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < K; k++) {
         double t = PROD ? 1.0 : 0.0;
@@ -441,21 +468,49 @@ SB_DEV int team_pick(Run &R, const double *val, int n, double u, double &total, 
         if (tid == 0) tred_put(R, R.par, s, 3);
         R.par ^= 1;
         team_sync(R);
-        // every warp on its own, lanes over the team's slots (a team can have more than a thousand CTAs when the
-        // objects are sharded over GPUs): totals by lane-strided sums + butterfly, the block that holds the target by a
-        // chunked warp scan -- the same result in every warp of every CTA
         const int lane = sb_lane();
-        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-        for (int r = lane; r < R.tsize; r += 32) { t0 += buf[r * SB_REDW]; t1 += buf[r * SB_REDW + 1]; t2 += buf[r * SB_REDW + 2]; }
-        total = warp_sum(t0);
-        const double e0 = warp_sum(t1), e1 = warp_sum(t2);
-        if (extra) { extra[0] = e0; extra[1] = e1; }
-        if (!(total > 0.0)) return -1;
-        const double target = u * total;
-        rb = -1; double prefix = 0.0, carry = 0.0;
-        for (int r0 = 0; r0 < R.tsize; r0 += 32) {
+        int s_lo = 0, s_hi = R.tsize;                 // slots scanned for the block that holds the target
+        double carry = 0.0, target;
+        if (R.tsize > split_min()) {
+            // the warps split the slots: range totals through shared memory, totals and the range that holds the target
+            // from them in every thread, then every warp scans that one range
+            int r_lo, r_hi, per; split_range(R, r_lo, r_hi, per);
+            double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+            for (int r = r_lo + lane; r < r_hi; r += 32) { t0 += buf[r * SB_REDW]; t1 += buf[r * SB_REDW + 1]; t2 += buf[r * SB_REDW + 2]; }
+            t0 = warp_sum(t0); t1 = warp_sum(t1); t2 = warp_sum(t2);
+            double *wt = R.c->sred + R.spar * (32 * SB_REDW);
+            R.spar ^= 1;
+            if (lane == 0) { wt[sb_warp() * SB_REDW] = t0; wt[sb_warp() * SB_REDW + 1] = t1; wt[sb_warp() * SB_REDW + 2] = t2; }
+            sb_cta_sync();
+            const int nw = sb_nwarps();
+            total = 0.0; double e0 = 0.0, e1 = 0.0;
+            for (int v = 0; v < nw; v++) { total += wt[v * SB_REDW]; e0 += wt[v * SB_REDW + 1]; e1 += wt[v * SB_REDW + 2]; }
+            if (extra) { extra[0] = e0; extra[1] = e1; }
+            if (!(total > 0.0)) return -1;
+            target = u * total;
+            int vs = -1; double acc = 0.0;
+            for (int v = 0; v < nw; v++) {
+                const double sv = wt[v * SB_REDW];
+                if (sv > 0.0) { vs = v; carry = acc; if (acc + sv > target) break; }
+                acc += sv;
+            }
+            if (vs < 0) vs = 0;
+            s_lo = vs * per; s_hi = s_lo + per < R.tsize ? s_lo + per : R.tsize;
+        } else {
+            // every warp on its own, lanes over the team's slots: totals by lane-strided sums + butterfly
+            double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+            for (int r = lane; r < R.tsize; r += 32) { t0 += buf[r * SB_REDW]; t1 += buf[r * SB_REDW + 1]; t2 += buf[r * SB_REDW + 2]; }
+            total = warp_sum(t0);
+            const double e0 = warp_sum(t1), e1 = warp_sum(t2);
+            if (extra) { extra[0] = e0; extra[1] = e1; }
+            if (!(total > 0.0)) return -1;
+            target = u * total;
+        }
+        // the block that holds the target by a chunked warp scan -- the same result in every warp of every CTA
+        rb = -1; double prefix = 0.0;
+        for (int r0 = s_lo; r0 < s_hi; r0 += 32) {
             const int r = r0 + lane;
-            const double sr = r < R.tsize ? buf[r * SB_REDW] : 0.0;
+            const double sr = r < s_hi ? buf[r * SB_REDW] : 0.0;
             double incl = sr;
             for (int off = 1; off < 32; off <<= 1) { const double t = sb_shfl_f64(incl, lane - off); if (lane >= off) incl += t; }
             const double excl = carry + (incl - sr);
@@ -529,7 +584,13 @@ SB_DEV int team_compact(Run &R, int n, int32_t *list, Pred pred) {
     R.par ^= 1;
     team_sync(R);
     int base = 0, total = 0;
-    {
+    if (R.tsize > split_min()) {
+        int r_lo, r_hi, per; split_range(R, r_lo, r_hi, per);
+        double bt[2] = {0.0, 0.0};      // (integers: exact in any order)
+        for (int r = r_lo + sb_lane(); r < r_hi; r += 32) { const double v = buf[r * SB_REDW]; if (r < R.rank) bt[0] += v; bt[1] += v; }
+        block_sum<2>(R, bt);
+        base = (int)bt[0]; total = (int)bt[1];
+    } else {
         double tb = 0.0, tt = 0.0;      // (integers: exact in any order)
         for (int r = sb_lane(); r < R.tsize; r += 32) { const double v = buf[r * SB_REDW]; if (r < R.rank) tb += v; tt += v; }
         base = (int)warp_sum(tb); total = (int)warp_sum(tt);

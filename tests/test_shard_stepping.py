@@ -87,6 +87,18 @@ def test_emulated_sharded_chain(lib, env, world, team_local, tiled):
     sharded_vs_single(prob, st0, cfgs, 45, world, team_local, lib=lib)
 
 
+@pytest.mark.parametrize("world,team_local,block", [(2, 3, 64), (3, 2, 96)])
+def test_emulated_sharded_chain_split_reductions(lib, env, world, team_local, block):
+    """the reduction path of large teams (the warps of a CTA split the team's slots), forced at a small team size"""
+    env["SB_HOSTSIM_BLOCK"] = str(block)
+    env["SB_HOSTSIM_SPLIT_MIN"] = "1"
+    env["SB_HOSTSIM_SMEM"] = str(16 * 1024)
+    prob, _ = synth.make_problem(N=90, F=18, S=4, K=3, n_fam=4, seed=31, max_size=35, jagged_states=True)
+    cfgs = [ChainConfig(seed=910), _ClusterHeavy(temperature=1.2, prior_temperature=1.1, seed=911)]
+    st0 = [synth.initial_state(prob, seed=45 + i, objects_per_cluster=7) for i in range(2)]
+    sharded_vs_single(prob, st0, cfgs, 40, world, team_local, lib=lib)
+
+
 @pytest.mark.gpu
 def test_gpu_sharded_chain_single_process():
     """all GPUs of the box driven by one process (peer access); skipped on a one-GPU box"""
