@@ -77,7 +77,8 @@ def main():
     prob, _ = synth.make_problem(N=3000, F=150, S=6, K=6, n_fam=12, seed=5)
     cfgs = [ChainConfig(seed=910), ChainConfig(temperature=1.2, prior_temperature=1.1, seed=911)]
     st0 = [synth.initial_state(prob, seed=45 + c) for c in range(2)]
-    team_local, n_steps = 8, 60
+    # (at eight ranks the team has 80 CTAs: above the size where the warps of a CTA split the reduction slots)
+    team_local, n_steps = (8 if world < 8 else 10), 60
     sc = ShardedChains(prob, 2, rank=rank, world=world, device=local, team=team_local)
     for ch in range(2):
         sc.configure(ch, cfgs[ch])
