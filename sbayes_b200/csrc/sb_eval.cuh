@@ -236,32 +236,42 @@ SB_DEV void ev_hist_fast(const SbEvalArgs &A) {
     const int cpr = ftw >> 4;
     const ev_bins_t bins = ev_bins(cnt);
     const uint8_t *src0 = st.src[0], *src1 = st.src[1];
-    for (int o0 = lo + sb_warp() * 32; o0 < hi; o0 += sb_nwarps() * 32) {
-        const int o = o0 + sb_lane();
-        const bool live = o < hi;
-        uint32_t gw = 0xFFFFFFFFu;
-        int hb = 0;
-        const uint8_t *xr = P.x, *sr = src0;
-        if (live) {
-            const int k = st.cluster_of[o];
-            const uint32_t pk = sb_ldg(P.obj_pack + o);          // independent of the other loads
-            gw = (uint32_t)(k >= 0 ? k : 255) | (pk & 0xFFFFFF00u);
-            hb = n_cnt + ((int)(pk & 255u) * 2 + (k >= 0 ? 1 : 0)) * hs;
-            const size_t off = (size_t)o * P.ldx + f0;
-            xr = P.x + off; sr = (st.osel[o] ? src1 : src0) + off;
-            if (tile == 0 && k >= 0) sb_atomic_add_i32(sz + k, 1);
-        }
-        sb_u4 xv, sv, xn, sn;
-        xn.x = xn.y = xn.z = xn.w = 0xFFFFFFFFu; sn = xn;
-        if (live) { xn = ev_load16(xr); sn = ev_load16(sr); }
-        for (int ch = 0; ch < cpr; ch++) {
-            xv = xn; sv = sn;
-            if (live && ch + 1 < cpr) { xn = ev_load16(xr + (ch + 1) * 16); sn = ev_load16(sr + (ch + 1) * 16); }
-            const int fl = ch << 4;
-            ev_fast_word(bins, xv.x, sv.x, C, S, gs, fl, gw, hb, trash);
-            ev_fast_word(bins, xv.y, sv.y, C, S, gs, fl + 4, gw, hb, trash);
-            ev_fast_word(bins, xv.z, sv.z, C, S, gs, fl + 8, gw, hb, trash);
-            ev_fast_word(bins, xv.w, sv.w, C, S, gs, fl + 12, gw, hb, trash);
+    // software pipeline over the warp's trips (see ev_hist_fine): per-object words of trip t + 2 and the first chunks of
+    // trip t + 1 are in flight while trip t is counted
+    const int stride = sb_nwarps() * 32;
+    const int o_first = lo + sb_warp() * 32 + sb_lane(), o_last = hi - 1;
+    auto clampo = [&](int o) { return o < hi ? o : o_last; };
+    if (lo + sb_warp() * 32 < hi) {
+        int kA, kB; uint32_t pkA, pkB; uint8_t selA, selB;
+        { const int o = clampo(o_first); kA = st.cluster_of[o]; pkA = sb_ldg(P.obj_pack + o); selA = st.osel[o]; }
+        { const int o = clampo(o_first + stride); kB = st.cluster_of[o]; pkB = sb_ldg(P.obj_pack + o); selB = st.osel[o]; }
+        const uint8_t *xrA, *srA;
+        { const size_t off = (size_t)clampo(o_first) * P.ldx + f0; xrA = P.x + off; srA = (selA ? src1 : src0) + off; }
+        sb_u4 xn = ev_load16(xrA), sn = ev_load16(srA);
+        for (int o = o_first; o - sb_lane() < hi; o += stride) {
+            const uint8_t *xrB, *srB;
+            { const size_t off = (size_t)clampo(o + stride) * P.ldx + f0; xrB = P.x + off; srB = (selB ? src1 : src0) + off; }
+            const sb_u4 xB = ev_load16(xrB), sB = ev_load16(srB);
+            int kC; uint32_t pkC; uint8_t selC;
+            { const int oc = clampo(o + 2 * stride); kC = st.cluster_of[oc]; pkC = sb_ldg(P.obj_pack + oc); selC = st.osel[oc]; }
+            if (o < hi) {                                            // (no warp-wide operation below)
+                const int k = kA;
+                const uint32_t gw = (uint32_t)(k >= 0 ? k : 255) | (pkA & 0xFFFFFF00u);
+                const int hb = n_cnt + ((int)(pkA & 255u) * 2 + (k >= 0 ? 1 : 0)) * hs;
+                if (tile == 0 && k >= 0) sb_atomic_add_i32(sz + k, 1);
+                sb_u4 xv, sv;
+                for (int ch = 0; ch < cpr; ch++) {
+                    xv = xn; sv = sn;
+                    if (ch + 1 < cpr) { xn = ev_load16(xrA + (ch + 1) * 16); sn = ev_load16(srA + (ch + 1) * 16); }
+                    const int fl = ch << 4;
+                    ev_fast_word(bins, xv.x, sv.x, C, S, gs, fl, gw, hb, trash);
+                    ev_fast_word(bins, xv.y, sv.y, C, S, gs, fl + 4, gw, hb, trash);
+                    ev_fast_word(bins, xv.z, sv.z, C, S, gs, fl + 8, gw, hb, trash);
+                    ev_fast_word(bins, xv.w, sv.w, C, S, gs, fl + 12, gw, hb, trash);
+                }
+            }
+            kA = kB; pkA = pkB; xrA = xrB; srA = srB; xn = xB; sn = sB;
+            kB = kC; pkB = pkC; selB = selC;
         }
     }
     sb_cta_sync();
@@ -447,6 +457,7 @@ SB_DEV void ev_hist_fine(const SbEvalArgs &A, const SbFineArgs &FA) {
         for (int k = sb_tid(); k < K; k += sb_nthr()) { if (own) st.sizes[k] = sz[k]; else if (sz[k]) sb_atomic_add_i32(st.sizes + k, sz[k]); }
 }
 
+// (capping the kernel at 64 registers for a fourth CTA per SM measured much slower: 122 -> 208 us at config 4, profiles/r4m_scale.txt)
 template <int S1>
 SB_KERNEL sb_eval_fine_kernel(const SB_GRID_CONSTANT SbEvalArgs A, const SB_GRID_CONSTANT SbFineArgs FA) { ev_hist_fine<S1>(A, FA); }
 
