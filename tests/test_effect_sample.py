@@ -68,7 +68,7 @@ def test_effect_draws_have_dirichlet_moments():
         st = synth.initial_state(prob, seed=3, objects_per_cluster=4)
         ctx.set_state(0, st)
         conc = E.concentration(prob, M.rebuild_counts(prob, st))
-        n = 600
+        n = 400
         draws = np.stack([ctx.effect_sample([0], step=1000 + i)[0] for i in range(n)])
     finally:
         ctx.close()
