@@ -45,7 +45,7 @@ def test_effect_draws_match_oracle(backend, shape):
         for c in range(2):
             ctx.configure(c, cfgs[c])
             ctx.set_state(c, synth.initial_state(prob, seed=70 + c, objects_per_cluster=5))
-        ctx.run(150)
+        ctx.run(150 if backend == "cuda" else 60)
         for step, chains in ((7, [0, 1]), (1 << 33, [1])):
             got = ctx.effect_sample(chains, step=step)
             for i, c in enumerate(chains):

@@ -84,10 +84,10 @@ def test_emulated_sharded_chain(lib, env, world, team_local, tiled):
     prob, _ = synth.make_problem(N=90, F=18, S=4, K=3, n_fam=4, seed=29, max_size=35, jagged_states=True)
     cfgs = [ChainConfig(seed=900), _ClusterHeavy(temperature=1.2, prior_temperature=1.1, seed=901)]
     st0 = [synth.initial_state(prob, seed=35 + i, objects_per_cluster=7) for i in range(2)]
-    sharded_vs_single(prob, st0, cfgs, 45, world, team_local, lib=lib)
+    sharded_vs_single(prob, st0, cfgs, 36, world, team_local, lib=lib)
 
 
-@pytest.mark.parametrize("world,team_local,block", [(2, 3, 96)])
+@pytest.mark.parametrize("world,team_local,block", [(2, 3, 64)])
 def test_emulated_sharded_chain_split_reductions(lib, env, world, team_local, block):
     """the reduction path of large teams (the warps of a CTA split the team's slots), forced at a small team size"""
     env["SB_HOSTSIM_BLOCK"] = str(block)
@@ -96,7 +96,7 @@ def test_emulated_sharded_chain_split_reductions(lib, env, world, team_local, bl
     prob, _ = synth.make_problem(N=90, F=18, S=4, K=3, n_fam=4, seed=31, max_size=35, jagged_states=True)
     cfgs = [ChainConfig(seed=910), _ClusterHeavy(temperature=1.2, prior_temperature=1.1, seed=911)]
     st0 = [synth.initial_state(prob, seed=45 + i, objects_per_cluster=7) for i in range(2)]
-    sharded_vs_single(prob, st0, cfgs, 30, world, team_local, lib=lib)
+    sharded_vs_single(prob, st0, cfgs, 20, world, team_local, lib=lib)
 
 
 @pytest.mark.gpu
