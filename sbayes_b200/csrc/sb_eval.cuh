@@ -216,7 +216,7 @@ SB_DEV void ev_fast_word(ev_bins_t bins, uint32_t xw, uint32_t sw, int C, int S,
 SB_DEV void ev_hist_fast(const SbEvalArgs &A) {
     const SbProblem &P = A.P;
     const SbEvalPlan &pl = A.plan;
-    const int F = P.F, S = P.S, C = P.C, nconf = P.n_conf;
+    const int F = P.F, S = P.S, C = P.C;
     int w = sb_cta();
     const int oblk = w % pl.n_oblk; w /= pl.n_oblk;
     const int tile = w % pl.n_ftiles; w /= pl.n_ftiles;
