@@ -270,7 +270,9 @@ SB_API int sb_effect_sample(sb_ctx *c, int32_t n, const int32_t *chains, uint64_
     }
     if (!fs->d_eff_chains) TRY(mk(c, &fs->d_eff_chains, (size_t)c->n_chains));
     if (n > c->n_chains) return fail(c, "sb_effect_sample: more entries than chains");
-    TRY(sb_eval_stats(c, nullptr));        // the count tensors of the committed states (a state set by sb_set_state has none yet)
+    // the count tensors of the committed states (a state set by sb_set_state has none yet); with the objects sharded over GPUs the
+    // statistics block holds the all-reduced counts of the last launch and a local pass would replace them by this rank's share
+    if (c->xworld == 1) TRY(sb_eval_stats(c, nullptr));
     TRY(h2d(c, fs->d_eff_chains, chains, sizeof(int32_t) * n));
     SbEffectArgs A; memset(&A, 0, sizeof A);
     A.P = P; A.states = c->d_states; A.slots = c->d_slots; A.chains = fs->d_eff_chains; A.n = n; A.step = step; A.out = fs->d_eff;
