@@ -169,7 +169,8 @@ int sb_obs_loglik(sb_ctx *ctx, float *lh_out, double *obj_ll_out, double *sums_o
 int sb_gibbs_sweep(sb_ctx *ctx, uint64_t step, int mode, double *log_q_out, int64_t *n_changed_out, float *ms);
 /* EM-style cluster initializer (SbayesInitializer.generate_clusters_em, sbayes/sampling/initializers.py:93-169):
  * n_steps EM steps on the soft assignment z0 [G_tot, N] float32 (rows: clusters, then every confounder's groups);
- * z_out [G_tot, N] receives the final assignment.  Uniform geo prior only. */
+ * z_out [G_tot, N] receives the final assignment; z0 must be zero outside a confounder group's members (the reference's
+ * start is: initializers.py:108-119).  Uniform geo prior only. */
 int sb_init_em(sb_ctx *ctx, int32_t n_steps, const float *z0, float *z_out, float *ms);
 /* Which statistics pass sb_eval_stats runs and its launch geometry: out8 = {pass (0 two-increment histogram, 1 int8
  * tcgen05 contraction, 2 fine-row histogram), feature-tile width, feature tiles, object blocks, dynamic shared memory,

@@ -17,9 +17,10 @@
 // 1.6e10 against 1.3e11.  Both kernels read the packed bytes x[o, f]; accumulation is fp64 (the reference
 // is float32 with numpy's pairwise sums; parity tolerance in tests/test_init_em.py).
 //
-//   sb_em_counts_kernel   CTA = (feature tile of 32, object block, group block): the CTA stages its z rows, a warp
-//                         walks the objects of the block, lane = feature; partial counts per object block are
-//                         summed in block order by sb_em_tables_kernel (deterministic)
+//   sb_em_counts_kernel   CTA = (feature tile of 32, object block, group block of 4): lane = feature, a warp walks the objects of
+//                         the block for the dense rows (clusters, the universal group) and the member lists of the sparse
+//                         rows (z is zero outside a confounder group), eight objects in flight; partial counts per object
+//                         block are summed in block order by sb_em_tables_kernel (deterministic)
 //   sb_em_tables_kernel   sums the partials, adds the prior counts, normalises, takes the log -> logp[g, f, s] f32
 //   sb_em_assign_kernel   warp per object: ll[g] for all groups (lanes over features, shuffle reduction),
 //                         masked tempered softmax over the groups -> z[:, o]
@@ -40,14 +41,6 @@ struct SbEmArgs {
     double inv_temperature;
 };
 
-// availability of group row g for object o (clusters: every object; confounder groups: their members)
-SB_DEV bool em_available(const SbProblem &P, int g, int o) {
-    if (g < P.K) return true;
-    int c = 1;
-    while (c < P.C && g >= P.goff[c + 1]) c++;
-    return sb_ldg(P.conf_gid + (size_t)(c - 1) * P.N + o) == g - P.goff[c];
-}
-
 SB_KERNEL sb_em_counts_kernel(const SB_GRID_CONSTANT SbEmArgs A) {
     const SbProblem &P = A.P;
     const int F = P.F, S = P.S, N = P.N, G = P.G_tot;
@@ -63,10 +56,82 @@ SB_KERNEL sb_em_counts_kernel(const SB_GRID_CONSTANT SbEmArgs A) {
     double *bins = (double *)sb_smem() + (size_t)sb_warp() * SB_EM_GB * S * 32;
     for (int i = sb_lane(); i < SB_EM_GB * S * 32; i += 32) bins[i] = 0.0;
     sb_warp_sync();
-    for (int o = lo + sb_warp(); o < hi; o += sb_nwarps()) {
-        const int x = f < F ? (int)sb_ldg(P.x + (size_t)o * P.ldx + f) : SB_NA_U8;
-        if (x == SB_NA_U8) continue;
-        for (int q = 0; q < ng; q++) bins[(q * S + x) * 32 + sb_lane()] += (double)A.z[(size_t)(g0 + q) * N + o];
+    // rows of the block: cluster rows and confounder groups that hold a large share of the objects (the universal group) are
+    // DENSE -- every object of the block is visited; the other confounder groups are SPARSE -- z is zero outside the group, so
+    // only the group's member list (P.cg_ptr / P.cg_idx) is walked
+    bool dense[SB_EM_GB]; bool any_dense = false;
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+    for (int q = 0; q < SB_EM_GB; q++) {
+        const int g = g0 + q;
+        dense[q] = q < ng && (g < P.K || 4LL * (sb_ldg(P.cg_ptr + g - P.K + 1) - sb_ldg(P.cg_ptr + g - P.K)) > (long long)N);
+        any_dense = any_dense || dense[q];
+    }
+    // dense rows: a warp takes the objects lo + warp + k * n_warps, eight at a time: the z values (one broadcast load per
+    // (object, group)) and the state bytes of all eight are requested before the first add; an object whose z is zero in every
+    // dense row of the block costs no state load and no add (adding 0.0 would not change a bin)
+    constexpr int U = 8;
+    const int nwp = sb_nwarps();
+    if (any_dense)
+    for (int o0 = lo + sb_warp(); o0 < hi; o0 += nwp * U) {
+        float zz[U][SB_EM_GB]; int xx[U];
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+        for (int u = 0; u < U; u++) {
+            const int o = o0 + u * nwp;
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+            for (int q = 0; q < SB_EM_GB; q++) zz[u][q] = (o < hi && dense[q]) ? A.z[(size_t)(g0 + q) * N + o] : 0.0f;
+        }
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+        for (int u = 0; u < U; u++) {
+            const int o = o0 + u * nwp;
+            bool any = false;
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+            for (int q = 0; q < SB_EM_GB; q++) any = any || zz[u][q] != 0.0f;
+            xx[u] = (any && f < F) ? (int)sb_ldg(P.x + (size_t)o * P.ldx + f) : SB_NA_U8;
+        }
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+        for (int u = 0; u < U; u++) {
+            const int x = xx[u];
+            if (x == SB_NA_U8) continue;
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+            for (int q = 0; q < SB_EM_GB; q++) if (zz[u][q] != 0.0f) bins[(q * S + x) * 32 + sb_lane()] += (double)zz[u][q];
+        }
+    }
+    // sparse rows: the members of the group that fall into this CTA's object block, eight at a time
+    for (int q = 0; q < ng; q++) {
+        if (dense[q]) continue;
+        const int g = g0 + q;
+        const int p0 = sb_ldg(P.cg_ptr + g - P.K), p1 = sb_ldg(P.cg_ptr + g - P.K + 1);
+        for (int i0 = p0 + sb_warp(); i0 < p1; i0 += nwp * U) {
+            float zz[U]; int xx[U];
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+            for (int u = 0; u < U; u++) {
+                const int i = i0 + u * nwp;
+                const int o = i < p1 ? sb_ldg(P.cg_idx + i) : -1;
+                const bool in = o >= lo && o < hi;
+                zz[u] = in ? A.z[(size_t)g * N + o] : 0.0f;
+                xx[u] = (in && f < F) ? (int)sb_ldg(P.x + (size_t)o * P.ldx + f) : SB_NA_U8;
+            }
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+            for (int u = 0; u < U; u++) if (xx[u] != SB_NA_U8 && zz[u] != 0.0f) bins[(q * S + xx[u]) * 32 + sb_lane()] += (double)zz[u];
+        }
     }
     sb_cta_sync();
     // the warps' bins are added in warp order; thread = (group, state, feature lane)
@@ -109,28 +174,54 @@ SB_KERNEL sb_em_assign_kernel(const SB_GRID_CONSTANT SbEmArgs A) {
     const int wpb = sb_nwarps();
     for (int o = sb_cta() * wpb + sb_warp(); o < N; o += sb_ncta() * wpb) {
         const uint8_t *xr = P.x + (size_t)o * P.ldx;
-        for (int g = 0; g < G; g++) {
+        // the rows available to this object: every cluster and, per confounder, the row of its group (em_available as one
+        // look-up per confounder instead of one per (group, object))
+        int crow[8];
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+        for (int c = 1; c < 8; c++) {
+            crow[c] = -1;
+            if (c < P.C) { const int gid = sb_ldg(P.conf_gid + (size_t)(c - 1) * N + o); if (gid >= 0) crow[c] = P.goff[c] + gid; }
+        }
+        const int n_rows = P.K + P.C - 1;
+        for (int r = 0; r < n_rows; r++) {
+            int g = r;
+            if (r >= P.K) {
+                g = -1;
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+                for (int c = 1; c < 8; c++) if (c == r - P.K + 1) g = crow[c];
+                if (g < 0) continue;                                 // (warp-uniform)
+            }
             double acc = 0.0;
-            if (em_available(P, g, o)) {
-                const float *lp = A.logp + (size_t)g * F * S;
-                for (int f = sb_lane(); f < F; f += 32) {
-                    const int x = (int)sb_ldg(xr + f);
-                    if (x != SB_NA_U8) acc += (double)lp[(size_t)f * S + x];
-                }
+            const float *lp = A.logp + (size_t)g * F * S;
+            for (int f = sb_lane(); f < F; f += 32) {
+                const int x = (int)sb_ldg(xr + f);
+                if (x != SB_NA_U8) acc += (double)lp[(size_t)f * S + x];
             }
             for (int d = 16; d > 0; d >>= 1) acc += sb_shfl_f64(acc, sb_lane() ^ d);
             if (sb_lane() == 0) ll[g] = acc;
         }
         sb_warp_sync();
         // masked tempered softmax over the groups (scipy.special.softmax of lh = ll / T, -inf where unavailable)
+        auto avail = [&](int g) {
+            bool a = g < P.K;
+#ifndef SB_HOSTSIM
+#pragma unroll
+#endif
+            for (int c = 1; c < 8; c++) a = a || crow[c] == g;
+            return a;
+        };
         double mx = -1e300;
-        for (int g = sb_lane(); g < G; g += 32) if (em_available(P, g, o)) { const double v = (double)(float)((double)(float)ll[g] * A.inv_temperature); mx = v > mx ? v : mx; }
+        for (int g = sb_lane(); g < G; g += 32) if (avail(g)) { const double v = (double)(float)((double)(float)ll[g] * A.inv_temperature); mx = v > mx ? v : mx; }
         for (int d = 16; d > 0; d >>= 1) { const double t = sb_shfl_f64(mx, sb_lane() ^ d); mx = t > mx ? t : mx; }
         double sum = 0.0;
-        for (int g = sb_lane(); g < G; g += 32) if (em_available(P, g, o)) sum += exp((double)(float)((double)(float)ll[g] * A.inv_temperature) - mx);
+        for (int g = sb_lane(); g < G; g += 32) if (avail(g)) sum += exp((double)(float)((double)(float)ll[g] * A.inv_temperature) - mx);
         for (int d = 16; d > 0; d >>= 1) sum += sb_shfl_f64(sum, sb_lane() ^ d);
         for (int g = sb_lane(); g < G; g += 32)
-            A.z[(size_t)g * N + o] = em_available(P, g, o) ? (float)(exp((double)(float)((double)(float)ll[g] * A.inv_temperature) - mx) / sum) : 0.0f;
+            A.z[(size_t)g * N + o] = avail(g) ? (float)(exp((double)(float)((double)(float)ll[g] * A.inv_temperature) - mx) / sum) : 0.0f;
         sb_warp_sync();
     }
 }

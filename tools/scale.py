@@ -74,6 +74,24 @@ def main():
                 print(f"[{name}] gibbs_sweep: {t*1e3:.1f} us  ({3*prob.N*prob.F*w['chains']/t/1e6:.1f} GB/s algorithmic at 3 B/obs)", flush=True)
             except Exception as e:
                 print(f"[{name}] gibbs_sweep failed: {e}", flush=True)
+            try:      # initializer EM: device ms per EM step against the float32 numpy einsum pair of the reference on this box's CPU
+                from sbayes_b200 import initializer as INI
+                from sbayes_b200.packed import NA
+                z0 = INI.initial_soft_assignment(prob, np.random.default_rng(1))
+                ctx.init_em(z0, 2)
+                _, ms = ctx.init_em(z0, 10, timing=True)
+                line = f"[{name}] init_em: {ms/10*1e3:.1f} us per EM step on the device (G_tot={prob.G_tot}, {prob.G_tot*prob.N*prob.F/1e6:.0f} M multiply-adds per contraction)"
+                if prob.N * prob.F * prob.S <= 8e6:
+                    X = np.zeros((prob.N, prob.F, prob.S), np.float32)
+                    o, f = np.nonzero(prob.x != NA); X[o, f, prob.x[o, f]] = 1.0
+                    t0 = time.perf_counter()
+                    cnt = np.einsum("ij,jkl->ikl", z0, X, optimize=True)
+                    p = np.log(cnt / cnt.sum(axis=-1, keepdims=True).clip(1e-30) + 1e-30)
+                    ll = np.einsum("ikl,jkl->ij", p, X, optimize=True)
+                    line += f"; numpy einsum pair of the reference (float32, this box's CPU) {(time.perf_counter()-t0)*1e3:.0f} ms"
+                print(line, flush=True)
+            except Exception as e:
+                print(f"[{name}] init_em failed: {e}", flush=True)
             if "--no-steps" in sys.argv: ctx.close(); continue
             ctx.run(10)
             torch.cuda.synchronize(); t = time.perf_counter()
