@@ -697,11 +697,12 @@ static inline int sb_obs_make_plan(const SbProblem &P, int n_states, int n_sm, S
 // pointers) is paid once per 16 observations; ft/16 lanes share a row, 32 / (ft/16) rows per warp iteration.
 // (Round 1 gave a lane 4 features of a row: coalesced single-byte loads, but the set-up -- about 100 instructions --
 // was paid per 4 observations.)
-template <int UC>
+// (EXACT: the problem has exactly UC components -- the guards `u < C` of the unrolled component loops fold away)
+template <int UC, bool EXACT = false>
 SB_DEV void ev_obs_body(const SbObsArgs &A) {
     const SbProblem &P = A.P;
     const SbObsPlan &pl = A.plan;
-    const int F = P.F, S = P.S, C = P.C, nconf = P.n_conf, N = P.N;
+    const int F = P.F, S = P.S, C = EXACT ? UC : P.C, nconf = P.n_conf, N = P.N;
     int w = sb_cta();
     const int oblk = w % pl.n_oblk; w /= pl.n_oblk;
     const int tile = w % pl.n_ftiles; w /= pl.n_ftiles;
@@ -767,7 +768,7 @@ SB_DEV void ev_obs_body(const SbObsArgs &A) {
 #ifndef SB_HOSTSIM
 #pragma unroll
 #endif
-                for (int u = 1; u < 4; u++) { const int g = (int)((pk >> (8 * u)) & 255u); if (g != 255) { gb[u] = g * gs; gr[u] = g * rs; } }
+                for (int u = 1; u < 4 && u < UC; u++) { const int g = (int)((pk >> (8 * u)) & 255u); if (g != 255) { gb[u] = g * gs; gr[u] = g * rs; } }
             } else {
                 const int combo = sb_ldg(P.combo_id + o);
                 const int32_t *rows = P.combo_rows + (size_t)combo * nconf;
@@ -840,7 +841,7 @@ SB_DEV void ev_obs_body(const SbObsArgs &A) {
 }
 
 SB_KERNEL sb_obs_lik_kernel(const SB_GRID_CONSTANT SbObsArgs A) {
-    if (A.P.C <= 4) ev_obs_body<4>(A); else ev_obs_body<8>(A);
+    if (A.P.C == 3) ev_obs_body<3, true>(A); else if (A.P.C <= 4) ev_obs_body<4>(A); else ev_obs_body<8>(A);
 }
 
 // obj_ll[state][o] = sum over tiles (tile order); sums[state] = sum over objects.  CTA =
@@ -906,19 +907,26 @@ struct SbGibbsArgs {
     int mode;
 };
 
-template <int UC>
+template <int UC, bool EXACT = false>
 SB_DEV void ev_gibbs_body(const SbGibbsArgs &A) {
     const SbProblem &P = A.P;
     const SbObsPlan &pl = A.plan;
-    const int F = P.F, S = P.S, C = P.C, nconf = P.n_conf, N = P.N;
+    const int F = P.F, S = P.S, C = EXACT ? UC : P.C, nconf = P.n_conf, N = P.N;
     int w = sb_cta();
     const int oblk = w % pl.n_oblk; w /= pl.n_oblk;
     const int tile = w % pl.n_ftiles; w /= pl.n_ftiles;
     const int s_idx = w;
     const SbShared st = A.states[s_idx];
-    double T = 1.0, Tp = 1.0; int sfp = 0; unsigned long long seed = 0;
-    for (int i = 0; i < A.n_states; i++)
-        if (A.slots[i].state == s_idx) { T = A.slots[i].cfg.temperature; Tp = A.slots[i].cfg.prior_temperature; sfp = A.slots[i].cfg.sample_from_prior; seed = A.slots[i].cfg.seed; }
+    // the slot (temperatures, Philox key) that currently holds this state: the threads search the slots in parallel
+    int *slot_of = (int *)sb_smem();
+    if (sb_tid() == 0) *slot_of = 0;
+    sb_cta_sync();
+    for (int i = sb_tid(); i < A.n_states; i += sb_nthr()) if (A.slots[i].state == s_idx) *slot_of = i;
+    sb_cta_sync();
+    const SbSlot sl = A.slots[*slot_of];
+    sb_cta_sync();                                                  // (the tables below reuse the word)
+    const double T = sl.cfg.temperature, Tp = sl.cfg.prior_temperature;
+    const int sfp = sl.cfg.sample_from_prior; const unsigned long long seed = sl.cfg.seed;
     const double invT = 1.0 / T, invTp = 1.0 / Tp;
     const bool unitT = T == 1.0, unitTp = Tp == 1.0;
     const int ft = pl.ft;
@@ -988,7 +996,7 @@ SB_DEV void ev_gibbs_body(const SbGibbsArgs &A) {
 #ifndef SB_HOSTSIM
 #pragma unroll
 #endif
-                for (int u = 1; u < 4; u++) { const int g = (int)((pk >> (8 * u)) & 255u); if (g != 255) gb[u] = g * gs; }
+                for (int u = 1; u < 4 && u < UC; u++) { const int g = (int)((pk >> (8 * u)) & 255u); if (g != 255) gb[u] = g * gs; }
             } else {
                 const int combo = sb_ldg(P.combo_id + o);
                 const int32_t *rows = P.combo_rows + (size_t)combo * nconf;
@@ -1089,7 +1097,7 @@ SB_DEV void ev_gibbs_body(const SbGibbsArgs &A) {
 }
 
 SB_KERNEL sb_gibbs_sweep_kernel(const SB_GRID_CONSTANT SbGibbsArgs A) {
-    if (A.P.C <= 4) ev_gibbs_body<4>(A); else ev_gibbs_body<8>(A);
+    if (A.P.C == 3) ev_gibbs_body<3, true>(A); else if (A.P.C <= 4) ev_gibbs_body<4>(A); else ev_gibbs_body<8>(A);
 }
 
 // commits the rows a draw wrote: osel[o] ^= 1 for every object of every state
