@@ -21,6 +21,7 @@ COMMON = ["sb_platform.cuh", "sb_types.h", "sb_plans.h", "sb_philox.cuh"]
 UNITS = {
     "sb_api.cu": COMMON + ["sb_ctx.h", "sb_core.cuh"],                     # the 4-component step kernel + the C ABI
     "sb_uc8.cu": COMMON + ["sb_core.cuh"],                                  # the 8-component step kernel
+    "sb_uc3.cu": COMMON + ["sb_core.cuh"],                                  # the step kernel for exactly 3 components
     "sb_api_eval.cu": COMMON + ["sb_ctx.h", "sb_eval.cuh", "sb_counts.cuh", "sb_init.cuh"],   # the streaming kernels
 }
 

@@ -15,6 +15,15 @@
 const void *sb_uc8_run_kernel_ptr();
 void sb_uc8_run_kernel_host(const SbLaunch &L);        // emulator builds: the kernel body as a host function
 long sb_uc8_tiled_calls(int kind);
+// (and the one for exactly 3 components, sb_uc3.cu: what every BASELINE configuration runs)
+const void *sb_uc3_run_kernel_ptr();
+void sb_uc3_run_kernel_host(const SbLaunch &L);
+long sb_uc3_tiled_calls(int kind);
+#if defined(SB_PHASE_PROF) || defined(SB_NO_UC3)
+static inline bool use_uc3(int) { return false; }      // (the phase counters live in the 4-component instantiation)
+#else
+static inline bool use_uc3(int C) { return C == 3; }
+#endif
 using uc4::FixedSmem; using uc4::sb_fixed_smem; using uc4::Draws; using uc4::Philox4; using uc4::philox4x32_10; using uc4::u01_double;
 using uc4::sb_export_kernel; using uc4::sb_export_samples_kernel;
 
@@ -326,7 +335,7 @@ static int create_impl(sb_ctx *c, const sb_problem_desc *d, int device, int n_ch
     int capacity = 64;
 #else
     c->block = SB_BLOCK;
-    c->kernel = C <= 4 ? (const void *)uc4::sb_run_kernel : sb_uc8_run_kernel_ptr();
+    c->kernel = use_uc3(C) ? sb_uc3_run_kernel_ptr() : (C <= 4 ? (const void *)uc4::sb_run_kernel : sb_uc8_run_kernel_ptr());
     CK(cudaFuncSetAttribute(c->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
     CK(cudaFuncSetAttribute(c->kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     int per_sm = 0;
@@ -525,7 +534,8 @@ static int launch(sb_ctx *c, long long n_steps, const sb_tape *tape_dev, sb_step
     TRY(prepare_launch(c, n_steps, tape_dev, rec_dev, &L));
 #ifdef SB_HOSTSIM
     if (c->xworld > 1) return fail(c, "emulator: chains sharded over ranks are launched together (sb_run_group)");
-    if (c->P.C <= 4) hostsim::launch([&]() { uc4::sb_run_kernel(L); }, c->grid, c->block, c->smem);
+    if (use_uc3(c->P.C)) hostsim::launch([&]() { sb_uc3_run_kernel_host(L); }, c->grid, c->block, c->smem);
+    else if (c->P.C <= 4) hostsim::launch([&]() { uc4::sb_run_kernel(L); }, c->grid, c->block, c->smem);
     else hostsim::launch([&]() { sb_uc8_run_kernel_host(L); }, c->grid, c->block, c->smem);
 #else
     if (c->use_cluster && c->xworld == 1) {
@@ -650,7 +660,7 @@ SB_API int sb_run_group(sb_ctx **ctxs, int n, int64_t n_steps, sb_step_record *r
             const int cta = hostsim::cta();
             int i = 0;
             while (i + 1 < n && cta >= L[i + 1].cta_base) i++;
-            if (ctxs[i]->P.C <= 4) uc4::sb_run_kernel(L[i]); else sb_uc8_run_kernel_host(L[i]);
+            if (use_uc3(ctxs[i]->P.C)) sb_uc3_run_kernel_host(L[i]); else if (ctxs[i]->P.C <= 4) uc4::sb_run_kernel(L[i]); else sb_uc8_run_kernel_host(L[i]);
         }, total, c0->block, smem);
     }
 #else
@@ -1003,7 +1013,7 @@ SB_API int64_t sb_clock_khz(const sb_ctx *c) { return c ? (int64_t)c->clock_khz 
 
 #ifdef SB_HOSTSIM
 // emulator builds only (not part of the ABI): calls of the tiled passes per kind {alter, wide, jump, alter on feature pairs}
-SB_API long sb_hostsim_tiled_calls(int kind) { return kind >= 0 && kind < 4 ? uc4::g_tiled_calls[kind] + sb_uc8_tiled_calls(kind) : -1; }
+SB_API long sb_hostsim_tiled_calls(int kind) { return kind >= 0 && kind < 4 ? uc4::g_tiled_calls[kind] + sb_uc8_tiled_calls(kind) + sb_uc3_tiled_calls(kind) : -1; }
 #endif
 
 #if defined(SB_PHASE_PROF) && !defined(SB_HOSTSIM)

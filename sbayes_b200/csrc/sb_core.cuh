@@ -32,7 +32,7 @@
 // What follows which reference code is cited function by function; the algorithmic
 // specification is SURVEY.md Appendix A, the executable one is oracle/operators.py.
 // This file is compiled once per unroll width of the mixture-component loops: the includer
-// defines SB_UC (4 or 8: the largest number of components the instantiation handles) and
+// defines SB_UC (3, 4 or 8: the largest number of components the instantiation handles; with SB_EXACT_C the exact number) and
 // SB_NS (the namespace the instantiation lives in); see sb_api.cu.
 #include "sb_platform.cuh"
 #include "sb_types.h"
@@ -44,6 +44,15 @@ namespace SB_NS {
 
 #undef SB_FOR_C
 #undef SB_FOR_C1
+#undef SB_CC
+// number of mixture components: a compile-time constant in an instantiation that serves problems with EXACTLY SB_UC components
+// (SB_EXACT_C; sb_uc3.cu: cluster + universal + one more confounder, every BASELINE configuration) -- the guards of the
+// unrolled component loops then fold away -- and the problem's own number otherwise
+#ifdef SB_EXACT_C
+#define SB_CC(P) SB_UC
+#else
+#define SB_CC(P) ((P).C)
+#endif
 #undef PH
 #undef SB_NPH
 #ifndef SB_EPS32
@@ -802,7 +811,7 @@ SB_DEV double ll_total(const Run &R) {          // every warp on its own; identi
 //   lw = log w1                             SourcePrior         (sbayes/model/prior.py:596-611)
 SB_DEV void weight_tables(Run &R) {
     const SbProblem &P = *R.P;
-    const int F = P.F, C = P.C, rows = P.n_pat * 2 * F;
+    const int F = P.F, C = SB_CC(P), rows = P.n_pat * 2 * F;
     const bool unitTp = R.Tp == 1.0;
     for (int i = sb_tid(); i < rows; i += sb_nthr()) {
         int f = i % F, pz = i / F, z = pz & 1, bits = P.pat_bits[pz >> 1];
@@ -829,7 +838,7 @@ SB_DEV void weight_tables(Run &R) {
 // histogram: sum_o sum_f log w~[o,f,src] = sum H * log w1.  Whole CTA; result in every thread.
 SB_DEV double source_prior_from_hist(Run &R, const int32_t *H) {
     const SbProblem &P = *R.P;
-    int n = P.n_pat * 2 * P.F * P.C;
+    int n = P.n_pat * 2 * P.F * SB_CC(P);
     double a[1] = {0.0};
     for (int i = sb_tid(); i < n; i += sb_nthr()) {
         int h = H[i];
@@ -842,8 +851,8 @@ SB_DEV double source_prior_from_hist(Run &R, const int32_t *H) {
 // scipy.stats.dirichlet._logpdf of one weight row (sbayes/util.py:49, prior.py:553-558)
 SB_DEV double weights_prior_row(const SbProblem &P, const float *Wrow, int f) {
     double t = 0.0;
-    for (int c = 0; c < P.C; c++) {
-        double a = sb_ldg(P.alpha_w + (size_t)f * P.C + c);
+    for (int c = 0; c < SB_CC(P); c++) {
+        double a = sb_ldg(P.alpha_w + (size_t)f * SB_CC(P) + c);
         if (a != 1.0) t += (a - 1.0) * log((double)Wrow[c]);
     }
     return -sb_ldg(P.wlnB + f) + t;
@@ -851,8 +860,8 @@ SB_DEV double weights_prior_row(const SbProblem &P, const float *Wrow, int f) {
 SB_DEV double weights_prior_row_reg(const SbProblem &P, const float (&Wrow)[SB_UC], int f) {
     if (P.wprior_uniform) return 0.0 - sb_ldg(P.wlnB + f);
     double t = 0.0;
-    SB_FOR_C(c, P.C) {
-        double a = sb_ldg(P.alpha_w + (size_t)f * P.C + c);
+    SB_FOR_C(c, SB_CC(P)) {
+        double a = sb_ldg(P.alpha_w + (size_t)f * SB_CC(P) + c);
         if (a != 1.0) t += (a - 1.0) * log((double)Wrow[c]);
     }
     return -sb_ldg(P.wlnB + f) + t;
@@ -861,7 +870,7 @@ SB_DEV double weights_prior_total(Run &R) {   // WeightsPrior.__call__ (prior.py
     const SbProblem &P = *R.P;
     if (P.wprior_uniform) return 0.0;
     double a[1] = {0.0};
-    for (int f = sb_tid(); f < P.F; f += sb_nthr()) a[0] += weights_prior_row(P, R.c->rp.W + (size_t)f * P.C, f);
+    for (int f = sb_tid(); f < P.F; f += sb_nthr()) a[0] += weights_prior_row(P, R.c->rp.W + (size_t)f * SB_CC(P), f);
     block_sum<1>(R, a);
     return a[0];
 }
@@ -968,7 +977,7 @@ struct Marg { Prod p0, p1; double geo; int on; };
 // tables over combos: tab[j,f,x].a = sum_{c>=1} l_c w0_c,  tab[j,f,x].b = l_0 w1_0 + sum_{c>=1} l_c w1_c.  CTA-local.
 SB_DEV void build_tables(Run &R, int k, bool wide) {
     const SbProblem &P = *R.P;
-    const int F = P.F, S = P.S, C = P.C;
+    const int F = P.F, S = P.S, C = SB_CC(P);
     const bool powT = wide && R.T != 1.0;
     for (int idx = sb_tid(); idx < P.n_combos * F; idx += sb_nthr()) {
         const int j = idx / F, f = idx % F;
@@ -1002,7 +1011,7 @@ SB_DEV void build_tables(Run &R, int k, bool wide) {
 template <bool TABLE>
 SB_DEV void obj_marginals(const Run &R, int o, int k, bool wide, Prod &p0, Prod &p1) {
     const SbProblem &P = *R.P;
-    const int F = P.F, S = P.S, C = P.C;
+    const int F = P.F, S = P.S, C = SB_CC(P);
     const uint32_t *xw = (const uint32_t *)x_row(R, o);
     const int nwords = P.ldx >> 2;
     p0 = prod_one(); p1 = prod_one();
@@ -1138,7 +1147,7 @@ SB_DEV Row16 load_row16(const uint8_t *p) {      // p is 16-byte aligned
 template <int KIND>
 SB_DEV void build_tile(Run &R, int k, int k2, int j0, int j1) {
     const SbProblem &P = *R.P;
-    const int F = P.F, S = P.S, C = P.C;
+    const int F = P.F, S = P.S, C = SB_CC(P);
     constexpr int W = KIND == TK_ALTER ? 1 : 2;
     double *tile = R.c->tile + 2;
     const bool powT = KIND == TK_WIDE && R.T != 1.0;
@@ -1206,7 +1215,7 @@ SB_DEV void chunk_products(const double *unit, const double *tc, int S, int fbas
 template <int SM>
 SB_DEV void ratio_row(const Run &R, int k, int j, int f, double (&r)[SM + 1]) {
     const SbProblem &P = *R.P;
-    const int F = P.F, S = P.S, C = P.C;
+    const int F = P.F, S = P.S, C = SB_CC(P);
 #pragma unroll
     for (int x = 0; x <= SM; x++) r[x] = 1.0;
     if (f >= F) return;
@@ -1403,7 +1412,7 @@ SB_DEV double posterior_tail(const Run &R, const Marg &a, bool flat, bool use_ge
 // (E_conf + w_0 p_src) and (E_conf + w_0 p_tgt) over the features, tempered tables throughout
 SB_DEV void jump_marginals(const Run &R, int o, int k_src, int k_tgt, Prod &ps, Prod &pj) {
     const SbProblem &P = *R.P;
-    const int F = P.F, C = P.C;
+    const int F = P.F, C = SB_CC(P);
     int gC[SB_UC];
     SB_FOR_C1(c, C) gC[c] = conf_group(R, c, o);
     const int pat = m_pat(R, o);
@@ -1459,7 +1468,7 @@ SB_DEV void mark_object(Run &R, int o) {
     int a = m_cl(R, o), b = cl_of(R, o, 1);
     if (a >= 0) R.c->rp.dirty[a] = 1;
     if (b >= 0) R.c->rp.dirty[b] = 1;
-    for (int c = 1; c < P.C; c++) { int g = conf_group(R, c, o); if (g >= 0) R.c->rp.dirty[g] = 1; }
+    for (int c = 1; c < SB_CC(P); c++) { int g = conf_group(R, c, o); if (g >= 0) R.c->rp.dirty[g] = 1; }
 }
 // group row an observation of object o assigned to component c counts towards
 SB_DEV int obs_group(const Run &R, int o, int c, int view) {
@@ -1476,7 +1485,7 @@ SB_DEV void count_add(Run &R, int g, int f, int x, int d) {
 // Ends with a barrier.  Returns the candidate histogram.
 SB_DEV int32_t *proposal_open(Run &R, int M, const int *S) {
     const SbProblem &P = *R.P;
-    const int nH = P.n_pat * 2 * P.F * P.C, F = P.F;
+    const int nH = P.n_pat * 2 * P.F * SB_CC(P), F = P.F;
     const int32_t *h = R.c->rp.H[R.hcur];
     int32_t *hc = R.c->rp.H[R.hcur ^ 1];
     for (int i = sb_tid(); i < nH; i += sb_nthr()) hc[i] = h[i];
@@ -1620,7 +1629,7 @@ SB_DEV double pick_c(const double (&q)[SB_UC], int C, int i) {     // q[i] witho
 // candidate rows, the candidate histogram and pr.sp_new / pr.geo_new.
 SB_DEV void resample_sources(Run &R, Prop &pr, int M, const int *S, int k_new, int k_old, bool jump, double &lq, double &lqb) {
     const SbProblem &P = *R.P;
-    const int F = P.F, C = P.C;
+    const int F = P.F, C = SB_CC(P);
     const long long items = (long long)M * F;
     PH(R, 5);
     int32_t *Hc = proposal_open(R, M, S);
@@ -2104,7 +2113,7 @@ SB_DEV Prop op_cluster_jump(Run &R) {
 // calculate_source_posterior (operators.py:554-574) of object o at feature f -> q[c] (normalised)
 SB_DEV void source_posterior(const Run &R, int o, int f, int x, int k_o, int pat, int z, double (&q)[SB_UC]) {
     const SbProblem &P = *R.P;
-    const int C = P.C;
+    const int C = SB_CC(P);
     const double *w = R.c->rp.wp + ((size_t)(pat * 2 + z) * P.F + f) * C;
     const bool unitT = R.T == 1.0;
     double tot = 0.0;
@@ -2121,7 +2130,7 @@ SB_DEV void source_posterior(const Run &R, int o, int f, int x, int k_o, int pat
 
 SB_DEV Prop op_gibbs_source(Run &R, bool groups_mode) {
     const SbProblem &P = *R.P;
-    const int N = P.N, F = P.F, C = P.C;
+    const int N = P.N, F = P.F, C = SB_CC(P);
     Prop pr = prop_init(1, 0.0, 0.0);
     // --- select_object_subset (operators.py:461-494) -> S[0..M)
     int M = 0;
@@ -2267,7 +2276,7 @@ SB_DEV double beta_logpdf_nolnB(double x, double a, double b) {   // scipy beta.
 }
 SB_DEV Prop op_gibbs_weights(Run &R) {
     const SbProblem &P = *R.P;
-    const int F = P.F, C = P.C;
+    const int F = P.F, C = SB_CC(P);
     Prop pr = prop_init(1, -SB_INF, 0.0);
     int i1, i2;
     draw_pair(R.D, SITE_WPAIR, C, i1, i2);
@@ -2336,7 +2345,7 @@ SB_DEV Prop op_gibbs_weights(Run &R) {
 // -----------------------------------------------------------------------------------------
 SB_DEV void rebuild_state(Run &R) {
     const SbProblem &P = *R.P;
-    const int N = P.N, F = P.F, S = P.S, C = P.C;
+    const int N = P.N, F = P.F, S = P.S, C = SB_CC(P);
     const size_t nG = (size_t)P.G_tot * F * S;
     const int nH = P.n_pat * 2 * F * C;
     // where the bins are accumulated and where the replicas are filled from: the chain's statistics block
@@ -2528,7 +2537,7 @@ SB_DEV void mcmc_step(Run &R, sb_step_record *rec) {
 SB_DEV void setup_replica(Run &R, const SbLaunch &L, char *smem, char *glob) {
     const SbProblem &P = L.P;
     const SbPlace &pl = L.place;
-    FixedSmem fx = sb_fixed_smem(P.G_tot, P.K, P.F, P.C, L.smem_members, pl.fixed_off);
+    FixedSmem fx = sb_fixed_smem(P.G_tot, P.K, P.F, SB_CC(P), L.smem_members, pl.fixed_off);
     RunC *c = (RunC *)(smem + fx.runc);
     R.c = c;
     int lo, hi; team_range(R, P.N, lo, hi);
@@ -2660,7 +2669,7 @@ SB_KERNEL_BIG sb_run_kernel(const SB_GRID_CONSTANT SbLaunch L) {
             // export copies of the replica for the host
             const size_t nG = (size_t)L.P.G_tot * L.P.F * L.P.S;
             for (size_t i = sb_tid(); i < nG; i += sb_nthr()) R.c->st.counts[i] = R.c->rp.counts[i];
-            for (int i = sb_tid(); i < L.P.F * L.P.C; i += sb_nthr()) R.c->st.W[i] = R.c->rp.W[i];
+            for (int i = sb_tid(); i < L.P.F * SB_CC(L.P); i += sb_nthr()) R.c->st.W[i] = R.c->rp.W[i];
             for (int g = sb_tid(); g < L.P.G_tot; g += sb_nthr()) R.c->st.glh[g] = R.sfp ? 0.0 : R.c->rp.lh[g];
             for (int k = sb_tid(); k < L.P.K; k += sb_nthr()) R.c->st.geo_out[k] = L.P.geo ? R.c->rp.geo_val[k] : 0.0;
             if (sb_tid() == 0) {
@@ -2680,7 +2689,7 @@ SB_KERNEL_BIG sb_run_kernel(const SB_GRID_CONSTANT SbLaunch L) {
 // sum_f log w~[o, f, src[o,f]] with w~ = has * W / sum(has * W), normalize_weights likelihood.py:171-190).
 // grid = (blocks, n); one warp per object for the rows.
 SB_KERNEL sb_export_samples_kernel(SbProblem P, const SbShared *states, SbExport E) {
-    const int N = P.N, F = P.F, C = P.C;
+    const int N = P.N, F = P.F, C = SB_CC(P);
 #ifdef SB_HOSTSIM
     const int j = sb_cta() % E.n, blk = sb_cta() / E.n, nblk = sb_ncta() / E.n;
 #else

@@ -17,7 +17,7 @@ def build(force: bool = False) -> str:
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     cmd = ["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-DSB_HOSTSIM", "-x", "c++",
            "-I" + os.path.join(ROOT, "tests", "hostsim"), "-I" + os.path.join(ROOT, "include"),
-           os.path.join(SRC, "sb_api.cu"), os.path.join(SRC, "sb_uc8.cu"), os.path.join(SRC, "sb_api_eval.cu"), "-o", OUT]
+           os.path.join(SRC, "sb_api.cu"), os.path.join(SRC, "sb_uc8.cu"), os.path.join(SRC, "sb_uc3.cu"), os.path.join(SRC, "sb_api_eval.cu"), "-o", OUT]
     subprocess.run(cmd, check=True)
     return OUT
 
